@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- train interactions/s of the BPRMF hot path (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py --gpus 1 --steps 200 --warmup 10          # this repository's sm_100a path
+    python bench.py --impl reference --steps 20 --warmup 3    # the reference's CPU path (oracle port) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, NCCL
+
+Workload (config.workload): BPRMF, embedding 64, batch 2048, Adam lr=1e-3 l2=1e-6 on the ml-1m-SHAPED synthetic
+corpus (6,040 users x 3,706 items, 836k interactions after the reader's rating filter, 668,862 train rows):
+`ml-1m.inter` is missing from the reference checkout and there is no network.
+A step = one mini-batch through the whole training path: gather + BPR loss + backward scatter (wr_bpr_fwd_bwd)
+and the dense Adam+L2 sweep over every table row (wr_adam_l2_sweep).
+
+value    : interactions/s with the epoch's batches already resident in HBM, device-timed (CUDA events around every
+           step, L2 flushed between steps by writing a 512 MB buffer, outside the events).
+e2e      : the same through the reference-facing API (model.predict / optimizer.step) with HOST batches: per
+           step a pinned H2D copy of the three id vectors and a D2H read of the loss, host-timed, same L2 flush.
+roofline : the Adam sweep (the dominant kernel: 32 B per parameter per step) against the measured HBM copy peak.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, D, LR, L2 = 2048, 64, 1e-3, 1e-6
+CACHE = os.environ.get('WR_CACHE', '/tmp/wr_cache')
+WORKLOAD = 'BPRMF emb=64 B=2048 Adam(lr=1e-3,l2=1e-6) on ml-1m-shaped synthetic (6040 users x 3706 items, 668862 train rows)'
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return p['hbm_gbs'], p.get('bf16_tflops_sustained', 1387.5), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.rows.extend(self.proc.stdout.readlines()), daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.rows:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_model(corpus, dev, cls_name='BPRMF', **over):
+    from whisprrec_b200.main import default_args as model_args
+    from whisprrec_b200.models.general.BPRMF import BPRMF
+    from whisprrec_b200.models.general.LightGCN import LightGCN
+    from whisprrec_b200.helpers.BaseRunner import BaseRunner
+    from whisprrec_b200.utils import utils
+    cls = {'BPRMF': BPRMF, 'LightGCN': LightGCN}[cls_name]
+    args = model_args(cls, lr=LR, l2=L2, batch_size=B, embedding_size=D, **over)
+    utils.init_seed(3407)
+    model = cls(args, corpus).to(dev)
+    model.fuse()
+    runner = BaseRunner(args)
+    model.optimizer = runner._build_optimizer(model)
+    data = {ph: cls.Dataset(model, corpus, ph) for ph in ('train', 'dev')}
+    return model, runner, data
+
+
+def algorithmic_bytes_adam(n_rows, d):
+    return 32 * d * n_rows            # read p, m, v, g; write p, m, v, g=0
+
+
+def algorithmic_bytes_bpr(b, d):
+    return 24 * b * d + 24 * b        # 3 gathered rows + 3 gradient rows of 4D bytes, 3 int64 ids
+
+
+def run_ours(a, rank, world, local_rank):
+    from whisprrec_b200.utils import synthetic
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    hbm_peak, _, peak_src = peaks()
+    corpus = synthetic.ml1m_shaped_corpus(cache_dir=os.path.join(CACHE, 'r%d' % rank))
+    model, runner, data = make_model(corpus, dev)
+    t = model.tables
+    n_rows = t.P.shape[0]
+    batches = runner.epoch_batches(data['train'])              # [3, n_train] int64, resident
+    n_train = batches.shape[1]
+    steps_per_epoch = n_train // B                             # full batches only inside the timed region
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    losses = torch.zeros(a.warmup + a.steps, device=dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+
+    def step(s, events=None):
+        lo = (s % steps_per_epoch) * B
+        batch = {'user_id': batches[0, lo:lo + B], 'pos_item': batches[1, lo:lo + B], 'neg_items': batches[2, lo:lo + B]}
+        if events: events[0].record()
+        model.predict(batch, loss_out=losses[s:s + 1])
+        if events: events[1].record()
+        model.optimizer.step()
+        if events: events[2].record()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for s in range(a.warmup):
+        flush.zero_()
+        step(s)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        wall0 = time.perf_counter()
+        for s in range(a.steps):
+            flush.zero_()                                      # L2 flush, outside the per-step events
+            step(a.warmup + s, ev[s])
+        barrier()
+        wall = time.perf_counter() - wall0
+        if wall < 1.5:                                         # keep the sampler alive long enough to see clocks
+            t_end = time.perf_counter() + 1.5 - wall
+            while time.perf_counter() < t_end:
+                flush.zero_(); step(0)
+            torch.cuda.synchronize()
+    clocks = clk.summary()
+    bpr_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    adam_ms = np.array([e[1].elapsed_time(e[2]) for e in ev])
+    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    t.ws.raise_on_status()
+    assert np.isfinite(losses.cpu().numpy()).all()
+    value = world * a.steps * B / (total_ms * 1e-3)
+
+    # ---- e2e: host batches -> pinned H2D -> predict -> step -> loss D2H, every step ----
+    host_batches = batches.cpu()
+    pinned = torch.empty((steps_per_epoch, 3, B), dtype=torch.int64).pin_memory()
+    for s in range(steps_per_epoch):
+        pinned[s].copy_(host_batches[:, s * B:(s + 1) * B])
+    stage = torch.empty((3, B), dtype=torch.int64, device=dev)
+    e2e_s = 0.0
+    for s in range(a.warmup + a.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stage.copy_(pinned[s % steps_per_epoch], non_blocking=True)
+        loss = model.predict({'user_id': stage[0], 'pos_item': stage[1], 'neg_items': stage[2]})
+        loss.backward()
+        model.optimizer.step()
+        loss_host = float(loss.cpu())
+        if s >= a.warmup:
+            e2e_s += time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    assert np.isfinite(loss_host)
+    e2e_value = world * a.steps * B / e2e_s
+
+    adam_bytes = algorithmic_bytes_adam(n_rows, D)
+    adam_avg_s = float(adam_ms.mean()) * 1e-3
+    achieved = adam_bytes / adam_avg_s / 1e9
+    line = {
+        'metric': 'train_interactions_per_s', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': total_ms / a.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'embedding_size': D, 'table_rows': int(n_rows),
+                   'l2_flush': '512 MB written between timed steps (tables are 10 MB, L2-resident otherwise)',
+                   'parallelism': 'single GPU' if world == 1 else 'replicas x%d' % world},
+        'e2e': {'value': e2e_value, 'unit': 'interactions/s', 'h2d_bytes_per_step': 3 * B * 8,
+                'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / a.steps * 1e3},
+        'gpu_launches': 2 * a.steps,
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'kernel': 'adam_sweep_kernel', 'achieved': achieved, 'peak': hbm_peak,
+                     'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                     'bytes_per_launch': adam_bytes, 'avg_launch_us': adam_avg_s * 1e6,
+                     'step_bytes': adam_bytes + algorithmic_bytes_bpr(B, D),
+                     'step_frac': (adam_bytes + algorithmic_bytes_bpr(B, D)) / (total_ms / a.steps * 1e-3) / 1e9 / hbm_peak},
+        'kernels_ms': {'bpr_fwd_bwd': float(bpr_ms.mean()), 'adam_l2_sweep': float(adam_ms.mean()),
+                       'step_median': float(np.median(step_ms))},
+    }
+    if rank == 0 and world == 1:
+        line['cpu_baseline'] = cpu_baseline(corpus, budget_s=a.cpu_budget)
+        if not a.no_extras:
+            line['extra'] = extras(corpus, dev, model, runner, data, hbm_peak)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_problem(corpus):
+    """The same workload for the CPU arm: reference-initialised tables and one epoch of reference-ordered batches."""
+    from whisprrec_b200.main import default_args as model_args
+    from whisprrec_b200.models.general.BPRMF import BPRMF
+    from whisprrec_b200.helpers.BaseRunner import dataloader_draws
+    from whisprrec_b200.utils import utils
+    args = model_args(BPRMF, lr=LR, l2=L2, batch_size=B, embedding_size=D)
+    args.device = torch.device('cpu')
+    utils.init_seed(3407)
+    model = BPRMF(args, corpus)
+    ds = BPRMF.Dataset(model, corpus, 'train')
+    ds.actions_before_epoch()
+    perm = dataloader_draws(len(ds), shuffle=True)
+    cols = [np.asarray(ds.data[k], dtype=np.int64)[perm] for k in ('user_id', 'item_id', 'neg_items')]
+    return model.user_embeddings.weight.detach().clone(), model.item_embeddings.weight.detach().clone(), cols
+
+
+def cpu_steps(U, I, cols, n_steps, start=0):
+    """n_steps of the oracle's restatement of predict -> backward -> Adam.step (reference BaseRunner.py:196-199)."""
+    from oracle import whispr_oracle as O
+    st = getattr(cpu_steps, 'state', None)
+    if st is None or st[0] is not U:
+        st = cpu_steps.state = (U, [torch.zeros_like(U), torch.zeros_like(U), torch.zeros_like(I), torch.zeros_like(I)], [0])
+    mU, vU, mI, vI = st[1]
+    spe = len(cols[0]) // B
+    t0 = time.perf_counter()
+    for s in range(start, start + n_steps):
+        lo = (s % spe) * B
+        loss, gU, gI = O.bpr_fwd_bwd(U, I, cols[0][lo:lo + B], cols[1][lo:lo + B], cols[2][lo:lo + B])
+        st[2][0] += 1
+        O.adam_l2_step(U, mU, vU, gU, st[2][0], LR, L2)
+        O.adam_l2_step(I, mI, vI, gI, st[2][0], LR, L2)
+    return time.perf_counter() - t0, float(loss)
+
+
+def cpu_baseline(corpus, budget_s=12.0):
+    U, I, cols = cpu_problem(corpus)
+    t3, _ = cpu_steps(U, I, cols, 3)
+    n = int(max(5, min(3000, budget_s / max(t3 / 3, 1e-6))))
+    dt, loss = cpu_steps(U, I, cols, n, start=3)
+    return {'value': n * B / dt, 'unit': 'interactions/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d steps of B=%d of the same workload through oracle/whispr_oracle.py (torch CPU ops, '
+                      'model-only: batches pre-assembled); host has %d logical cores' % (n, B, os.cpu_count())}
+
+
+def run_reference(a, rank):
+    """The reference arm: the reference's CPU implementation of the path.  The reference is pure Python on top of
+    torch and cannot travel to the GPU box, so this is the oracle port of it, on all host threads."""
+    if rank != 0:
+        return
+    from whisprrec_b200.utils import synthetic
+    corpus = synthetic.ml1m_shaped_corpus(cache_dir=os.path.join(CACHE, 'ref'))
+    U, I, cols = cpu_problem(corpus)
+    per_step = 100                                            # a "step" of this arm = a bounded sample of 100 batches
+    cpu_steps(U, I, cols, a.warmup * 5)
+    dt = 0.0
+    for k in range(a.steps):
+        d, loss = cpu_steps(U, I, cols, per_step, start=a.warmup * 5 + k * per_step)
+        dt += d
+    value = a.steps * per_step * B / dt
+    sample = '%d batches of B=%d per step, model-only (batches pre-assembled), oracle port of the reference' % (per_step, B)
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'train_interactions_per_s', 'value': value, 'unit': 'interactions/s',
+        'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dt / a.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'embedding_size': D},
+        'cpu_baseline': {'value': value, 'unit': 'interactions/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': 'interactions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# secondary measurements (reported under "extra"; never replace the contract fields)
+# ---------------------------------------------------------------------------------------------------------------
+
+def timed(fn, reps, flush=None):
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.median(ms)), float(np.mean(ms))
+
+
+def extras(corpus, dev, model, runner, data, hbm_peak):
+    from whisprrec_b200 import _lib
+    out = {}
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    try:    # full-ranking eval of the dev split, fp32-exact kernel
+        (user, pos), (hptr, hidx) = runner._eval_inputs(data['dev'])
+        ue, ie = model.eval_tables()
+        fn = lambda: _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws)
+        fn(); torch.cuda.synchronize()
+        med, _ = timed(fn, 10, flush)
+        R, nI = user.numel(), ie.shape[0]
+        out['eval_fp32'] = {'users_per_s': R / (med * 1e-3), 'rows': R, 'items': nI, 'ms': med,
+                            'tflops': 2.0 * R * nI * D / (med * 1e-3) / 1e12}
+        fn = lambda: _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, k=10)
+        fn(); torch.cuda.synchronize()
+        med, _ = timed(fn, 5, flush)
+        out['eval_fp32_top10'] = {'users_per_s': R / (med * 1e-3), 'ms': med}
+    except Exception as e:  # noqa: BLE001
+        out['eval_fp32'] = {'error': repr(e)}
+    try:    # LightGCN L=2 on the same graph (BASELINE.json configs[2])
+        lg, lrun, ldata = make_model(corpus, dev, 'LightGCN', gcn_layers=2)
+        batches = lrun.epoch_batches(ldata['train'])
+        def lstep(s=[0]):
+            lo = (s[0] % (batches.shape[1] // B)) * B; s[0] += 1
+            lg.predict({'user_id': batches[0, lo:lo + B], 'pos_item': batches[1, lo:lo + B], 'neg_items': batches[2, lo:lo + B]})
+            lg.optimizer.step()
+        for _ in range(5): lstep()
+        med, mean = timed(lstep, 30, flush)
+        N, nnz = lg.tables.P.shape[0], lg.adj_col.numel()
+        Pb = nnz * (4 + 4 + 4 * D) + N * (4 + 4 * D)
+        step_bytes = 4 * Pb + 2 * 4 * N * 4 * D + 32 * D * N + 48 * B * D + 12 * B
+        spmm = lambda: _lib.csr_spmm(lg.adj_rowptr, lg.adj_col, lg.adj_val, lg.tables.P, Y=lg.layer[0])
+        smed, _ = timed(spmm, 20, flush)
+        out['lightgcn_L2'] = {'interactions_per_s': B / (med * 1e-3), 'ms_per_step': med, 'nodes': N, 'nnz': nnz,
+                              'algorithmic_step_gbs': step_bytes / (med * 1e-3) / 1e9,
+                              'spmm_ms': smed, 'spmm_algorithmic_gbs': Pb / (smed * 1e-3) / 1e9,
+                              'spmm_frac_of_hbm_peak': Pb / (smed * 1e-3) / 1e9 / hbm_peak,
+                              'note': 'no-reuse byte model; the 2.5 MB table is cache-resident, so > 1.0 is possible'}
+        del lg, batches
+    except Exception as e:  # noqa: BLE001
+        out['lightgcn_L2'] = {'error': repr(e)}
+    try:    # the same two training kernels where HBM really is the bound: 10M users x 2M items, D=128
+        nU, nI, d, b = 10_000_000, 2_000_000, 128, 65536
+        P = torch.empty((nU + nI, d), device=dev).normal_(0, 0.01)
+        M, V, G = torch.zeros_like(P), torch.zeros_like(P), torch.zeros_like(P)
+        ws, loss = _lib.Workspace(dev), torch.zeros(1, device=dev)
+        u = torch.randint(0, nU, (b,), device=dev); p = torch.randint(0, nI, (b,), device=dev); n = torch.randint(1, nI, (b,), device=dev)
+        k = [0]
+        def big():
+            k[0] += 1
+            _lib.bpr_fwd_bwd(P[:nU], P[nU:], u, p, n, G[:nU], G[nU:], loss, ws)
+            _lib.adam_l2_sweep(P, M, V, G, k[0], LR, L2)
+        adam = lambda: _lib.adam_l2_sweep(P, M, V, G, 1, LR, L2)
+        bpr = lambda: _lib.bpr_fwd_bwd(P[:nU], P[nU:], u, p, n, G[:nU], G[nU:], loss, ws)
+        big(); torch.cuda.synchronize()
+        med, _ = timed(big, 5)
+        amed, _ = timed(adam, 5)
+        bmed, _ = timed(bpr, 5)
+        ab = algorithmic_bytes_adam(nU + nI, d)
+        out['bprmf_10Mx2M_d128_b65536'] = {
+            'interactions_per_s': b / (med * 1e-3), 'ms_per_step': med, 'adam_ms': amed, 'bpr_ms': bmed,
+            'adam_gbs': ab / (amed * 1e-3) / 1e9, 'adam_frac_of_hbm_peak': ab / (amed * 1e-3) / 1e9 / hbm_peak,
+            'bpr_gbs': algorithmic_bytes_bpr(b, d) / (bmed * 1e-3) / 1e9,
+            'step_frac_of_hbm_peak': (ab + algorithmic_bytes_bpr(b, d)) / (med * 1e-3) / 1e9 / hbm_peak,
+            'note': 'tables 24.6 GB >> L2; dense Adam makes the sweep the whole step'}
+        del P, M, V, G
+    except Exception as e:  # noqa: BLE001
+        out['bprmf_10Mx2M_d128_b65536'] = {'error': repr(e)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', type=str, default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-budget', type=float, default=12.0, dest='cpu_budget')
+    ap.add_argument('--no-extras', action='store_true', dest='no_extras')
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    import logging
+    logging.disable(logging.INFO)
+    if a.impl == 'reference':
+        run_reference(a, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device for the sm_100a arm (there is no CPU fallback); '
+                         'use --impl reference for the CPU arm')
+    run_ours(a, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

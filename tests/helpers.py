@@ -43,3 +43,28 @@ def clicked_sets(n_users, pairs):
     for u, i in pairs:
         s[int(u)].add(int(i))
     return s
+
+
+# ---- corpora / args for the host-side mirror ----------------------------------------------------------
+
+def frames_corpus(train, dev, test, n_users=None, n_items=None):
+    """BaseReader built from (user, item) pair arrays."""
+    import pandas as pd
+    from whisprrec_b200.helpers.BaseReader import BaseReader
+    frames = []
+    for pairs in (train, dev, test):
+        pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+        frames.append(pd.DataFrame({'user_id': pairs[:, 0], 'item_id': pairs[:, 1],
+                                    'timestamp': np.zeros(len(pairs), dtype=np.int64)}))
+    return BaseReader.from_frames(*frames, n_users=n_users, n_items=n_items)
+
+
+def ml100k_corpus():
+    c = load('ml100k_corpus.npz')
+    parts = [np.stack([c[ph + '_user'], c[ph + '_item']], 1) for ph in ('train', 'dev', 'test')]
+    return frames_corpus(*parts)
+
+
+def model_args(cls, **over):
+    from whisprrec_b200 import main as wr_main
+    return wr_main.default_args(cls, **over)

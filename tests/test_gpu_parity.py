@@ -1,0 +1,454 @@
+"""Parity of the sm_100a path against the CPU oracle and the reference's golden outputs.  Needs a B200.
+
+Every kernel is reached through the C-ABI (ctypes) -- directly via whisprrec_b200._lib or through the
+host-side mirror of the reference's model / runner classes.
+Tolerance (tests/helpers.py): |a-b| <= 1e-5 |b| + 1e-6 max|b| for fp32 values; integer results bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import whispr_oracle as O
+from tests.helpers import assert_close, frames_corpus, load, ml100k_corpus, model_args, small_case
+from whisprrec_b200 import _lib
+from whisprrec_b200.helpers.BaseRunner import BaseRunner
+from whisprrec_b200.models.general.BPRMF import BPRMF
+from whisprrec_b200.models.general.LightGCN import LightGCN
+from whisprrec_b200.utils import utils
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+SMALL = ['bprmf_d16', 'bprmf_d64', 'lgcn_d16_l2', 'lgcn_d64_l3']
+
+
+def dv(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope='module')
+def ws():
+    return _lib.Workspace(DEV)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# training kernels
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('tag', SMALL[:2])
+def test_bprmf_steps_match_reference_golden(tag, ws):
+    """Three reference optimiser steps (duplicate-heavy batches, ragged last batch) replayed on the device."""
+    s = small_case(load('small_cases.npz'), tag)
+    lr, l2 = float(s['hp'][0]), float(s['hp'][1])
+    nU = s['U0'].shape[0]
+    P = dv(np.concatenate([s['U0'], s['I0']]))
+    M, V, G = torch.zeros_like(P), torch.zeros_like(P), torch.zeros_like(P)
+    loss = torch.zeros(1, device=DEV)
+    for step in range(3):
+        user, pos, neg = (dv(s[f's{step}/{k}'], torch.int64) for k in ('user', 'pos', 'neg'))
+        _lib.bpr_fwd_bwd(P[:nU], P[nU:], user, pos, neg, G[:nU], G[nU:], loss, ws)
+        assert_close(host(loss)[0], s[f's{step}/loss'], f'{tag} loss step {step}')
+        assert_close(host(G[:nU]), s[f's{step}/gU'], f'{tag} gU step {step}')
+        assert_close(host(G[nU:]), s[f's{step}/gI'], f'{tag} gI step {step}')
+        _lib.adam_l2_sweep(P, M, V, G, step + 1, lr, l2)
+        assert float(G.abs().max()) == 0.0                   # the sweep hands back a zeroed gradient table
+        assert_close(host(P[:nU]), s[f's{step}/U'], f'{tag} U step {step}')
+        assert_close(host(P[nU:]), s[f's{step}/I'], f'{tag} I step {step}')
+    assert_close(host(M[:nU]), s['mU'], f'{tag} exp_avg')
+    assert_close(host(V[:nU]), s['vU'], f'{tag} exp_avg_sq')
+    assert ws.status() == 0
+
+
+@pytest.mark.parametrize('D', [16, 32, 64, 128, 256, 48, 8])
+@pytest.mark.parametrize('B', [1, 31, 480, 2048])
+def test_bpr_fwd_bwd_vs_oracle(D, B, ws):
+    rng = np.random.RandomState(D * 7 + B)
+    nU, nI = 37, 53
+    U = (rng.randn(nU, D) * 0.3).astype(np.float32)
+    I = (rng.randn(nI, D) * 0.3).astype(np.float32)
+    user = (nU * rng.rand(B) ** 2).astype(np.int64)          # skewed: many duplicates
+    pos = (nI * rng.rand(B) ** 1.5).astype(np.int64)
+    neg = rng.randint(1, nI, size=B).astype(np.int64)
+    o_loss, o_gU, o_gI = O.bpr_fwd_bwd(U, I, user, pos, neg)
+    dU, dI = dv(U), dv(I)
+    gU, gI, loss = torch.zeros_like(dU), torch.zeros_like(dI), torch.zeros(1, device=DEV)
+    _lib.bpr_fwd_bwd(dU, dI, dv(user), dv(pos), dv(neg), gU, gI, loss, ws)
+    assert_close(host(loss)[0], o_loss.item(), 'loss')
+    assert_close(host(gU), o_gU.numpy(), 'gU')
+    assert_close(host(gI), o_gI.numpy(), 'gI')
+    # grad_scale and loss accumulation (the LightGCN call shape)
+    gU.zero_(); gI.zero_()
+    _lib.bpr_fwd_bwd(dU, dI, dv(user), dv(pos), dv(neg), gU, gI, loss, ws, grad_scale=0.25, accumulate_loss=True)
+    assert_close(host(loss)[0], 2 * o_loss.item(), 'accumulated loss')
+    assert_close(host(gU), 0.25 * o_gU.numpy(), 'scaled gU')
+
+
+def test_bpr_all_rows_identical_and_extreme_scores(ws):
+    """Every interaction hits the same three rows (maximal atomic contention); saturated sigmoids stay finite."""
+    D, B = 64, 4096
+    U = np.full((4, D), 0.5, dtype=np.float32)
+    I = np.zeros((5, D), dtype=np.float32)
+    I[1], I[2] = 3.0, -3.0                                    # s+ - s- = +-192: sigmoid saturates
+    for pos_id, neg_id in ((1, 2), (2, 1)):
+        user = np.full(B, 3, dtype=np.int64)
+        pos, neg = np.full(B, pos_id, dtype=np.int64), np.full(B, neg_id, dtype=np.int64)
+        o_loss, o_gU, o_gI = O.bpr_fwd_bwd(U, I, user, pos, neg)
+        gU, gI, loss = torch.zeros(4, D, device=DEV), torch.zeros(5, D, device=DEV), torch.zeros(1, device=DEV)
+        _lib.bpr_fwd_bwd(dv(U), dv(I), dv(user), dv(pos), dv(neg), gU, gI, loss, ws)
+        assert np.isfinite(host(loss)).all()
+        assert_close(host(loss)[0], o_loss.item(), 'loss', rtol=1e-5)
+        assert_close(host(gU), o_gU.numpy(), 'gU', rtol=1e-4, atol_scale=1e-5)   # 4096-term sums, order differs
+        assert_close(host(gI), o_gI.numpy(), 'gI', rtol=1e-4, atol_scale=1e-5)
+
+
+def test_out_of_range_index_raises_like_embedding(ws):
+    D = 64
+    U, I = torch.randn(10, D, device=DEV), torch.randn(12, D, device=DEV)
+    gU, gI, loss = torch.zeros_like(U), torch.zeros_like(I), torch.zeros(1, device=DEV)
+    user = dv(np.array([1, 2, 10], dtype=np.int64))          # 10 is out of range
+    pos, neg = dv(np.array([0, 1, 2], dtype=np.int64)), dv(np.array([3, 4, 5], dtype=np.int64))
+    _lib.bpr_fwd_bwd(U, I, user, pos, neg, gU, gI, loss, ws)
+    with pytest.raises(IndexError):
+        ws.raise_on_status()
+    assert ws.status() == 0                                   # read-and-clear
+    assert float(gU[3:].abs().max()) == 0.0 and float(gU[1].abs().max()) > 0.0
+
+
+@pytest.mark.parametrize('n', [4, 1003, 64 * 1000, 1 << 20])
+def test_adam_l2_sweep_vs_oracle(n):
+    rng = np.random.RandomState(n % 1000)
+    p0 = rng.randn(n).astype(np.float32) * 0.1
+    P, M, V = dv(p0), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    op, om, ov = torch.from_numpy(p0.copy()), torch.zeros(n), torch.zeros(n)
+    for step in range(1, 5):
+        g = (rng.randn(n) * (rng.rand(n) < 0.3)).astype(np.float32) * 1e-2      # mostly-zero dense gradient
+        G = dv(g)
+        _lib.adam_l2_sweep(P, M, V, G, step, 1e-3, 1e-4)
+        O.adam_l2_step(op, om, ov, torch.from_numpy(g), step, 1e-3, 1e-4)
+        assert float(G.abs().max()) == 0.0
+        assert_close(host(P), op.numpy(), f'p step {step}')
+        assert_close(host(M), om.numpy(), f'm step {step}')
+        assert_close(host(V), ov.numpy(), f'v step {step}')
+    # device-resident scalars (CUDA-graph replay form) give the same bits as by-value scalars
+    P2, M2, V2 = P.clone(), M.clone(), V.clone()
+    g = dv((rng.randn(n) * 1e-2).astype(np.float32))
+    g2 = g.clone()
+    _lib.adam_l2_sweep(P, M, V, g, 5, 1e-3, 1e-4)
+    ss, bc = _lib.adam_scalars(5, 1e-3)
+    _lib.adam_l2_sweep(P2, M2, V2, g2, 1, 7.0, 1e-4, dev_scalars=dv(np.array([ss, bc], dtype=np.float32)))
+    assert torch.equal(P, P2) and torch.equal(M, M2) and torch.equal(V, V2)
+
+
+def test_adam_zero_gradient_no_decay_is_identity():
+    P = torch.randn(1000, 64, device=DEV)
+    P0 = P.clone()
+    M, V, G = torch.zeros_like(P), torch.zeros_like(P), torch.zeros_like(P)
+    _lib.adam_l2_sweep(P, M, V, G, 1, 1e-3, 0.0)
+    assert torch.equal(P, P0) and float(M.abs().max()) == 0 and float(V.abs().max()) == 0
+
+
+def test_gather_and_scatter_add_rows(ws):
+    rng = np.random.RandomState(3)
+    T = rng.randn(100, 64).astype(np.float32)
+    idx = rng.randint(0, 100, size=777).astype(np.int64)
+    out = _lib.gather_rows(dv(T), dv(idx), ws)
+    assert (host(out) == T[idx]).all()
+    rows = rng.randn(777, 64).astype(np.float32)
+    G = torch.zeros(100, 64, device=DEV)
+    _lib.scatter_add_rows(G, dv(idx), dv(rows), ws)
+    ref = torch.zeros(100, 64).index_add_(0, torch.from_numpy(idx), torch.from_numpy(rows))
+    assert_close(host(G), ref.numpy(), 'scatter_add')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LightGCN propagation
+# ---------------------------------------------------------------------------------------------------------
+
+def random_csr(rng, N, avg_deg, heavy=0):
+    deg = rng.poisson(avg_deg, size=N)
+    deg[rng.rand(N) < 0.1] = 0                                # isolated nodes
+    if heavy:
+        deg[rng.randint(0, N, size=3)] = heavy                # a few very long rows
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = rng.randint(0, N, size=rowptr[-1]).astype(np.int32)
+    val = rng.rand(rowptr[-1]).astype(np.float32)
+    return rowptr, col, val
+
+
+@pytest.mark.parametrize('D', [16, 32, 64, 128, 256, 24])
+def test_csr_spmm_vs_oracle(D):
+    rng = np.random.RandomState(D)
+    N = 700
+    rowptr, col, val = random_csr(rng, N, 9, heavy=1500)
+    X = rng.randn(N, D).astype(np.float32)
+    A = O.csr_to_torch(rowptr, col, val, N)
+    ref = torch.sparse.mm(A, torch.from_numpy(X)).numpy()
+    d = [dv(rowptr), dv(col), dv(val)]
+    Y = torch.empty(N, D, device=DEV)
+    _lib.csr_spmm(*d, dv(X), Y=Y)
+    assert_close(host(Y), ref, 'Y = A X', rtol=1e-5, atol_scale=2e-6)
+    # fused epilogues: addend (+ recycle), running layer sum with the final division
+    add = rng.randn(N, D).astype(np.float32)
+    acc = rng.randn(N, D).astype(np.float32)
+    dadd, dacc = dv(add), dv(acc)
+    pool = torch.empty(N, D, device=DEV)
+    _lib.csr_spmm(*d, dv(X), Y=Y, add=dadd, zero_add=True, acc_in=dacc, acc_out=pool, acc_div=3.0)
+    assert_close(host(Y), ref + add, 'Y = A X + add', rtol=1e-5, atol_scale=2e-6)
+    assert_close(host(pool), (acc + ref + add) / np.float32(3.0), 'pool', rtol=1e-5, atol_scale=2e-6)
+    assert float(dadd.abs().max()) == 0.0
+    _lib.csr_spmm(*d, dv(X), acc_in=dacc, acc_out=dacc, acc_div=1.0)            # in place, no Y
+    assert_close(host(dacc), acc + ref, 'in-place layer sum', rtol=1e-5, atol_scale=2e-6)
+
+
+def test_csr_norm_weights_bit_exact():
+    c = load('ml100k_corpus.npz')
+    rowptr, col, val = O.build_norm_adj_csr(c['n_users'], c['n_items'], c['train_user'], c['train_item'])
+    dinv = O.deg_inv_sqrt(np.diff(rowptr))
+    out = torch.empty(len(col), device=DEV)
+    _lib.csr_norm_weights(dv(rowptr), dv(col), dv(dinv), out)
+    assert host(out).tobytes() == val.tobytes()               # bit-equal to the reference on every edge
+
+
+def lightgcn_from_case(s, tag):
+    lr, l2, reg_w, L, D = float(s['hp'][0]), float(s['hp'][1]), float(s['hp'][2]), int(s['hp'][3]), int(s['hp'][4])
+    nU, nI = s['U0'].shape[0], s['I0'].shape[0]
+    corpus = frames_corpus(s['train'], s['dev'], s['test'], n_users=nU, n_items=nI)
+    args = model_args(LightGCN, lr=lr, l2=l2, reg_weight=reg_w, gcn_layers=L, embedding_size=D)
+    model = LightGCN(args, corpus)
+    model.load_state_dict({'user_embedding.weight': torch.from_numpy(s['U0']),
+                           'item_embedding.weight': torch.from_numpy(s['I0'])})
+    return model.to(DEV), corpus, args
+
+
+@pytest.mark.parametrize('tag', SMALL[2:])
+def test_lightgcn_steps_match_reference_golden(tag):
+    s = small_case(load('small_cases.npz'), tag)
+    model, corpus, args = lightgcn_from_case(s, tag)
+    nU = s['U0'].shape[0]
+    pu, pi = model.forward()
+    assert_close(host(pu), s['pooled_user0'], f'{tag} pooled users')
+    assert_close(host(pi), s['pooled_item0'], f'{tag} pooled items')
+    dense = host(model.norm_adj.to_dense())
+    # bit-equal when this host's NumPy rounds fp32 pow like the golden host's did (it is SIMD-dispatched and
+    # not correctly rounded, see tests/test_oracle.py); never more than 1 ulp per factor apart
+    assert ((dense != 0) == (s['adj_dense'] != 0)).all()
+    assert_close(dense, s['adj_dense'], f'{tag} adjacency', rtol=3e-7, atol_scale=0)
+    opt = model.build_optimizer('Adam', args.lr, args.l2)
+    t = model.tables
+    for step in range(3):
+        batch = {'user_id': dv(s[f's{step}/user'], torch.int64), 'pos_item': dv(s[f's{step}/pos'], torch.int64),
+                 'neg_items': dv(s[f's{step}/neg'], torch.int64)}
+        loss = model.predict(batch)
+        loss.backward()
+        assert_close(float(loss), s[f's{step}/loss'], f'{tag} loss step {step}')
+        assert_close(host(t.G[:nU]), s[f's{step}/gU'], f'{tag} gU step {step}')
+        assert_close(host(t.G[nU:]), s[f's{step}/gI'], f'{tag} gI step {step}')
+        assert float(model.pool_grad.abs().max()) == 0.0      # recycled for the next step
+        opt.step()
+        assert_close(host(model.user_embedding.weight), s[f's{step}/U'], f'{tag} U step {step}')
+        assert_close(host(model.item_embedding.weight), s[f's{step}/I'], f'{tag} I step {step}')
+    t.ws.raise_on_status()
+
+
+@pytest.mark.parametrize('L', [1, 2, 3, 4])
+def test_lightgcn_step_vs_oracle_layers(L):
+    rng = np.random.RandomState(L)
+    nU, nI, D, B = 60, 90, 32, 300
+    pairs = np.unique(np.stack([rng.randint(0, nU, 900), rng.randint(0, nI, 900)], 1), axis=0)
+    corpus = frames_corpus(pairs, pairs[:5], pairs[5:10], n_users=nU, n_items=nI)
+    args = model_args(LightGCN, gcn_layers=L, embedding_size=D, reg_weight=1e-3)
+    model = LightGCN(args, corpus).to(DEV)
+    U0, I0 = host(model.user_embedding.weight).copy(), host(model.item_embedding.weight).copy()
+    rowptr, col, val = O.build_norm_adj_csr(nU, nI, pairs[:, 0], pairs[:, 1])
+    A = O.csr_to_torch(rowptr, col, val, nU + nI)
+    user, pos, neg = rng.randint(0, nU, B), rng.randint(0, nI, B), rng.randint(1, nI, B)
+    o_loss, o_gU, o_gI = O.lightgcn_fwd_bwd(A, U0, I0, user, pos, neg, L, 1e-3)
+    loss = model.predict({'user_id': dv(user, torch.int64), 'pos_item': dv(pos, torch.int64),
+                          'neg_items': dv(neg, torch.int64)})
+    t = model.tables
+    assert_close(float(loss), o_loss.item(), 'loss')
+    assert_close(host(t.G[:nU]), o_gU.numpy(), 'gU', rtol=1e-5, atol_scale=2e-6)
+    assert_close(host(t.G[nU:]), o_gI.numpy(), 'gI', rtol=1e-5, atol_scale=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-ranking evaluation
+# ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('tag', SMALL)
+def test_eval_ranks_and_metrics_match_reference_golden(tag, ws):
+    s = small_case(load('small_cases.npz'), tag)
+    nU, nI = s['U0'].shape[0], s['I0'].shape[0]
+    U, I = torch.from_numpy(s['s2/U']), torch.from_numpy(s['s2/I'])
+    if tag.startswith('lgcn'):
+        rowptr, col, val = O.build_norm_adj_csr(nU, nI, s['train'][:, 0], s['train'][:, 1])
+        P = O.lightgcn_propagate(O.csr_to_torch(rowptr, col, val, nU + nI), torch.cat([U, I]), int(s['hp'][3]))
+        U, I = P[:nU].contiguous(), P[nU:].contiguous()
+    user, pos = s['test'][:, 0].astype(np.int64), s['test'][:, 1].astype(np.int64)
+    hp, hi = O.history_csr(nU, s['train'], np.concatenate([s['dev'], s['test']]))
+    rank, target, tki, tkv, scores = _lib.eval_rank_topk(U.to(DEV), I.to(DEV), dv(user), dv(pos), dv(hp), dv(hi),
+                                                         ws, k=10, scores=True)
+    assert (host(rank) == s['eval_rank']).all()               # ranks bit-exact against the reference's argsort
+    assert_close(host(target), s['eval_pred'][:, 0], f'{tag} target scores')
+    ref_scores = s['eval_pred'][:, 1:]
+    finite = np.isfinite(ref_scores)
+    assert_close(host(scores)[finite], ref_scores[finite], f'{tag} score matrix')
+    # top-k: same ids as a stable argsort of the reference's masked scores
+    ref_idx = np.argsort(-ref_scores, axis=1, kind='stable')[:, :10]
+    ref_val = np.take_along_axis(ref_scores, ref_idx, axis=1)
+    got_idx, got_val = host(tki), host(tkv)
+    differ = got_idx != ref_idx
+    assert differ.mean() < 0.02
+    assert np.all(np.abs(got_val[differ] - ref_val[differ]) <= 1e-6)          # only exact near-ties may swap
+    res = host(_lib.metrics(rank, [5, 10, 20], ws))
+    for k, v in zip(s['eval_keys'], s['eval_vals']):
+        name, cut = str(k).split('@')
+        i = [5, 10, 20].index(int(cut))
+        got = {'HR': res[0, i], 'RECALL': res[0, i], 'NDCG': res[1, i], 'PRECISION': res[0, i] / int(cut)}[name]
+        assert got == pytest.approx(float(v), rel=1e-12), k
+    assert ws.status() == 0
+
+
+@pytest.mark.parametrize('R,nI,D', [(1, 10, 16), (65, 64, 32), (300, 129, 64), (3000, 5000, 64), (500, 1000, 128)])
+def test_eval_rank_topk_vs_oracle_and_self_consistency(R, nI, D, ws):
+    """Ragged tiles, users with no / full history, splits of the item range, k = 1..32."""
+    rng = np.random.RandomState(R + nI + D)
+    nU = max(2, R // 3)
+    U = rng.randn(nU, D).astype(np.float32)
+    I = rng.randn(nI, D).astype(np.float32)
+    user = rng.randint(0, nU, R).astype(np.int64)
+    pos = rng.randint(0, nI, R).astype(np.int64)
+    hist = [np.sort(rng.choice(nI, size=min(nI, rng.randint(0, 40)), replace=False)) for _ in range(nU)]
+    hist[0] = np.arange(nI)                                   # a user who has seen everything
+    hist[1] = np.zeros(0, dtype=np.int64)                     # and one with no history
+    hp = np.zeros(nU + 1, dtype=np.int64)
+    np.cumsum([len(h) for h in hist], out=hp[1:])
+    hi = np.concatenate(hist + [np.zeros(1)]).astype(np.int32)
+    k = min(32, nI)
+    for want_topk in (0, k):
+        rank, target, tki, tkv, scores = _lib.eval_rank_topk(dv(U), dv(I), dv(user), dv(pos), dv(hp), dv(hi), ws,
+                                                             k=want_topk, scores=True)
+        sc = host(scores)
+        # (1) against the oracle's scores: values within tolerance, ranks equal except at fp32 near-ties
+        o_scores = O.full_scores(U, I, user).numpy()
+        assert_close(sc, o_scores, 'scores', rtol=1e-5, atol_scale=2e-6)
+        o_rank, o_target = O.ranks_count(o_scores, user, pos, hp, hi)
+        assert np.mean(host(rank) != o_rank) <= 2e-3
+        # (2) exact self-consistency: ranks / top-k recomputed on the host from the kernel's own scores
+        s_rank, s_target = O.ranks_count(sc, user, pos, hp, hi)
+        assert (host(rank) == s_rank).all()
+        assert (host(target) == s_target).all()
+        if want_topk:
+            ref_idx, ref_val = O.topk_masked(sc, user, hp, hi, k)
+            got_idx, got_val = host(tki), host(tkv)
+            filled = np.isfinite(ref_val)
+            assert (got_idx[filled] == ref_idx[filled]).all()          # bit-exact ids, ties to the lower id
+            assert (got_val[filled] == ref_val[filled]).all()
+            assert (got_idx[~filled] == -1).all() and np.isneginf(got_val[~filled]).all()
+    assert ws.status() == 0
+
+
+def test_eval_ties_resolve_to_lower_id(ws):
+    D, nI = 16, 200
+    U = np.ones((2, D), dtype=np.float32)
+    I = np.zeros((nI, D), dtype=np.float32)
+    I[50:60] = 1.0                                            # ten items tied at the top
+    I[120] = 2.0
+    hp, hi = np.array([0, 1, 1], dtype=np.int64), np.array([120], dtype=np.int32)   # user 0 has seen item 120
+    user, pos = np.array([0, 1], dtype=np.int64), np.array([55, 55], dtype=np.int64)
+    rank, target, tki, tkv, _ = _lib.eval_rank_topk(dv(U), dv(I), dv(user), dv(pos), dv(hp), dv(hi), ws, k=5)
+    assert host(rank).tolist() == [1, 2]                      # strict '>' : ties do not push the target down
+    assert host(tki)[0].tolist() == [50, 51, 52, 53, 54]
+    assert host(tki)[1].tolist() == [120, 50, 51, 52, 53]
+
+
+def test_metrics_kernel_vs_oracle(ws):
+    rng = np.random.RandomState(0)
+    rank = rng.randint(1, 3000, size=100_003).astype(np.int32)
+    ks = [1, 5, 10, 20, 50, 100]
+    res = host(_lib.metrics(dv(rank), ks, ws))
+    ref = O.evaluate_method(rank, ks, ['HR', 'NDCG'])
+    for i, k in enumerate(ks):
+        assert res[0, i] == pytest.approx(ref[f'HR@{k}'], rel=1e-13)
+        assert res[1, i] == pytest.approx(ref[f'NDCG@{k}'], rel=1e-13)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# end to end through the reference-facing classes: one ml-100k epoch + dev evaluation
+# ---------------------------------------------------------------------------------------------------------
+
+def run_epoch(cls, **over):
+    corpus = ml100k_corpus()
+    args = model_args(cls, **over)
+    utils.init_seed(3407)                                     # main.py:44
+    model = cls(args, corpus).to(DEV)                         # main.py:66
+    data = {ph: cls.Dataset(model, corpus, ph) for ph in ('train', 'dev', 'test')}
+    runner = BaseRunner(args)
+    mean_loss = runner.fit(data['train'], epoch=1)
+    return model, data, runner, mean_loss
+
+
+def test_ml100k_epoch_bprmf_matches_reference():
+    g = load('ml100k_bprmf.npz')
+    model, data, runner, mean_loss = run_epoch(BPRMF, lr=1e-3, l2=1e-6)
+    assert (data['train'].data['neg_items'] == g['neg_epoch1']).all()          # negatives bit-exact
+    assert mean_loss == pytest.approx(float(g['epoch_mean_loss']), rel=1e-5)
+    # Adam's m/sqrt(v) amplifies 1-ulp gradient differences: parameters after 33 steps at 1e-4 of max|.|
+    assert_close(host(model.user_embeddings.weight[:64]), g['after_user_rows'], 'U', rtol=1e-4, atol_scale=1e-4)
+    assert_close(host(model.item_embeddings.weight[:64]), g['after_item_rows'], 'I', rtol=1e-4, atol_scale=1e-4)
+    assert float(model.user_embeddings.weight.double().norm()) == pytest.approx(float(g['after_user_norm']), rel=1e-5)
+    rank, target = runner.rank_topk(data['dev'])[:2]
+    assert_close(host(target), g['dev_target'], 'dev target', rtol=1e-4, atol_scale=1e-4)
+    assert np.mean(host(rank) != g['dev_rank']) < 0.01
+    res = runner.evaluate(data['dev'], [10, 20], ['NDCG', 'HR'])
+    for k, v in zip(g['dev_metric_keys'], g['dev_metric_vals']):
+        assert res[str(k)] == pytest.approx(float(v), abs=5e-4), k
+
+
+def test_ml100k_epoch_lightgcn_matches_reference():
+    g = load('ml100k_lightgcn.npz')
+    corpus = ml100k_corpus()
+    args = model_args(LightGCN, lr=2e-3, gcn_layers=2)
+    utils.init_seed(3407)
+    model = LightGCN(args, corpus).to(DEV)
+    pu, pi = model.forward()
+    assert_close(host(pu[:64]), g['pooled_user_rows'], 'pooled users at init')
+    assert_close(host(pi[:64]), g['pooled_item_rows'], 'pooled items at init')
+    assert float(pu.double().norm()) == pytest.approx(float(g['pooled_user_norm']), rel=1e-6)
+    data = {ph: LightGCN.Dataset(model, corpus, ph) for ph in ('train', 'dev', 'test')}
+    runner = BaseRunner(args)
+    mean_loss = runner.fit(data['train'], epoch=1)
+    assert mean_loss == pytest.approx(float(g['epoch_mean_loss']), rel=1e-4)
+    assert_close(host(model.user_embedding.weight[:64]), g['after_user_rows'], 'U', rtol=1e-3, atol_scale=1e-3)
+    assert_close(host(model.item_embedding.weight[:64]), g['after_item_rows'], 'I', rtol=1e-3, atol_scale=1e-3)
+    res = runner.evaluate(data['dev'], [10, 20], ['NDCG', 'HR'])
+    for k, v in zip(g['dev_metric_keys'], g['dev_metric_vals']):
+        assert res[str(k)] == pytest.approx(float(v), abs=2e-3), k
+    rank = host(runner.rank_topk(data['dev'])[0])
+    assert np.mean(np.abs(rank - g['dev_rank'].astype(np.int64)) > 3) < 0.02
+
+
+def test_compat_api_full_predict_and_interface():
+    corpus = ml100k_corpus()
+    args = model_args(BPRMF)
+    utils.init_seed(3407)
+    model = BPRMF(args, corpus).to(DEV)
+    data = BPRMF.Dataset(model, corpus, 'dev')
+    user = dv(data.data['user_id'][:100].astype(np.int64))
+    scores = model.full_predict({'user_id': user})
+    ref = O.full_scores(host(model.user_embeddings.weight), host(model.item_embeddings.weight), host(user))
+    assert scores.shape == (100, corpus.n_items)
+    assert_close(host(scores), ref.numpy(), 'full_predict', rtol=1e-5, atol_scale=2e-6)
+    runner = BaseRunner(args)
+    pred = runner.interface(data)
+    assert pred.shape == (len(data), corpus.n_items + 1)
+    res = BaseRunner.evaluate_method(pred, [10], ['NDCG', 'HR'])
+    fused = runner.evaluate(data, [10], ['NDCG', 'HR'])
+    assert res['HR@10'] == fused['HR@10'] and res['NDCG@10'] == pytest.approx(fused['NDCG@10'], rel=1e-12)

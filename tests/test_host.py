@@ -1,0 +1,187 @@
+"""Host-side logic and the C-ABI surface, CPU only (no kernel is launched here)."""
+import argparse
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import whispr_oracle as O
+from tests.helpers import load, ml100k_corpus, model_args
+from whisprrec_b200 import _lib
+from whisprrec_b200 import main as wr_main
+from whisprrec_b200.helpers.BaseReader import BaseReader
+from whisprrec_b200.helpers.BaseRunner import BaseRunner, dataloader_draws
+from whisprrec_b200.models.general.BPRMF import BPRMF
+from whisprrec_b200.models.general.LightGCN import LightGCN, build_norm_adj_csr
+from whisprrec_b200.utils import utils
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DATA = '/root/reference/data/'
+
+
+def test_library_exports_every_declared_symbol():
+    """The header is the contract: every wr_* it declares must be exported, and bound with a signature."""
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    header = open(os.path.join(ROOT, 'include', 'whisprrec_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(wr_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib.wr_version.restype = ctypes.c_int
+    assert lib.wr_version() == 100
+    lib.wr_workspace_bytes.restype = ctypes.c_size_t
+    assert 1024 < lib.wr_workspace_bytes() < (1 << 20)
+    lib.wr_error_string.restype = ctypes.c_char_p
+    assert b'NULL' in lib.wr_error_string(-1)
+
+
+def test_argument_errors_need_no_gpu():
+    """NULL / size / dimension checks run before any CUDA call."""
+    lib = _lib.load()
+    assert lib.wr_adam_l2_sweep(None, None, None, None, 10, 0.0, 0.9, 0.999, 1e-8, 1e-3, 1.0, None, None) == -1
+    assert lib.wr_bpr_fwd_bwd(16, 16, 16, 16, 16, 8, 6, 4, 4, 1e-10, 1.0, 16, 16, 16, 0, 16, None) == -3   # D=6
+    assert lib.wr_bpr_fwd_bwd(16, 16, 16, 16, 16, 0, 8, 4, 4, 1e-10, 1.0, 16, 16, 16, 0, 16, None) == -2   # B=0
+    assert lib.wr_bpr_fwd_bwd(16, 20, 16, 16, 16, 8, 8, 4, 4, 1e-10, 1.0, 16, 16, 16, 0, 16, None) == -5   # align
+    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 33, 0, 16, 16, 16, 16, None, 16, None) == -4
+    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 0, 7, None, None, 16, 16, None, 16, None) == -6
+
+
+def test_product_refuses_cpu_tensors():
+    with pytest.raises(_lib.WhisprError):
+        _lib.ptr(torch.zeros(4))
+    corpus = ml100k_corpus()
+    model = BPRMF(model_args(BPRMF), corpus)
+    with pytest.raises(_lib.WhisprError):
+        model.fuse()                                   # parameters still on the CPU: no fallback
+
+
+def test_negative_sampler_bit_exact_on_ml100k():
+    """Dataset.actions_before_epoch == reference BaseModel.py:167-177 on NumPy's global stream."""
+    g = load('ml100k_bprmf.npz')
+    corpus = ml100k_corpus()
+    utils.init_seed(3407)
+    model = BPRMF(model_args(BPRMF), corpus)
+    ds = BPRMF.Dataset(model, corpus, 'train')
+    ds.actions_before_epoch()
+    assert ds.data['neg_items'].dtype == np.int64
+    assert (ds.data['neg_items'] == g['neg_epoch1']).all()
+    ds.actions_before_epoch()
+    assert hashlib.sha256(ds.data['neg_items'].astype(np.int64).tobytes()).hexdigest() == str(g['neg_epoch2_sha'])
+    assert (ds.data['neg_items'][:64] == g['neg_epoch2_head']).all()
+
+
+def test_init_and_batch_order_bit_exact_on_ml100k():
+    g = load('ml100k_bprmf.npz')
+    corpus = ml100k_corpus()
+    utils.init_seed(3407)
+    model = BPRMF(model_args(BPRMF), corpus)
+    assert hashlib.sha256(model.user_embeddings.weight.detach().numpy().tobytes()).hexdigest() == str(g['init_user_sha'])
+    assert hashlib.sha256(model.item_embeddings.weight.detach().numpy().tobytes()).hexdigest() == str(g['init_item_sha'])
+    assert model.count_variables() == 161088
+    assert sorted(model.state_dict().keys()) == ['item_embeddings.weight', 'user_embeddings.weight']
+    ds = BPRMF.Dataset(model, corpus, 'train')
+    ds.actions_before_epoch()
+    perm = dataloader_draws(len(ds), shuffle=True)
+    for b in (0, 1):
+        sel = perm[b * 2048:(b + 1) * 2048]
+        assert (ds.data['user_id'][sel] == g[f'batch{b}_user']).all()
+        assert (ds.data['item_id'][sel] == g[f'batch{b}_pos']).all()
+        assert (ds.data['neg_items'][sel] == g[f'batch{b}_neg']).all()
+
+
+def test_dataloader_draws_match_a_real_dataloader():
+    from torch.utils.data import DataLoader
+    for shuffle in (True, False):
+        torch.manual_seed(5)
+        dl = DataLoader(list(range(1000)), batch_size=64, shuffle=shuffle)
+        ref = torch.cat([b for b in dl]).numpy()
+        after_ref = torch.empty((), dtype=torch.int64).random_().item()
+        torch.manual_seed(5)
+        perm = dataloader_draws(1000, shuffle)
+        after = torch.empty((), dtype=torch.int64).random_().item()
+        assert after == after_ref                      # the global generator is left in the same state
+        assert (ref == (perm if shuffle else np.arange(1000))).all()
+
+
+def test_lightgcn_init_and_adjacency_structure():
+    g = load('ml100k_lightgcn.npz')
+    corpus = ml100k_corpus()
+    utils.init_seed(3407)
+    model = LightGCN(model_args(LightGCN, lr=2e-3), corpus)
+    assert hashlib.sha256(model.user_embedding.weight.detach().numpy().tobytes()).hexdigest() == str(g['init_user_sha'])
+    assert hashlib.sha256(model.item_embedding.weight.detach().numpy().tobytes()).hexdigest() == str(g['init_item_sha'])
+    assert sorted(model.state_dict().keys()) == ['item_embedding.weight', 'user_embedding.weight']
+    rowptr, col, dinv = model._adj_host
+    c = load('ml100k_corpus.npz')
+    o_rowptr, o_col, o_val = O.build_norm_adj_csr(c['n_users'], c['n_items'], c['train_user'], c['train_item'])
+    assert (rowptr == o_rowptr).all() and (col == o_col).all()
+    rows = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+    val = (dinv[rows] * np.float32(1.0)) * dinv[col]            # what wr_csr_norm_weights computes
+    assert val.dtype == np.float32 and val.tobytes() == o_val.tobytes()
+    assert hashlib.sha256(val.tobytes()).hexdigest() == str(g['adj_val_sha'])
+
+
+def test_history_csr_matches_oracle():
+    corpus = ml100k_corpus()
+    c = load('ml100k_corpus.npz')
+    tr = np.stack([c['train_user'], c['train_item']], 1).astype(np.int64)
+    rest = np.concatenate([np.stack([c['dev_user'], c['dev_item']], 1), np.stack([c['test_user'], c['test_item']], 1)])
+    op, oi = O.history_csr(int(c['n_users']), tr, rest.astype(np.int64))
+    hp, hi = corpus.history_csr()
+    assert (hp == op).all() and (hi == oi).all()
+    for u in (0, 17, 942):
+        assert set(hi[hp[u]:hp[u + 1]]) == corpus.train_clicked_set[u] | corpus.residual_clicked_set[u]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DATA, 'ml-100k', 'ml-100k.inter')),
+                    reason='reference data only exists in the authoring container')
+def test_reader_reproduces_reference_split():
+    c = load('ml100k_corpus.npz')
+    args = model_args(BPRMF, path=REF_DATA, dataset='ml-100k')
+    corpus = BaseReader(args)
+    assert int(corpus.n_users) == int(c['n_users']) == 943 and int(corpus.n_items) == int(c['n_items']) == 1574
+    for ph in ('train', 'dev', 'test'):
+        assert (corpus.data_df[ph]['user_id'].to_numpy() == c[ph + '_user']).all()
+        assert (corpus.data_df[ph]['item_id'].to_numpy() == c[ph + '_item']).all()
+
+
+def test_cli_surface_matches_reference():
+    init_args, args, (model_class, reader_class, runner_class, reader_name) = wr_main.build_args(
+        ['--model_name', 'LightGCN', '--emb_size', '32', '--gcn_layers', '3', '--lr', '2e-3', '--bogus', '1'])
+    assert model_class is LightGCN and reader_name == 'BaseReader' and runner_class is BaseRunner
+    assert args.embedding_size == 64                   # `--emb_size` is silently ignored, as in the reference
+    assert args.gcn_layers == 3 and args.lr == 2e-3 and args.batch_size == 2048 and args.topk == '10,20'
+    assert args.log_file == '../log/LightGCN/LightGCN__ml-100k__3407__lr=0.002__l2=0__embedding_size=64__' \
+                            'gcn_layers=3__reg_weight=1e-05.txt'
+    assert args.model_path.endswith('.pt') and '/model/LightGCN/' in args.model_path
+    with pytest.raises(NameError):
+        wr_main.build_args(['--model_name', 'NoSuchModel'])
+
+
+def test_metric_formatting_and_host_metrics():
+    res = {'NDCG@10': np.float64(0.05551), 'HR@10': np.float64(0.1087), 'HR@20': 0.25, 'NDCG@20': np.float32(0.1)}
+    assert utils.format_metric(res) == 'HR@10:0.1087,NDCG@10:0.0555,HR@20:0.2500,NDCG@20:0.1000'
+    s = load('small_cases.npz')
+    pred, rank = s['bprmf_d16/eval_pred'], s['bprmf_d16/eval_rank']
+    out = BaseRunner.evaluate_method(pred, [5, 10, 20], ['NDCG', 'HR', 'RECALL', 'PRECISION'])
+    for k, v in zip(s['bprmf_d16/eval_keys'], s['bprmf_d16/eval_vals']):
+        assert out[str(k)] == pytest.approx(float(v), rel=1e-12)
+    assert BaseRunner.metrics_from_ranks(rank, [10], ['HR'])['HR@10'] == out['HR@10']
+    with pytest.raises(ValueError):
+        BaseRunner.metrics_from_ranks(rank, [10], ['MAP'])
+
+
+def test_early_stop_rule():
+    r = BaseRunner(model_args(BPRMF))
+    assert not r.eval_termination([0.1] * 5)
+    assert r.eval_termination([0.5] + [0.4] * 10)                  # best is more than early_stop epochs old
+    assert r.eval_termination(list(np.linspace(1.0, 0.0, 11)))     # non-increasing for early_stop epochs

@@ -1,0 +1,199 @@
+"""ctypes binding of libwhisprrec_b200.so (the C-ABI declared in include/whisprrec_b200.h).
+
+PyTorch is only the plumbing here: it owns device memory and the stream; every call below hands raw
+`data_ptr()`s and the current stream to a hand-written sm_100a kernel.  There is no CPU or eager-torch
+fallback: a missing library or a CPU tensor raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libwhisprrec_b200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+_c = ctypes
+_p, _i64, _int, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/whisprrec_b200.h declares
+SIGNATURES = {
+    'wr_version': (_int, []),
+    'wr_error_string': (_c.c_char_p, [_int]),
+    'wr_workspace_bytes': (_sz, []),
+    'wr_workspace_init': (_int, [_p, _p]),
+    'wr_status': (_int, [_p, _c.POINTER(_c.c_uint32), _p]),
+    'wr_bpr_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _p, _p, _p, _int, _p, _p]),
+    'wr_embloss_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _p, _p, _p, _p, _p]),
+    'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p, _p]),
+    'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
+    'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p]),
+    'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
+                                 _p]),
+    'wr_metrics': (_int, [_p, _i64, _c.POINTER(_int), _int, _p, _p, _p]),
+    'wr_gather_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
+    'wr_scatter_add_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class WhisprError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile the library in-tree with nvcc for sm_100a (works without a GPU)."""
+    r = subprocess.run(['make', '-C', CSRC, '-j4'], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode != 0:
+        raise WhisprError('building libwhisprrec_b200.so failed')
+    return LIB_PATH
+
+
+def load():
+    """dlopen the library and attach signatures.  Raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WhisprError(f'{LIB_PATH} not found: run `python -c "import __graft_entry__ as g; g.build()"` '
+                              f'or `make -C {CSRC}`; there is no CPU fallback')
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.wr_version() != 100:
+            raise WhisprError('libwhisprrec_b200.so version mismatch')
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise WhisprError(f'whisprrec_b200 error {rc}: {load().wr_error_string(rc).decode()}')
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise WhisprError('whisprrec_b200 kernels need CUDA tensors (no CPU fallback)')
+    if dtype is not None and t.dtype != dtype:
+        raise WhisprError(f'expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise WhisprError('tensor must be contiguous')
+    return t.data_ptr()
+
+
+class Workspace:
+    """Device scratch for the reductions; one per stream."""
+
+    def __init__(self, device):
+        lib = load()
+        self.buf = torch.empty(lib.wr_workspace_bytes(), dtype=torch.uint8, device=device)
+        check(lib.wr_workspace_init(self.buf.data_ptr(), stream_ptr()))
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def status(self):
+        """Read-and-clear the device status word (synchronises)."""
+        out = ctypes.c_uint32(0)
+        check(load().wr_status(self.ptr, ctypes.byref(out), stream_ptr()))
+        return out.value
+
+    def raise_on_status(self):
+        st = self.status()
+        if st & 1:
+            raise IndexError('index out of range in self')      # what nn.Embedding raises in the reference
+
+
+# ------------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (argument checks live in the C side)
+# ------------------------------------------------------------------------------------------------------
+F32, I64, I32 = torch.float32, torch.int64, torch.int32
+
+
+def bpr_fwd_bwd(U, I, user, pos, neg, gU, gI, loss_out, ws, gamma=1e-10, grad_scale=1.0, accumulate_loss=False):
+    D = U.shape[1]
+    check(load().wr_bpr_fwd_bwd(ptr(U, F32), ptr(I, F32), ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
+                                user.numel(), D, U.shape[0], I.shape[0], gamma, grad_scale,
+                                ptr(gU, F32), ptr(gI, F32), ptr(loss_out, F32), int(accumulate_loss),
+                                ws.ptr, stream_ptr()))
+
+
+def embloss_fwd_bwd(U0, I0, user, pos, neg, gU0, gI0, loss_out, ws, reg_weight):
+    D = U0.shape[1]
+    check(load().wr_embloss_fwd_bwd(ptr(U0, F32), ptr(I0, F32), ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
+                                    user.numel(), D, U0.shape[0], I0.shape[0], reg_weight,
+                                    ptr(gU0, F32), ptr(gI0, F32), ptr(loss_out, F32), ws.ptr, stream_ptr()))
+
+
+def adam_scalars(step, lr, beta1=0.9, beta2=0.999):
+    """(lr / (1 - beta1^t), sqrt(1 - beta2^t)) in Python doubles, as torch/optim/adam.py computes them."""
+    return lr / (1.0 - beta1 ** step), (1.0 - beta2 ** step) ** 0.5
+
+
+def adam_l2_sweep(P, M, V, G, step, lr, l2, beta1=0.9, beta2=0.999, eps=1e-8, dev_scalars=None):
+    ss, bc2s = adam_scalars(step, lr, beta1, beta2)
+    check(load().wr_adam_l2_sweep(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), P.numel(), l2, beta1, beta2,
+                                  eps, ss, bc2s, ptr(dev_scalars, F32), stream_ptr()))
+
+
+def csr_norm_weights(rowptr, col, dinv, val):
+    check(load().wr_csr_norm_weights(ptr(rowptr, I64), ptr(col, I32), ptr(dinv, F32), rowptr.numel() - 1,
+                                     ptr(val, F32), stream_ptr()))
+
+
+def csr_spmm(rowptr, col, val, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None, acc_div=1.0):
+    N, D = X.shape
+    check(load().wr_csr_spmm(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), N, D, ptr(X, F32), ptr(Y, F32),
+                             ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32), acc_div,
+                             stream_ptr()))
+
+
+def eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k=0, precision=0, scores=False):
+    """Returns (rank int32 [R], target fp32 [R], topk_idx int32 [R,k] | None, topk_val fp32 [R,k] | None,
+    scores fp32 [R, n_items] | None)."""
+    R, D = user.numel(), Uemb.shape[1]
+    dev = Uemb.device
+    rank = torch.empty(R, dtype=I32, device=dev)
+    target = torch.empty(R, dtype=F32, device=dev)
+    tki = torch.empty((R, k), dtype=I32, device=dev) if k > 0 else None
+    tkv = torch.empty((R, k), dtype=F32, device=dev) if k > 0 else None
+    sc = torch.empty((R, Iemb.shape[0]), dtype=F32, device=dev) if scores else None
+    check(load().wr_eval_rank_topk(ptr(Uemb, F32), ptr(Iemb, F32), ptr(user, I64), ptr(pos, I64), R,
+                                   Uemb.shape[0], Iemb.shape[0], D, ptr(hist_ptr, I64), ptr(hist_idx, I32),
+                                   k, precision, ptr(tki, I32), ptr(tkv, F32), ptr(rank, I32), ptr(target, F32),
+                                   ptr(sc, F32), ws.ptr, stream_ptr()))
+    return rank, target, tki, tkv, sc
+
+
+def metrics(rank, ks, ws):
+    """float64 tensor [2, len(ks)]: row 0 = HR@k, row 1 = NDCG@k."""
+    nk = len(ks)
+    out = torch.empty((2, nk), dtype=torch.float64, device=rank.device)
+    arr = (ctypes.c_int * nk)(*[int(k) for k in ks])
+    check(load().wr_metrics(ptr(rank, I32), rank.numel(), arr, nk, out.data_ptr(), ws.ptr, stream_ptr()))
+    return out
+
+
+def gather_rows(T, idx, ws, out=None):
+    if out is None:
+        out = torch.empty((idx.numel(), T.shape[1]), dtype=F32, device=T.device)
+    check(load().wr_gather_rows(ptr(T, F32), ptr(idx, I64), idx.numel(), T.shape[1], T.shape[0], ptr(out, F32),
+                                ws.ptr, stream_ptr()))
+    return out
+
+
+def scatter_add_rows(G, idx, rows, ws):
+    check(load().wr_scatter_add_rows(ptr(G, F32), ptr(idx, I64), idx.numel(), G.shape[1], G.shape[0],
+                                     ptr(rows, F32), ws.ptr, stream_ptr()))

@@ -1,0 +1,126 @@
+// Shared device helpers for libwhisprrec_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/whisprrec_b200.h"
+
+#define WR_MAX_PARTIAL_BLOCKS 2048
+
+// Device scratch block handed in by the caller (wr_workspace_bytes()).
+struct WrWorkspace {
+    uint32_t status;                           // WR_STATUS_* bits
+    uint32_t ticket[7];                        // "last block done" counters, one per reduction in flight
+    float norms[4];                            // EmbLoss: ||U0_b||, ||P0_b||, ||N0_b||
+    float partial[3 * WR_MAX_PARTIAL_BLOCKS];  // per-block partial sums, summed in block order (deterministic)
+    double dpartial[2 * 8 * 64];               // wr_metrics
+};
+
+#define WR_CHECK_LAUNCH()                        \
+    do {                                         \
+        cudaError_t e__ = cudaGetLastError();    \
+        if (e__ != cudaSuccess) return (int)e__; \
+    } while (0)
+
+static inline bool wr_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+namespace wr {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int WIDTH>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = WIDTH / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the block; the result is valid in thread 0.  `red` needs blockDim.x/32 floats.
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (w == 0) {
+        t = lane < nw ? red[lane] : 0.f;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+// 128-bit fire-and-forget reduction into global memory (REDG.E.ADD.F32x4): one L2 transaction per 16 B.
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 sub4(float4 a, float4 b) {
+    return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 fma4(float s, float4 x, float4 a) {
+    return make_float4(fmaf(s, x.x, a.x), fmaf(s, x.y, a.y), fmaf(s, x.z, a.z), fmaf(s, x.w, a.w));
+}
+
+// The last block to arrive returns true (after all other blocks' prior global writes are visible).
+__device__ __forceinline__ bool last_block_arrives(uint32_t *ticket, bool *smem_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(ticket, 1u);
+        *smem_flag = (t == gridDim.x - 1);
+        if (*smem_flag) *ticket = 0;  // re-arm for the next launch on this stream
+    }
+    __syncthreads();
+    const bool last = *smem_flag;
+    if (last) __threadfence();
+    return last;
+}
+
+// Row layout shared by the gather-style kernels: a row of D = 4*LPR*VPL floats is covered by LPR lanes,
+// each holding VPL float4 at stride LPR; 32/LPR rows are processed by a warp at a time.
+template <int LPR, int VPL>
+struct RowGroup {
+    static constexpr int D = 4 * LPR * VPL;
+    static constexpr int GROUPS = 32 / LPR;
+    __device__ static __forceinline__ void load(const float *row, int sub, float4 (&r)[VPL]) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) r[v] = ldg4(row + 4 * (sub + v * LPR));
+    }
+    __device__ static __forceinline__ void zero(float4 (&r)[VPL]) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) r[v] = f4_zero();
+    }
+};
+
+}  // namespace wr
+
+// Dispatch on the embedding size: the row is split over LPR lanes x VPL float4 per lane.
+#define WR_DISPATCH_D(D, CALL)                 \
+    switch (D) {                               \
+        case 4: { CALL(1, 1); } break;         \
+        case 8: { CALL(2, 1); } break;         \
+        case 16: { CALL(4, 1); } break;        \
+        case 32: { CALL(8, 1); } break;        \
+        case 64: { CALL(16, 1); } break;       \
+        case 128: { CALL(32, 1); } break;      \
+        case 256: { CALL(32, 2); } break;      \
+        case 512: { CALL(32, 4); } break;      \
+        default: return WR_E_DIM;              \
+    }

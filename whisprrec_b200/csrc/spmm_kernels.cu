@@ -1,0 +1,186 @@
+// LightGCN propagation: CSR SpMM over the symmetric-normalised bipartite adjacency with the layer-mean
+// (and, in the backward direction, the pooled-gradient addend) fused into the epilogue.
+#include "common.cuh"
+
+namespace wr {
+
+struct SpmmParams {
+    const int64_t *rowptr;
+    const int32_t *col;
+    const float *val;
+    int64_t N;
+    const float *X;
+    float *Y;
+    float *add;
+    int zero_add;
+    const float *acc_in;
+    float *acc_out;
+    float acc_div;
+};
+
+// A warp owns a row.  The row of D = 4*LPR*VPL floats is covered by LPR lanes, so 32/LPR neighbour rows are
+// fetched per step (one 128-bit load per lane each), UNROLL steps in flight.  Column ids / weights are read
+// 32 at a time, coalesced, and handed round with shuffles.
+template <int LPR, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParams p) {
+    using RG = RowGroup<LPR, VPL>;
+    constexpr int D = RG::D;
+    constexpr int EPS = RG::GROUPS;  // edges per step
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp; row < p.N; row += nwarps) {
+        const int64_t beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+        float4 acc[VPL];
+        RG::zero(acc);
+        for (int64_t base = beg; base < end; base += 32) {
+            const int cnt = (int)min((int64_t)32, end - base);
+            int c = 0;
+            float w = 0.f;
+            if (lane < cnt) {
+                c = __ldg(p.col + base + lane);
+                w = __ldg(p.val + base + lane);
+            }
+            for (int j = 0; j < cnt; j += EPS * UNROLL) {
+                float4 x[UNROLL][VPL];
+                float ww[UNROLL];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const int e = j + u * EPS + grp;
+                    const int cc = __shfl_sync(0xffffffffu, c, e & 31);
+                    ww[u] = __shfl_sync(0xffffffffu, w, e & 31);
+                    if (e < cnt) {
+                        RG::load(p.X + (int64_t)cc * D, sub, x[u]);
+                    } else {
+                        RG::zero(x[u]);
+                        ww[u] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                    for (int v = 0; v < VPL; ++v) acc[v] = fma4(ww[u], x[u][v], acc[v]);
+            }
+        }
+        // fold the 32/LPR partial rows held by the lane groups
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+                acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+                acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+                acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+            }
+        if (grp == 0) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int64_t off = row * D + 4 * (sub + v * LPR);
+                float4 y = acc[v];
+                if (p.add) {
+                    float4 *ap = reinterpret_cast<float4 *>(p.add + off);
+                    y = add4(y, *ap);
+                    if (p.zero_add) *ap = f4_zero();
+                }
+                if (p.Y) *reinterpret_cast<float4 *>(p.Y + off) = y;
+                if (p.acc_out) {
+                    const float4 a = add4(*reinterpret_cast<const float4 *>(p.acc_in + off), y);
+                    // ATen's mean is sum().div_(count): a true division, not a multiply by the reciprocal
+                    *reinterpret_cast<float4 *>(p.acc_out + off) =
+                        p.acc_div == 1.0f ? a
+                                          : make_float4(a.x / p.acc_div, a.y / p.acc_div, a.z / p.acc_div,
+                                                        a.w / p.acc_div);
+                }
+            }
+        }
+    }
+}
+
+// Any D % 4 == 0.
+__global__ void __launch_bounds__(256) csr_spmm_generic_kernel(SpmmParams p, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int D4 = D >> 2;
+    for (int64_t row = warp; row < p.N; row += nwarps) {
+        const int64_t beg = p.rowptr[row], end = p.rowptr[row + 1];
+        for (int v = lane; v < D4; v += 32) {
+            float4 acc = f4_zero();
+            for (int64_t e = beg; e < end; ++e)
+                acc = fma4(__ldg(p.val + e), ldg4(p.X + (int64_t)__ldg(p.col + e) * D + 4 * v), acc);
+            const int64_t off = row * D + 4 * v;
+            if (p.add) {
+                float4 *ap = reinterpret_cast<float4 *>(p.add + off);
+                acc = add4(acc, *ap);
+                if (p.zero_add) *ap = f4_zero();
+            }
+            if (p.Y) *reinterpret_cast<float4 *>(p.Y + off) = acc;
+            if (p.acc_out) {
+                const float4 a = add4(*reinterpret_cast<const float4 *>(p.acc_in + off), acc);
+                *reinterpret_cast<float4 *>(p.acc_out + off) =
+                    p.acc_div == 1.0f
+                        ? a
+                        : make_float4(a.x / p.acc_div, a.y / p.acc_div, a.z / p.acc_div, a.w / p.acc_div);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) csr_norm_weights_kernel(const int64_t *__restrict__ rowptr,
+                                                                const int32_t *__restrict__ col,
+                                                                const float *__restrict__ dinv, int64_t N,
+                                                                float *__restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = warp; row < N; row += nwarps) {
+        const int64_t beg = rowptr[row], end = rowptr[row + 1];
+        // LightGCN.py:95-97: (D^-1/2 A) D^-1/2 on a binary A: two roundings, row factor first
+        const float dr = __fmul_rn(dinv[row], 1.0f);
+        for (int64_t e = beg + lane; e < end; e += 32) val[e] = __fmul_rn(dr, dinv[col[e]]);
+    }
+}
+
+}  // namespace wr
+
+using namespace wr;
+
+extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D,
+                           const float *X, float *Y, float *add, int zero_add, const float *acc_in,
+                           float *acc_out, float acc_div, void *stream) {
+    if (!rowptr || !col || !val || !X) return WR_E_NULL;
+    if (!Y && !acc_out) return WR_E_NULL;
+    if (acc_out && !acc_in) return WR_E_NULL;
+    if (N <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(X) || (Y && !wr_aligned16(Y)) || (add && !wr_aligned16(add)) ||
+        (acc_in && !wr_aligned16(acc_in)) || (acc_out && !wr_aligned16(acc_out)))
+        return WR_E_ALIGN;
+    if (X == Y || X == acc_out) return WR_E_SIZE;
+    SpmmParams p{rowptr, col, val, N, X, Y, add, zero_add, acc_in, acc_out, acc_div};
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t g = (N + 7) / 8;
+    if (g > 16 * kSMs) g = 16 * kSMs;
+    const int grid = (int)g;
+    switch (D) {
+        case 16: csr_spmm_kernel<4, 1, 2><<<grid, 256, 0, st>>>(p); break;
+        case 32: csr_spmm_kernel<8, 1, 2><<<grid, 256, 0, st>>>(p); break;
+        case 64: csr_spmm_kernel<16, 1, 4><<<grid, 256, 0, st>>>(p); break;
+        case 128: csr_spmm_kernel<32, 1, 4><<<grid, 256, 0, st>>>(p); break;
+        case 256: csr_spmm_kernel<32, 2, 2><<<grid, 256, 0, st>>>(p); break;
+        default: csr_spmm_generic_kernel<<<grid, 256, 0, st>>>(p, D);
+    }
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_csr_norm_weights(const int64_t *rowptr, const int32_t *col, const float *dinv, int64_t N,
+                                   float *val, void *stream) {
+    if (!rowptr || !col || !dinv || !val) return WR_E_NULL;
+    if (N <= 0) return WR_E_SIZE;
+    int64_t g = (N + 7) / 8;
+    if (g > 16 * kSMs) g = 16 * kSMs;
+    csr_norm_weights_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(rowptr, col, dinv, N, val);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}

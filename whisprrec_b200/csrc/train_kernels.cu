@@ -1,0 +1,443 @@
+// Training-step kernels: fused BPR forward+backward, EmbLoss, dense Adam+L2 sweep, row gather / scatter-add.
+// See include/whisprrec_b200.h for the reference lines each entry point replaces.
+#include "common.cuh"
+
+namespace wr {
+
+// ------------------------------------------------------------------------------------------------------
+// BPR forward + backward.  One group of LPR lanes per interaction; the three rows stay in registers
+// between the dot products and the gradient reductions, so each row is read exactly once.
+// ------------------------------------------------------------------------------------------------------
+struct BprParams {
+    const float *U, *I;
+    const int64_t *user, *pos, *neg;
+    int64_t B, n_users, n_items;
+    float gamma, coef;  // coef = grad_scale / B
+    float *gU, *gI, *loss_out;
+    int accumulate_loss;
+    WrWorkspace *ws;
+};
+
+__device__ __forceinline__ void bpr_pointwise(float sp, float sn, float gamma, float coef, float &loss, float &c) {
+    // utils/loss.py:38: -log(gamma + sigmoid(pos - neg)); d/ds+ = -(sig (1-sig)) / (gamma + sig)
+    const float x = sp - sn;
+    const float sig = 1.0f / (1.0f + expf(-x));
+    loss = -logf(gamma + sig);
+    c = -(sig * (1.0f - sig)) / (gamma + sig) * coef;
+}
+
+// Deterministic epilogue shared by the loss kernels: per-block partials, summed in block order by the last block.
+__device__ __forceinline__ void finish_loss(float local, float *red, bool *flag, WrWorkspace *ws, int slot,
+                                            int64_t B, float *loss_out, int accumulate) {
+    const float bsum = block_sum(local, red);
+    if (threadIdx.x == 0) ws->partial[slot * WR_MAX_PARTIAL_BLOCKS + blockIdx.x] = bsum;
+    if (last_block_arrives(&ws->ticket[slot], flag)) {
+        if (threadIdx.x < 32) {
+            float t = 0.f;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32)
+                t += __ldcg(&ws->partial[slot * WR_MAX_PARTIAL_BLOCKS + i]);
+            t = warp_sum(t);
+            if (threadIdx.x == 0) {
+                const float mean = t / (float)B;
+                loss_out[0] = accumulate ? loss_out[0] + mean : mean;
+            }
+        }
+    }
+}
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParams p) {
+    using RG = RowGroup<LPR, VPL>;
+    constexpr int D = RG::D;
+    __shared__ float red[8];
+    __shared__ bool flag;
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float local = 0.f;
+    for (int64_t base = warp * RG::GROUPS; base < p.B; base += nwarps * RG::GROUPS) {
+        const int64_t b = base + grp;
+        const bool valid = b < p.B;
+        int64_t u = 0, i = 0, j = 0;
+        if (valid) {
+            u = p.user[b];
+            i = p.pos[b];
+            j = p.neg[b];
+        }
+        const bool ok = valid && (uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
+                        (uint64_t)j < (uint64_t)p.n_items;
+        if (valid && !ok && sub == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+        float4 ue[VPL], pe[VPL], ne[VPL];
+        if (ok) {
+            RG::load(p.U + u * D, sub, ue);
+            RG::load(p.I + i * D, sub, pe);
+            RG::load(p.I + j * D, sub, ne);
+        } else {
+            RG::zero(ue);
+            RG::zero(pe);
+            RG::zero(ne);
+        }
+        float sp = 0.f, sn = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            sp += dot4(ue[v], pe[v]);
+            sn += dot4(ue[v], ne[v]);
+        }
+        sp = group_sum<LPR>(sp);
+        sn = group_sum<LPR>(sn);
+        if (ok) {
+            float l, c;
+            bpr_pointwise(sp, sn, p.gamma, p.coef, l, c);
+            if (sub == 0) local += l;
+            float *gu = p.gU + u * D, *gp = p.gI + i * D, *gn = p.gI + j * D;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int off = 4 * (sub + v * LPR);
+                red_add_v4(gu + off, scale4(sub4(pe[v], ne[v]), c));
+                red_add_v4(gp + off, scale4(ue[v], c));
+                red_add_v4(gn + off, scale4(ue[v], -c));
+            }
+        }
+    }
+    finish_loss(local, red, &flag, p.ws, 0, p.B, p.loss_out, p.accumulate_loss);
+}
+
+// Any D % 4 == 0: a warp per interaction, rows re-read for the gradient (they are L1 hits).
+__global__ void __launch_bounds__(256) bpr_fwd_bwd_generic_kernel(BprParams p, int D) {
+    __shared__ float red[8];
+    __shared__ bool flag;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int D4 = D >> 2;
+    float local = 0.f;
+    for (int64_t b = warp; b < p.B; b += nwarps) {
+        const int64_t u = p.user[b], i = p.pos[b], j = p.neg[b];
+        const bool ok = (uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
+                        (uint64_t)j < (uint64_t)p.n_items;
+        if (!ok) {
+            if (lane == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+            continue;
+        }
+        const float *ur = p.U + u * D, *pr = p.I + i * D, *nr = p.I + j * D;
+        float sp = 0.f, sn = 0.f;
+        for (int v = lane; v < D4; v += 32) {
+            const float4 a = ldg4(ur + 4 * v);
+            sp += dot4(a, ldg4(pr + 4 * v));
+            sn += dot4(a, ldg4(nr + 4 * v));
+        }
+        sp = warp_sum(sp);
+        sn = warp_sum(sn);
+        float l, c;
+        bpr_pointwise(sp, sn, p.gamma, p.coef, l, c);
+        if (lane == 0) local += l;
+        for (int v = lane; v < D4; v += 32) {
+            const float4 a = ldg4(ur + 4 * v), x = ldg4(pr + 4 * v), y = ldg4(nr + 4 * v);
+            red_add_v4(p.gU + u * D + 4 * v, scale4(sub4(x, y), c));
+            red_add_v4(p.gI + i * D + 4 * v, scale4(a, c));
+            red_add_v4(p.gI + j * D + 4 * v, scale4(a, -c));
+        }
+    }
+    finish_loss(local, red, &flag, p.ws, 0, p.B, p.loss_out, p.accumulate_loss);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// EmbLoss: phase 1 sums squares of the gathered ego rows (per occurrence), phase 2 scatters row/||.||.
+// ------------------------------------------------------------------------------------------------------
+struct EmbParams {
+    const float *U0, *I0;
+    const int64_t *user, *pos, *neg;
+    int64_t B, n_users, n_items;
+    float reg_weight;
+    float *gU0, *gI0, *loss_out;
+    WrWorkspace *ws;
+};
+
+__global__ void __launch_bounds__(256) embloss_sumsq_kernel(EmbParams p, int D) {
+    __shared__ float red[8];
+    __shared__ bool flag;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int D4 = D >> 2;
+    float su = 0.f, sp = 0.f, sn = 0.f;
+    // lanes cover (interaction, float4) pairs so that D=64 rows keep all 32 lanes busy
+    const int64_t total = p.B * D4;
+    for (int64_t t = warp * 32 + lane; t < total; t += nwarps * 32) {
+        const int64_t b = t / D4;
+        const int v = (int)(t - b * D4);
+        const int64_t u = p.user[b], i = p.pos[b], j = p.neg[b];
+        if ((uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
+            (uint64_t)j < (uint64_t)p.n_items) {
+            const float4 a = ldg4(p.U0 + u * D + 4 * v), x = ldg4(p.I0 + i * D + 4 * v),
+                         y = ldg4(p.I0 + j * D + 4 * v);
+            su += dot4(a, a);
+            sp += dot4(x, x);
+            sn += dot4(y, y);
+        }
+    }
+    const float bu = block_sum(su, red), bp = block_sum(sp, red), bn = block_sum(sn, red);
+    if (threadIdx.x == 0) {
+        p.ws->partial[0 * WR_MAX_PARTIAL_BLOCKS + blockIdx.x] = bu;
+        p.ws->partial[1 * WR_MAX_PARTIAL_BLOCKS + blockIdx.x] = bp;
+        p.ws->partial[2 * WR_MAX_PARTIAL_BLOCKS + blockIdx.x] = bn;
+    }
+    if (last_block_arrives(&p.ws->ticket[1], &flag)) {
+        if (threadIdx.x < 32) {
+            float t[3] = {0.f, 0.f, 0.f};
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32)
+#pragma unroll
+                for (int q = 0; q < 3; ++q) t[q] += __ldcg(&p.ws->partial[q * WR_MAX_PARTIAL_BLOCKS + i]);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) t[q] = sqrtf(warp_sum(t[q]));
+            if (threadIdx.x == 0) {
+                p.ws->norms[0] = t[0];
+                p.ws->norms[1] = t[1];
+                p.ws->norms[2] = t[2];
+                // utils/loss.py:94-98: (sum of the three norms) / B, scaled by reg_weight at LightGCN.py:175
+                p.loss_out[0] += p.reg_weight * ((t[0] + t[1] + t[2]) / (float)p.B);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) embloss_scatter_kernel(EmbParams p, int D) {
+    const int D4 = D >> 2;
+    const float k = p.reg_weight / (float)p.B;
+    const float nu = p.ws->norms[0], np_ = p.ws->norms[1], nn = p.ws->norms[2];
+    const float ku = nu > 0.f ? k / nu : 0.f, kp = np_ > 0.f ? k / np_ : 0.f, kn = nn > 0.f ? k / nn : 0.f;
+    const int64_t total = p.B * D4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / D4;
+        const int v = (int)(t - b * D4);
+        const int64_t u = p.user[b], i = p.pos[b], j = p.neg[b];
+        if ((uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
+            (uint64_t)j < (uint64_t)p.n_items) {
+            red_add_v4(p.gU0 + u * D + 4 * v, scale4(ldg4(p.U0 + u * D + 4 * v), ku));
+            red_add_v4(p.gI0 + i * D + 4 * v, scale4(ldg4(p.I0 + i * D + 4 * v), kp));
+            red_add_v4(p.gI0 + j * D + 4 * v, scale4(ldg4(p.I0 + j * D + 4 * v), kn));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Dense Adam with coupled L2 and fused zero_grad: one streaming pass, 32 B of traffic per parameter.
+// ------------------------------------------------------------------------------------------------------
+struct AdamScalars {
+    float l2, w1, beta2, w2, eps, step_size, bc2_sqrt;
+};
+
+__device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g, const AdamScalars &s) {
+    g = fmaf(s.l2, p, g);                    // grad.add(param, alpha=weight_decay)
+    m = fmaf(s.w1, g - m, m);                // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(s.w2 * g, g, v * s.beta2);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
+    p = p + (-s.step_size * m) / denom;      // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256) adam_sweep_kernel(float4 *__restrict__ P, float4 *__restrict__ M,
+                                                          float4 *__restrict__ V, float4 *__restrict__ G,
+                                                          int64_t n4, AdamScalars s, const float *dev_scalars) {
+    if (dev_scalars) {
+        s.step_size = __ldg(dev_scalars);
+        s.bc2_sqrt = __ldg(dev_scalars + 1);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 z = f4_zero();
+    for (; i + (UNROLL - 1) * stride < n4; i += UNROLL * stride) {
+        float4 p[UNROLL], m[UNROLL], v[UNROLL], g[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            p[u] = P[i + u * stride];
+            m[u] = M[i + u * stride];
+            v[u] = V[i + u * stride];
+            g[u] = G[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            adam_elem(p[u].x, m[u].x, v[u].x, g[u].x, s);
+            adam_elem(p[u].y, m[u].y, v[u].y, g[u].y, s);
+            adam_elem(p[u].z, m[u].z, v[u].z, g[u].z, s);
+            adam_elem(p[u].w, m[u].w, v[u].w, g[u].w, s);
+            P[i + u * stride] = p[u];
+            M[i + u * stride] = m[u];
+            V[i + u * stride] = v[u];
+            G[i + u * stride] = z;
+        }
+    }
+    for (; i < n4; i += stride) {
+        float4 p = P[i], m = M[i], v = V[i], g = G[i];
+        adam_elem(p.x, m.x, v.x, g.x, s);
+        adam_elem(p.y, m.y, v.y, g.y, s);
+        adam_elem(p.z, m.z, v.z, g.z, s);
+        adam_elem(p.w, m.w, v.w, g.w, s);
+        P[i] = p;
+        M[i] = m;
+        V[i] = v;
+        G[i] = z;
+    }
+}
+
+__global__ void adam_tail_kernel(float *P, float *M, float *V, float *G, int64_t from, int64_t n, AdamScalars s,
+                                 const float *dev_scalars) {
+    if (dev_scalars) {
+        s.step_size = dev_scalars[0];
+        s.bc2_sqrt = dev_scalars[1];
+    }
+    const int64_t i = from + threadIdx.x;
+    if (i < n) {
+        adam_elem(P[i], M[i], V[i], G[i], s);
+        G[i] = 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Row movement for row-sharded tables.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ T, const int64_t *idx,
+                                                           int64_t B, int D, int64_t n_rows, float *out,
+                                                           WrWorkspace *ws) {
+    const int D4 = D >> 2;
+    const int64_t total = B * D4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / D4;
+        const int v = (int)(t - b * D4);
+        const int64_t r = idx[b];
+        float4 x = f4_zero();
+        if ((uint64_t)r < (uint64_t)n_rows)
+            x = ldg4(T + r * D + 4 * v);
+        else if (v == 0)
+            atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+        reinterpret_cast<float4 *>(out)[t] = x;
+    }
+}
+
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(float *G, const int64_t *idx, int64_t B, int D,
+                                                                int64_t n_rows, const float *__restrict__ rows,
+                                                                WrWorkspace *ws) {
+    const int D4 = D >> 2;
+    const int64_t total = B * D4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / D4;
+        const int v = (int)(t - b * D4);
+        const int64_t r = idx[b];
+        if ((uint64_t)r < (uint64_t)n_rows)
+            red_add_v4(G + r * D + 4 * v, ldg4(rows + t * 4));
+        else if (v == 0)
+            atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+    }
+}
+
+static inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
+    int64_t g = (work_items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+}  // namespace wr
+
+using namespace wr;
+
+extern "C" int wr_bpr_fwd_bwd(const float *U, const float *I, const int64_t *user, const int64_t *pos,
+                              const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma,
+                              float grad_scale, float *gU, float *gI, float *loss_out, int accumulate_loss,
+                              void *ws, void *stream) {
+    if (!U || !I || !user || !pos || !neg || !gU || !gI || !loss_out || !ws) return WR_E_NULL;
+    if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(U) || !wr_aligned16(I) || !wr_aligned16(gU) || !wr_aligned16(gI)) return WR_E_ALIGN;
+    BprParams p{U, I, user, pos, neg, B, n_users, n_items, gamma, grad_scale / (float)B,
+                gU, gI, loss_out, accumulate_loss, (WrWorkspace *)ws};
+    cudaStream_t st = (cudaStream_t)stream;
+#define WR_BPR_CALL(LPR, VPL)                                                              \
+    {                                                                                      \
+        const int per_block = 8 * (32 / LPR);                                              \
+        const int grid = grid_for(B, per_block, 8 * kSMs);                                 \
+        bpr_fwd_bwd_kernel<LPR, VPL><<<grid, 256, 0, st>>>(p);                             \
+    }
+    switch (D) {
+        case 16: WR_BPR_CALL(4, 1) break;
+        case 32: WR_BPR_CALL(8, 1) break;
+        case 64: WR_BPR_CALL(16, 1) break;
+        case 128: WR_BPR_CALL(32, 1) break;
+        case 256: WR_BPR_CALL(32, 2) break;
+        default: {
+            const int grid = grid_for(B, 8, 8 * kSMs);
+            bpr_fwd_bwd_generic_kernel<<<grid, 256, 0, st>>>(p, D);
+        }
+    }
+#undef WR_BPR_CALL
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_t *user, const int64_t *pos,
+                                  const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items,
+                                  float reg_weight, float *gU0, float *gI0, float *loss_out, void *ws,
+                                  void *stream) {
+    if (!U0 || !I0 || !user || !pos || !neg || !gU0 || !gI0 || !loss_out || !ws) return WR_E_NULL;
+    if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(U0) || !wr_aligned16(I0) || !wr_aligned16(gU0) || !wr_aligned16(gI0)) return WR_E_ALIGN;
+    EmbParams p{U0, I0, user, pos, neg, B, n_users, n_items, reg_weight, gU0, gI0, loss_out, (WrWorkspace *)ws};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(B * (D / 4), 256, 4 * kSMs);
+    embloss_sumsq_kernel<<<grid, 256, 0, st>>>(p, D);
+    WR_CHECK_LAUNCH();
+    embloss_scatter_kernel<<<grid, 256, 0, st>>>(p, D);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, float l2, float beta1,
+                                float beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
+                                void *stream) {
+    if (!P || !M || !V || !G) return WR_E_NULL;
+    if (n_elems <= 0) return WR_E_SIZE;
+    if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
+    // torch evaluates 1-beta in Python double and hands the fp32 kernels the rounded value
+    AdamScalars s{l2, (float)(1.0 - (double)beta1), beta2, (float)(1.0 - (double)beta2), eps, step_size, bc2_sqrt};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n4 = n_elems >> 2;
+    if (n4 > 0) {
+        // 4 independent 16 B loads x 4 streams in flight per thread; grid sized to a whole number of waves
+        const int grid = grid_for(n4, 256 * 4, 8 * kSMs);
+        adam_sweep_kernel<4><<<grid, 256, 0, st>>>((float4 *)P, (float4 *)M, (float4 *)V, (float4 *)G, n4, s,
+                                                    dev_scalars);
+        WR_CHECK_LAUNCH();
+    }
+    if (n_elems & 3) {
+        adam_tail_kernel<<<1, 32, 0, st>>>(P, M, V, G, n4 << 2, n_elems, s, dev_scalars);
+        WR_CHECK_LAUNCH();
+    }
+    return WR_OK;
+}
+
+extern "C" int wr_gather_rows(const float *T, const int64_t *idx, int64_t B, int D, int64_t n_rows, float *out,
+                              void *ws, void *stream) {
+    if (!T || !idx || !out || !ws) return WR_E_NULL;
+    if (B < 0 || n_rows <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(T) || !wr_aligned16(out)) return WR_E_ALIGN;
+    if (B == 0) return WR_OK;
+    gather_rows_kernel<<<grid_for(B * (D / 4), 256, 8 * kSMs), 256, 0, (cudaStream_t)stream>>>(
+        T, idx, B, D, n_rows, out, (WrWorkspace *)ws);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_scatter_add_rows(float *G, const int64_t *idx, int64_t B, int D, int64_t n_rows,
+                                   const float *rows, void *ws, void *stream) {
+    if (!G || !idx || !rows || !ws) return WR_E_NULL;
+    if (B < 0 || n_rows <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(G) || !wr_aligned16(rows)) return WR_E_ALIGN;
+    if (B == 0) return WR_OK;
+    scatter_add_rows_kernel<<<grid_for(B * (D / 4), 256, 8 * kSMs), 256, 0, (cudaStream_t)stream>>>(
+        G, idx, B, D, n_rows, rows, (WrWorkspace *)ws);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}

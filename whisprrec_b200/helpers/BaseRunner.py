@@ -1,0 +1,279 @@
+"""Training / evaluation driver with the reference's interface (reference src/helpers/BaseRunner.py).
+
+Same flags, same epoch loop, same early stopping, same log lines.  Differences are all underneath:
+
+* fit():   the epoch's batches are assembled once on the host in the reference's order (the torch-global-generator
+           draws of DataLoader + RandomSampler are replayed, BaseRunner.py:188-193), uploaded once, and every
+           step is `model.predict` (fused forward+backward kernel) + `optimizer.step` (fused Adam sweep).
+           Per-step losses stay on the device and are read back once per epoch (the reference syncs every
+           step, :200).
+* evaluate(): ranks come from the fused score/mask/rank kernel and HR/NDCG from wr_metrics; the
+           [n_eval, n_items] score matrix of interface() (:242-257) is never built.
+"""
+import gc
+import logging
+import os
+from time import time
+
+import numpy as np
+import torch
+
+from ..utils import utils
+from .. import _lib
+
+
+def dataloader_draws(n, shuffle):
+    """What `iter(DataLoader(...))` takes from torch's global CPU generator (torch/utils/data/dataloader.py
+    `_base_seed`, torch/utils/data/sampler.py RandomSampler.__iter__).  Returns the epoch permutation for a
+    shuffling loader, None for a sequential one.  Keeping these draws keeps every later epoch's order equal
+    to the reference's."""
+    torch.empty((), dtype=torch.int64).random_()
+    if not shuffle:
+        return None
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g).numpy()
+
+
+class BaseRunner(object):
+    @staticmethod
+    def parse_runner_args(parser):
+        parser.add_argument('--epoch', type=int, default=200, help='Number of epochs.')
+        parser.add_argument('--check_epoch', type=int, default=1, help='Check some tensors every check_epoch.')
+        parser.add_argument('--test_epoch', type=int, default=-1,
+                            help='Print test results every test_epoch (-1 means no print).')
+        parser.add_argument('--early_stop', type=int, default=10,
+                            help='The number of epochs when dev results drop continuously.')
+        parser.add_argument('--lr', type=float, default=5e-4, help='Learning rate.')
+        parser.add_argument('--l2', type=float, default=0, help='Weight decay in optimizer.')
+        parser.add_argument('--batch_size', type=int, default=2048, help='Batch size during training.')
+        parser.add_argument('--eval_batch_size', type=int, default=2048, help='Batch size during testing.')
+        parser.add_argument('--optimizer', type=str, default='Adam', help='optimizer: SGD, Adam, Adagrad, Adadelta')
+        parser.add_argument('--num_workers', type=int, default=5,
+                            help='Number of processors when prepare batches in DataLoader')
+        parser.add_argument('--pin_memory', type=int, default=0, help='pin_memory in DataLoader')
+        parser.add_argument('--topk', type=str, default='10,20', help='The number of items recommended to each user.')
+        parser.add_argument('--metric', type=str, default='NDCG, HR', help='metrics: NDCG, RECALL')
+        return parser
+
+    @staticmethod
+    def metrics_from_ranks(gt_rank, topk, metrics):
+        """BaseRunner.py:76-88 given the rank of the ground-truth item (host, float64)."""
+        gt_rank = np.asarray(gt_rank)
+        out = dict()
+        for k in topk:
+            hit = gt_rank <= k
+            for metric in metrics:
+                key = '{}@{}'.format(metric, k)
+                name = metric.lower()
+                if name in ('hr', 'recall'):
+                    out[key] = hit.mean()
+                elif name == 'ndcg':
+                    out[key] = np.mean(hit / np.log2(gt_rank + 1))
+                elif name == 'precision':
+                    out[key] = hit.sum() / (hit.shape[0] * k)
+                else:
+                    raise ValueError('Undefined evaluation metric: {}.'.format(metric))
+        return out
+
+    @staticmethod
+    def evaluate_method(predictions, topk, metrics):
+        """BaseRunner.py:50-92: `predictions` is [n, 1 + n_candidates] with the ground truth in column 0."""
+        order = (-predictions).argsort(axis=1)
+        gt_rank = np.argwhere(order == 0)[:, 1] + 1
+        return BaseRunner.metrics_from_ranks(gt_rank, topk, metrics)
+
+    def __init__(self, args):
+        self.epoch = args.epoch
+        self.check_epoch = args.check_epoch
+        self.test_epoch = args.test_epoch
+        self.early_stop = args.early_stop
+        self.learning_rate = float(args.lr)
+        self.batch_size = args.batch_size
+        self.eval_batch_size = args.eval_batch_size
+        self.l2 = args.l2
+        self.optimizer_name = args.optimizer
+        self.num_workers = args.num_workers
+        self.pin_memory = args.pin_memory
+        self.topk = [int(x) for x in args.topk.split(',')]
+        self.metrics = [m.strip().upper() for m in args.metric.split(',')]
+        self.main_metric = '{}@{}'.format(self.metrics[0], self.topk[0])
+        self.time = None
+        self.eval_precision = getattr(args, 'eval_precision', 0)
+        self.last_epoch_stats = {}
+
+    def _check_time(self, start=False):
+        if self.time is None or start:
+            self.time = [time()] * 2
+            return self.time[0]
+        previous = self.time[1]
+        self.time[1] = time()
+        return self.time[1] - previous
+
+    def _build_optimizer(self, model):
+        logging.info('Optimizer: ' + self.optimizer_name)
+        return model.build_optimizer(self.optimizer_name, self.learning_rate, self.l2)
+
+    def train(self, data_dict):
+        """BaseRunner.py:126-178."""
+        model = data_dict['train'].model
+        main_metric_results, dev_results = list(), list()
+        self._check_time(start=True)
+        try:
+            for epoch in range(self.epoch):
+                self._check_time()
+                gc.collect()
+                torch.cuda.empty_cache()
+                loss = self.fit(data_dict['train'], epoch=epoch + 1)
+                training_time = self._check_time()
+
+                if len(model.check_list) > 0 and self.check_epoch > 0 and epoch % self.check_epoch == 0:
+                    utils.check(model.check_list)
+
+                dev_result = self.evaluate(data_dict['dev'], self.topk[:1], self.metrics)
+                dev_results.append(dev_result)
+                main_metric_results.append(dev_result[self.main_metric])
+                logging_str = 'Epoch {:<5} loss={:<.4f} [{:<3.1f} s]    dev=({})'.format(
+                    epoch + 1, loss, training_time, utils.format_metric(dev_result))
+
+                if self.test_epoch > 0 and epoch % self.test_epoch == 0:
+                    test_result = self.evaluate(data_dict['test'], self.topk[:1], self.metrics)
+                    logging_str += ' test=({})'.format(utils.format_metric(test_result))
+                testing_time = self._check_time()
+                logging_str += ' [{:<.1f} s]'.format(testing_time)
+
+                if max(main_metric_results) == main_metric_results[-1] or \
+                        (hasattr(model, 'stage') and model.stage == 1):
+                    model.save_model()
+                    logging_str += ' *'
+                logging.info(logging_str)
+
+                if self.early_stop > 0 and self.eval_termination(main_metric_results):
+                    logging.info('Early stop at %d based on dev result.' % (epoch + 1))
+                    break
+        except KeyboardInterrupt:
+            logging.info('Early stop manually')
+            exit_here = input('Exit completely without evaluation? (y/n) (default n):')
+            if exit_here.lower().startswith('y'):
+                logging.info(os.linesep + '-' * 45 + ' END: ' + utils.get_time() + ' ' + '-' * 45)
+                exit(1)
+
+        best_epoch = main_metric_results.index(max(main_metric_results))
+        logging.info(os.linesep + 'Best Iter(dev)={:>5}\t dev=({}) [{:<.1f} s] '.format(
+            best_epoch + 1, utils.format_metric(dev_results[best_epoch]), self.time[1] - self.time[0]))
+        model.load_model()
+
+    def epoch_batches(self, dataset):
+        """The epoch's (user, pos, neg) in the reference's batch order, as int64 device tensors."""
+        model = dataset.model
+        dataset.actions_before_epoch()                       # BaseRunner.py:184 (must precede the loader draws)
+        perm = dataloader_draws(len(dataset), shuffle=True)  # BaseRunner.py:188-193
+        dev = model.tables.P.device
+        cols = [dataset.data['user_id'], dataset.data['item_id'], dataset.data['neg_items']]
+        host = torch.from_numpy(np.stack([np.asarray(c, dtype=np.int64)[perm] for c in cols]))
+        return host.to(dev, non_blocking=False)
+
+    def fit(self, dataset, epoch=-1):
+        """BaseRunner.py:180-201."""
+        model = dataset.model
+        model.fuse()
+        if model.optimizer is None:
+            model.optimizer = self._build_optimizer(model)
+        if model.num_neg != 1:
+            raise NotImplementedError('the fused BPR step takes one negative per interaction (reference default)')
+        model.train()
+        t0 = time()
+        batches = self.epoch_batches(dataset)
+        t1 = time()
+        n = batches.shape[1]
+        starts = list(range(0, n, self.batch_size))
+        losses = torch.empty(len(starts), dtype=torch.float32, device=batches.device)
+        for s, lo in enumerate(starts):
+            hi = min(n, lo + self.batch_size)
+            batch = {'user_id': batches[0, lo:hi], 'pos_item': batches[1, lo:hi], 'neg_items': batches[2, lo:hi],
+                     'batch_size': hi - lo, 'phase': 'train'}
+            model.optimizer.zero_grad()
+            loss = model.predict(batch, loss_out=losses[s:s + 1])
+            loss.backward()
+            model.optimizer.step()
+        loss_host = losses.cpu().numpy()                    # one sync per epoch
+        model.tables.ws.raise_on_status()
+        self.last_epoch_stats = {'host_prep_s': t1 - t0, 'device_s': time() - t1, 'steps': len(starts), 'rows': n}
+        return np.mean(loss_host).item()
+
+    def eval_termination(self, criterion):
+        if len(criterion) > self.early_stop and utils.non_increasing(criterion[-self.early_stop:]):
+            return True
+        elif len(criterion) - criterion.index(max(criterion)) > self.early_stop:
+            return True
+        return False
+
+    def _eval_inputs(self, dataset):
+        """Device copies of the eval rows and the history CSR, cached on the dataset / model."""
+        model = dataset.model
+        t = model.fuse()
+        dev = t.P.device
+        if getattr(dataset, '_dev_rows', None) is None or dataset._dev_rows[0].device != dev:
+            dataset._dev_rows = (torch.from_numpy(np.asarray(dataset.data['user_id'], dtype=np.int64)).to(dev),
+                                 torch.from_numpy(np.asarray(dataset.data['item_id'], dtype=np.int64)).to(dev))
+        if getattr(model, '_dev_hist', None) is None or model._dev_hist[0].device != dev:
+            ptr, idx = dataset.corpus.history_csr()
+            if len(idx) == 0:
+                idx = np.zeros(1, dtype=np.int32)
+            model._dev_hist = (torch.from_numpy(ptr).to(dev), torch.from_numpy(idx).to(dev))
+        return dataset._dev_rows, model._dev_hist
+
+    def rank_topk(self, dataset, k=0):
+        """Ranks of the ground-truth items (and optionally the top-k lists) on the device."""
+        model = dataset.model
+        model.eval()
+        dataloader_draws(len(dataset), shuffle=False)        # the `_base_seed` draw of BaseRunner.py:229-234
+        if not model.test_all:
+            raise KeyError('neg_items')                      # what the reference hits with --test_all 0
+        (user, pos), (hptr, hidx) = self._eval_inputs(dataset)
+        ue, ie = model.eval_tables()
+        out = _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, k=k,
+                                  precision=self.eval_precision)
+        return out
+
+    def evaluate(self, dataset, topks, metrics):
+        """BaseRunner.py:210-216 -> {metric@k: float64}."""
+        rank = self.rank_topk(dataset)[0]
+        ws = dataset.model.tables.ws
+        for m in metrics:
+            if m.lower() not in ('hr', 'ndcg', 'recall', 'precision'):
+                raise ValueError('Undefined evaluation metric: {}.'.format(m))
+        res = _lib.metrics(rank, topks, ws).cpu().numpy()   # [2, nk] float64: HR, NDCG
+        ws.raise_on_status()
+        out = dict()
+        for i, k in enumerate(topks):
+            for metric in metrics:
+                name = metric.lower()
+                key = '{}@{}'.format(metric, k)
+                if name in ('hr', 'recall'):
+                    out[key] = res[0, i]
+                elif name == 'ndcg':
+                    out[key] = res[1, i]
+                else:
+                    out[key] = res[0, i] / k                # hits / (n * k)
+        return out
+
+    def interface(self, dataset):
+        """BaseRunner.py:218-258: the dense [n, 1 + n_items] prediction matrix (compatibility API; small data)."""
+        model = dataset.model
+        model.eval()
+        dataloader_draws(len(dataset), shuffle=False)
+        (user, pos), (hptr, hidx) = self._eval_inputs(dataset)
+        ue, ie = model.eval_tables()
+        _, target, _, _, scores = _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, scores=True)
+        scores, target = scores.cpu().numpy(), target.cpu().numpy()
+        hp, hi = dataset.corpus.history_csr()
+        if model.test_all:
+            for row, u in enumerate(dataset.data['user_id']):
+                scores[row, hi[hp[u]:hp[u + 1]]] = -np.inf
+        return np.concatenate([target[:, np.newaxis], scores], axis=1)
+
+    def print_res(self, dataset):
+        result_dict = self.evaluate(dataset, self.topk, self.metrics)
+        return '(' + utils.format_metric(result_dict) + ')'

@@ -1,0 +1,71 @@
+"""BPRMF on the fused sm_100a path (reference src/models/general/BPRMF.py).
+
+CMD example (same as the reference):
+    python main.py --model_name BPRMF --emb_size 64 --lr 1e-3 --l2 1e-6 --dataset 'ml-100k'
+"""
+import torch
+import torch.nn as nn
+
+from .. import BaseModel as _base
+from ..BaseModel import GeneralModel
+from ..init import xavier_normal_initialization
+from ... import _lib
+
+
+class BPRMF(GeneralModel):
+    reader = 'BaseReader'
+    runner = 'BaseRunner'
+    extra_log_args = ['embedding_size']
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument('--embedding_size', type=int, default=64, help='Size of embedding vectors.')
+        return GeneralModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        super().__init__(args, corpus)
+        self.emb_size = args.embedding_size
+        # Built on the CPU in this order so the torch generator is consumed exactly as BPRMF.py:35-40 does
+        # (normal_ x2 inside nn.Embedding, then xavier_normal_ x2): the initial weights are bit-identical.
+        self.user_embeddings = nn.Embedding(self.user_num, self.emb_size)
+        self.item_embeddings = nn.Embedding(self.item_num, self.emb_size)
+        self.apply(xavier_normal_initialization)
+
+    def _embedding_pair(self):
+        return self.user_embeddings, self.item_embeddings
+
+    def get_user_embedding(self, user):
+        t = self.fuse()
+        return _lib.gather_rows(t.users(t.P), user, t.ws)
+
+    def get_item_embedding(self, item):
+        t = self.fuse()
+        return _lib.gather_rows(t.items(t.P), item, t.ws)
+
+    def forward(self, user, item):
+        return self.get_user_embedding(user), self.get_item_embedding(item)
+
+    def predict(self, feed_dict, loss_out=None):
+        """BPRMF.py:69-80 + the backward of BaseRunner.py:198 in one launch; gradient lands in tables.G."""
+        t = self.fuse()
+        out = t.loss if loss_out is None else loss_out
+        _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), feed_dict['user_id'], feed_dict['pos_item'],
+                         feed_dict['neg_items'], t.users(t.G), t.items(t.G), out, t.ws)
+        return out[0].detach().as_subclass(_base.FusedLoss)
+
+    def full_predict(self, feed_dict):
+        """BPRMF.py:82-91: the dense [B, n_items] score matrix (compatibility API; the runner's evaluation
+        uses the fused rank kernel and never materialises it)."""
+        t = self.fuse()
+        user = feed_dict['user_id']
+        pos = feed_dict.get('pos_item', torch.zeros_like(user))
+        corpus_hist = self._empty_history(t)
+        return _lib.eval_rank_topk(t.users(t.P), t.items(t.P), user, pos, corpus_hist[0], corpus_hist[1], t.ws,
+                                   scores=True)[4]
+
+    def _empty_history(self, t):
+        if not hasattr(self, '_no_hist'):
+            dev = t.P.device
+            self._no_hist = (torch.zeros(self.user_num + 1, dtype=torch.int64, device=dev),
+                             torch.zeros(1, dtype=torch.int32, device=dev))
+        return self._no_hist

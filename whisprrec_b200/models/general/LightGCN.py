@@ -1,0 +1,156 @@
+"""LightGCN on the fused sm_100a path (reference src/models/general/LightGCN.py).
+
+CMD example (same as the reference):
+    python main.py --model_name LightGCN --emb_size 64 --gcn_layers 3 --lr 1e-3 --l2 1e-8 --dataset 'ml-100k'
+
+The adjacency is kept SPARSE (CSR) on the device.  The reference means to do the same but its device test
+(`self.device == 'cuda'`, LightGCN.py:114) compares a torch.device with a str, so it always densifies; the
+operator is identical, only the order of the row sums differs.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import BaseModel as _base
+from ..BaseModel import GeneralModel
+from ..init import xavier_uniform_initialization
+from ... import _lib
+
+
+def build_norm_adj_csr(n_users, n_items, train_ptr, train_idx):
+    """CSR structure of [[0, R], [R^T, 0]] plus d^-1/2 per node (LightGCN.py:54-97).
+
+    Returns (rowptr int64 [N+1], col int32 [2E], dinv fp32 [N]); rows and columns ascending.  The edge
+    weights fl32(fl32(dinv[r]*1)*dinv[c]) are filled on the device by wr_csr_norm_weights.
+    dinv = np.power(fp32(deg) + 1e-10, -0.5) is the reference's own NumPy call (:89-93), so its bits match
+    the reference on the same host.
+    """
+    U, I = int(n_users), int(n_items)
+    deg_u = np.diff(train_ptr)
+    users = np.repeat(np.arange(U, dtype=np.int64), deg_u)
+    items = train_idx.astype(np.int64)
+    order = np.lexsort((users, items))                       # item-major, users ascending inside an item
+    deg_i = np.bincount(items, minlength=I)
+    deg = np.concatenate([deg_u, deg_i])
+    rowptr = np.zeros(U + I + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = np.concatenate([U + items, users[order]]).astype(np.int32)
+    rowsum = deg.astype(np.float32) + 1e-10
+    dinv = np.power(rowsum, -0.5).astype(np.float32)
+    dinv[np.isinf(dinv)] = 0.
+    return rowptr, col, dinv
+
+
+class LightGCN(GeneralModel):
+    reader = 'BaseReader'
+    runner = 'BaseRunner'
+    extra_log_args = ['embedding_size', 'gcn_layers', 'reg_weight']
+
+    @staticmethod
+    def parse_model_args(parser):
+        parser.add_argument('--embedding_size', type=int, default=64, help='Size of embedding vectors.')
+        parser.add_argument('--gcn_layers', type=int, default=2, help='Number of LightGCN layers.')
+        parser.add_argument('--reg_weight', type=float, default=1e-05, help='The L2 regularization weight.')
+        return GeneralModel.parse_model_args(parser)
+
+    def __init__(self, args, corpus):
+        super().__init__(args, corpus)
+        self.emb_size = args.embedding_size
+        self.gcn_layers = args.gcn_layers
+        self.n_users = corpus.n_users
+        self.n_items = corpus.n_items
+        self.reg_weight = float(args.reg_weight)
+        # same construction order as LightGCN.py:45-52: the adjacency build draws nothing from torch's RNG
+        self.user_embedding = nn.Embedding(self.n_users, self.emb_size)
+        self.item_embedding = nn.Embedding(self.n_items, self.emb_size)
+        self._adj_host = build_norm_adj_csr(self.n_users, self.n_items, *corpus.train_csr())
+        self.apply(xavier_uniform_initialization)
+        self._fresh = False          # pooled tables valid for the current parameters?
+
+    def _embedding_pair(self):
+        return self.user_embedding, self.item_embedding
+
+    def _on_fused(self):
+        t = self.tables
+        dev = t.P.device
+        rowptr, col, dinv = self._adj_host
+        self.adj_rowptr = torch.from_numpy(rowptr).to(dev)
+        self.adj_col = torch.from_numpy(col).to(dev)
+        self.adj_val = torch.empty(len(col), dtype=torch.float32, device=dev)
+        _lib.csr_norm_weights(self.adj_rowptr, self.adj_col, torch.from_numpy(dinv).to(dev), self.adj_val)
+        self.pool = torch.empty_like(t.P)            # mean_k E^k
+        self.layer = [torch.empty_like(t.P), torch.empty_like(t.P)]
+        self.pool_grad = torch.zeros_like(t.P)       # dL/d(pool); re-zeroed by the last backward SpMM
+        self._fresh = False
+
+    @property
+    def norm_adj(self):
+        """The normalised adjacency as a torch sparse CSR tensor (reference attribute name)."""
+        self.fuse()
+        n = self.adj_rowptr.numel() - 1
+        return torch.sparse_csr_tensor(self.adj_rowptr, self.adj_col.long(), self.adj_val, size=(n, n))
+
+    def get_ego_embeddings(self):
+        return self.fuse().P
+
+    def _propagate(self):
+        """LightGCN.py:134-148: L SpMMs with the running layer sum (and the final /(L+1)) in their epilogue."""
+        t = self.fuse()
+        L = self.gcn_layers
+        if L == 0:
+            self.pool.copy_(t.P)
+            return
+        x = t.P
+        for k in range(1, L + 1):
+            y = self.layer[(k - 1) & 1]
+            _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, x, Y=y if k < L else None,
+                          acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
+                          acc_div=float(L + 1) if k == L else 1.0)
+            x = y
+
+    def forward(self):
+        self._propagate()
+        t = self.tables
+        return t.users(self.pool), t.items(self.pool)
+
+    def predict(self, feed_dict, loss_out=None):
+        """LightGCN.py:150-175 and its backward: propagate, BPR on pooled rows, adjoint propagation, EmbLoss."""
+        t = self.fuse()
+        out = t.loss if loss_out is None else loss_out
+        user, pos, neg = feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items']
+        L = self.gcn_layers
+        self._propagate()
+        if L == 0:
+            _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws)
+        else:
+            g = self.pool_grad
+            _lib.bpr_fwd_bwd(t.users(self.pool), t.items(self.pool), user, pos, neg, t.users(g), t.items(g), out,
+                             t.ws, grad_scale=1.0 / (L + 1))
+            # pool = 1/(L+1) sum_k A^k E0 with A symmetric  =>  dE0 = H_0,  H_L = g,  H_{k-1} = g + A H_k
+            h = g
+            for k in range(1, L + 1):
+                last = k == L
+                y = t.G if last else self.layer[(k - 1) & 1]
+                # the fused re-zeroing of g is only safe when g is not also the SpMM input (L >= 2)
+                _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, h, Y=y, add=g, zero_add=last and L > 1)
+                h = y
+            if L == 1:
+                g.zero_()
+        _lib.embloss_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws,
+                             self.reg_weight)
+        return out[0].detach().as_subclass(_base.FusedLoss)
+
+    def eval_tables(self):
+        return self.forward()
+
+    def full_predict(self, feed_dict):
+        """LightGCN.py:177-187 (compatibility API, dense output; the runner uses the fused rank kernel)."""
+        ue, ie = self.forward()
+        user = feed_dict['user_id']
+        pos = feed_dict.get('pos_item', torch.zeros_like(user))
+        dev = ue.device
+        if not hasattr(self, '_no_hist'):
+            self._no_hist = (torch.zeros(self.user_num + 1, dtype=torch.int64, device=dev),
+                             torch.zeros(1, dtype=torch.int32, device=dev))
+        return _lib.eval_rank_topk(ue, ie, user, pos, self._no_hist[0], self._no_hist[1], self.tables.ws,
+                                   scores=True)[4]
