@@ -356,7 +356,7 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
         N, nnz = lg.tables.P.shape[0], lg.adj_col.numel()
         Pb = nnz * (4 + 4 + 4 * D) + N * (4 + 4 * D)
         step_bytes = 4 * Pb + 2 * 4 * N * 4 * D + 32 * D * N + 48 * B * D + 12 * B
-        spmm = lambda: _lib.csr_spmm(lg.adj_rowptr, lg.adj_col, lg.adj_val, lg.tables.P, Y=lg.layer[0])
+        spmm = lambda: _lib.csr_spmm(lg.adj_rowptr, lg.adj_col, lg.adj_val, lg.tables.P, Y=lg.layer[0], plan=lg.adj_plan)
         smed, _ = timed(spmm, 20, flush)
         out['lightgcn_L2'] = {'interactions_per_s': B / (med * 1e-3), 'ms_per_step': med, 'nodes': N, 'nnz': nnz,
                               'algorithmic_step_gbs': step_bytes / (med * 1e-3) / 1e9,

@@ -74,11 +74,12 @@ int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_t *user, co
  * called at :199 (torch/optim/adam.py _single_tensor_adam), plus the zero_grad of :196, fused in one sweep
  * over ALL rows (dense Adam: every row moves every step).
  *   g += l2 p;  m += (1-b1)(g-m);  v = b2 v + (1-b2) g g;  p -= step_size * m / (sqrt(v)/bc2_sqrt + eps);  g = 0
- * step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are evaluated in double by the caller as torch does.
+ * step_size = lr/(1-b1^t) and bc2_sqrt = sqrt(1-b2^t) are evaluated in double by the caller as torch does;
+ * the betas are doubles because torch forms 1-beta in double before rounding it for the fp32 kernels.
  * If dev_scalars != NULL, {step_size, bc2_sqrt} are read from that device array instead (lets a captured
  * CUDA graph be replayed for later steps).
  */
-int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, float l2, float beta1, float beta2,
+int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, float l2, double beta1, double beta2,
                      float eps, float step_size, float bc2_sqrt, const float *dev_scalars, void *stream);
 
 /* ---- LightGCN propagation ------------------------------------------------------------------------------
@@ -97,9 +98,24 @@ int wr_csr_norm_weights(const int64_t *rowptr, const int32_t *col, const float *
  * zero_add != 0 clears add[r] after reading it (recycles the pooled-gradient buffer for the next step).
  * X must not alias Y / acc_out.
  */
+typedef struct wr_spmm_plan {
+    /* HOST struct of DEVICE pointers: how rows with more than long_threshold non-zeros are cut into slices so
+     * that no warp walks more than one slice (power-law graphs: a 10^6-edge item row would otherwise be the tail
+     * of every launch).  Built once per graph by the caller (whisprrec_b200/_lib.py SpmmPlan does it in NumPy). */
+    int64_t long_threshold;       /* rows with more non-zeros than this are split */
+    int64_t n_chunks, n_long;     /* number of slices, number of split rows */
+    const int32_t *chunk_row;     /* [n_chunks] row a slice belongs to */
+    const int64_t *chunk_beg;     /* [n_chunks] first edge of the slice */
+    const int32_t *chunk_len;     /* [n_chunks] edges in the slice */
+    const int32_t *chunk_slot;    /* [n_chunks] index of the split row in the slot arrays */
+    const int32_t *slot_chunks;   /* [n_long] slices per split row */
+    int32_t *slot_arrivals;       /* [n_long] zeroed; left zeroed by every call */
+    float *slot_partial;          /* [n_long, D] zeroed; left zeroed by every call */
+} wr_spmm_plan;
+
 int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D, const float *X,
                 float *Y, float *add, int zero_add, const float *acc_in, float *acc_out, float acc_div,
-                void *stream);
+                const wr_spmm_plan *host_plan /* nullable */, void *stream);
 
 /* ---- full-ranking evaluation ---------------------------------------------------------------------------
  * wr_eval_rank_topk: BPRMF.py:82-91 / LightGCN.py:177-187 (S = U[user] I^T), BaseRunner.py:238 (target

@@ -194,12 +194,20 @@ def test_csr_spmm_vs_oracle(D):
     Y = torch.empty(N, D, device=DEV)
     _lib.csr_spmm(*d, dv(X), Y=Y)
     assert_close(host(Y), ref, 'Y = A X', rtol=1e-5, atol_scale=2e-6)
+    # long rows cut into slices (three 1500-edge rows here); twice, to check the scratch is left clean
+    plan = _lib.SpmmPlan(rowptr, D, DEV, threshold=64, chunk=48)
+    assert plan.n_long >= 3 and plan.n_chunks >= 3 * 32
+    for _ in range(2):
+        Y.fill_(float('nan'))
+        _lib.csr_spmm(*d, dv(X), Y=Y, plan=plan)
+        assert_close(host(Y), ref, 'Y = A X (split rows)', rtol=1e-5, atol_scale=2e-6)
+    assert float(plan.slot_partial.abs().max()) == 0.0 and int(plan.slot_arrivals.abs().max()) == 0
     # fused epilogues: addend (+ recycle), running layer sum with the final division
     add = rng.randn(N, D).astype(np.float32)
     acc = rng.randn(N, D).astype(np.float32)
     dadd, dacc = dv(add), dv(acc)
     pool = torch.empty(N, D, device=DEV)
-    _lib.csr_spmm(*d, dv(X), Y=Y, add=dadd, zero_add=True, acc_in=dacc, acc_out=pool, acc_div=3.0)
+    _lib.csr_spmm(*d, dv(X), Y=Y, add=dadd, zero_add=True, acc_in=dacc, acc_out=pool, acc_div=3.0, plan=plan)
     assert_close(host(Y), ref + add, 'Y = A X + add', rtol=1e-5, atol_scale=2e-6)
     assert_close(host(pool), (acc + ref + add) / np.float32(3.0), 'pool', rtol=1e-5, atol_scale=2e-6)
     assert float(dadd.abs().max()) == 0.0

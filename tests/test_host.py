@@ -185,3 +185,21 @@ def test_early_stop_rule():
     assert not r.eval_termination([0.1] * 5)
     assert r.eval_termination([0.5] + [0.4] * 10)                  # best is more than early_stop epochs old
     assert r.eval_termination(list(np.linspace(1.0, 0.0, 11)))     # non-increasing for early_stop epochs
+
+
+def test_spmm_plan_slices_tile_the_long_rows_exactly():
+    rng = np.random.RandomState(1)
+    deg = rng.poisson(20, size=500)
+    deg[[3, 77, 400]] = [129, 1000, 4097]
+    rowptr = np.zeros(501, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    plan = _lib.SpmmPlan(rowptr, 64, 'cpu', threshold=128, chunk=128)
+    assert plan.n_long == 3 and plan.n_chunks == 2 + 8 + 33
+    row, beg, ln, slot = (x.numpy() for x in (plan.chunk_row, plan.chunk_beg, plan.chunk_len, plan.chunk_slot))
+    assert (plan.slot_chunks.numpy() == [2, 8, 33]).all()
+    for s, r in enumerate([3, 77, 400]):
+        sel = slot == s
+        assert (row[sel] == r).all()
+        assert beg[sel][0] == rowptr[r] and (beg[sel][1:] == beg[sel][:-1] + ln[sel][:-1]).all()
+        assert beg[sel][-1] + ln[sel][-1] == rowptr[r + 1] and ln[sel].max() <= 128 and ln[sel].min() >= 1
+    assert _lib.SpmmPlan(rowptr, 64, 'cpu', threshold=10_000).ref() is None      # nothing to split

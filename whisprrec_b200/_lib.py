@@ -16,6 +16,7 @@ CSRC = os.path.join(_HERE, 'csrc')
 
 _c = ctypes
 _p, _i64, _int, _f32, _sz = _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_size_t
+_f64 = _c.c_double
 
 # name -> (restype, argtypes); must list every symbol include/whisprrec_b200.h declares
 SIGNATURES = {
@@ -26,9 +27,9 @@ SIGNATURES = {
     'wr_status': (_int, [_p, _c.POINTER(_c.c_uint32), _p]),
     'wr_bpr_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _p, _p, _p, _int, _p, _p]),
     'wr_embloss_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _p, _p, _p, _p, _p]),
-    'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _p, _p]),
+    'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f64, _f64, _f32, _f32, _f32, _p, _p]),
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
-    'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p]),
+    'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
                                  _p]),
     'wr_metrics': (_int, [_p, _i64, _c.POINTER(_int), _int, _p, _p, _p]),
@@ -153,11 +154,58 @@ def csr_norm_weights(rowptr, col, dinv, val):
                                      ptr(val, F32), stream_ptr()))
 
 
-def csr_spmm(rowptr, col, val, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None, acc_div=1.0):
+class _PlanStruct(ctypes.Structure):
+    """Mirror of `wr_spmm_plan` (include/whisprrec_b200.h)."""
+    _fields_ = [('long_threshold', _i64), ('n_chunks', _i64), ('n_long', _i64),
+                ('chunk_row', _p), ('chunk_beg', _p), ('chunk_len', _p), ('chunk_slot', _p), ('slot_chunks', _p),
+                ('slot_arrivals', _p), ('slot_partial', _p)]
+
+
+class SpmmPlan:
+    """Slices of the rows with more than `threshold` non-zeros, so that no warp walks more than `chunk` edges.
+
+    Built once per graph from the host row pointers (vectorised NumPy, O(rows)); the device arrays and the
+    zeroed scratch live as long as the plan does.
+    """
+
+    def __init__(self, rowptr_host, D, device, threshold=128, chunk=128):
+        import numpy as np
+        deg = np.diff(rowptr_host)
+        long_rows = np.nonzero(deg > threshold)[0]
+        self.threshold, self.chunk, self.n_long = int(threshold), int(chunk), int(len(long_rows))
+        per_row = (deg[long_rows] + chunk - 1) // chunk
+        self.n_chunks = int(per_row.sum())
+        self.struct = None
+        if self.n_chunks == 0:
+            return
+        slot = np.repeat(np.arange(self.n_long, dtype=np.int32), per_row)
+        first = np.zeros(self.n_long, dtype=np.int64)
+        np.cumsum(per_row[:-1], out=first[1:])
+        k = np.arange(self.n_chunks, dtype=np.int64) - first[slot]          # slice number inside its row
+        beg = rowptr_host[long_rows][slot] + k * chunk
+        length = np.minimum(chunk, rowptr_host[long_rows + 1][slot] - beg)
+        # longest-first over slots keeps the last wave short
+        to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(device)
+        self.chunk_row, self.chunk_beg = to(long_rows[slot], np.int32), to(beg, np.int64)
+        self.chunk_len, self.chunk_slot = to(length, np.int32), to(slot, np.int32)
+        self.slot_chunks = to(per_row, np.int32)
+        self.slot_arrivals = torch.zeros(self.n_long, dtype=I32, device=device)
+        self.slot_partial = torch.zeros((self.n_long, D), dtype=F32, device=device)
+        self.struct = _PlanStruct(self.threshold, self.n_chunks, self.n_long, self.chunk_row.data_ptr(),
+                                  self.chunk_beg.data_ptr(), self.chunk_len.data_ptr(), self.chunk_slot.data_ptr(),
+                                  self.slot_chunks.data_ptr(), self.slot_arrivals.data_ptr(),
+                                  self.slot_partial.data_ptr())
+
+    def ref(self):
+        return None if self.struct is None else ctypes.addressof(self.struct)
+
+
+def csr_spmm(rowptr, col, val, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None, acc_div=1.0,
+             plan=None):
     N, D = X.shape
     check(load().wr_csr_spmm(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), N, D, ptr(X, F32), ptr(Y, F32),
                              ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32), acc_div,
-                             stream_ptr()))
+                             None if plan is None else plan.ref(), stream_ptr()))
 
 
 def eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k=0, precision=0, scores=False):

@@ -16,81 +16,132 @@ struct SpmmParams {
     const float *acc_in;
     float *acc_out;
     float acc_div;
+    wr_spmm_plan plan;       // by value; long_threshold = INT64_MAX when there is no plan
+    int row_blocks;          // CTAs [0, row_blocks) walk rows, the rest walk the chunks of split rows
 };
 
-// A warp owns a row.  The row of D = 4*LPR*VPL floats is covered by LPR lanes, so 32/LPR neighbour rows are
-// fetched per step (one 128-bit load per lane each), UNROLL steps in flight.  Column ids / weights are read
-// 32 at a time, coalesced, and handed round with shuffles.
+// acc += sum_{e in [beg, end)} val[e] * X[col[e]] for the lane's slice of the row (partial over lane groups).
+template <int LPR, int VPL, int UNROLL>
+__device__ __forceinline__ void spmm_accumulate(const SpmmParams &p, int64_t beg, int64_t end, int lane, int sub,
+                                                int grp, float4 (&acc)[VPL]) {
+    using RG = RowGroup<LPR, VPL>;
+    constexpr int D = RG::D;
+    constexpr int EPS = RG::GROUPS;  // edges per step
+    for (int64_t base = beg; base < end; base += 32) {
+        const int cnt = (int)min((int64_t)32, end - base);
+        int c = 0;
+        float w = 0.f;
+        if (lane < cnt) {
+            c = __ldg(p.col + base + lane);
+            w = __ldg(p.val + base + lane);
+        }
+        for (int j = 0; j < cnt; j += EPS * UNROLL) {
+            float4 x[UNROLL][VPL];
+            float ww[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const int e = j + u * EPS + grp;
+                const int cc = __shfl_sync(0xffffffffu, c, e & 31);
+                ww[u] = __shfl_sync(0xffffffffu, w, e & 31);
+                if (e < cnt) {
+                    RG::load(p.X + (int64_t)cc * D, sub, x[u]);
+                } else {
+                    RG::zero(x[u]);
+                    ww[u] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) acc[v] = fma4(ww[u], x[u][v], acc[v]);
+        }
+    }
+    // fold the 32/LPR partial rows held by the lane groups
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
+            acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
+            acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
+            acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+        }
+}
+
+// y (+ add) -> Y, running layer sum / mean.  Called by the lanes of group 0 with their slice of the finished row.
+__device__ __forceinline__ void spmm_row_epilogue(const SpmmParams &p, int64_t off, float4 y) {
+    if (p.add) {
+        float4 *ap = reinterpret_cast<float4 *>(p.add + off);
+        y = add4(y, *ap);
+        if (p.zero_add) *ap = f4_zero();
+    }
+    if (p.Y) *reinterpret_cast<float4 *>(p.Y + off) = y;
+    if (p.acc_out) {
+        const float4 a = add4(*reinterpret_cast<const float4 *>(p.acc_in + off), y);
+        // ATen's mean is sum().div_(count): a true division, not a multiply by the reciprocal
+        *reinterpret_cast<float4 *>(p.acc_out + off) =
+            p.acc_div == 1.0f ? a : make_float4(a.x / p.acc_div, a.y / p.acc_div, a.z / p.acc_div, a.w / p.acc_div);
+    }
+}
+
+// A warp owns a row (or, for rows longer than plan.long_threshold, one <= chunk-sized slice of it).  The row of
+// D = 4*LPR*VPL floats is covered by LPR lanes, so 32/LPR neighbour rows are fetched per step (one 128-bit load per
+// lane each), UNROLL steps in flight.  Column ids / weights are read 32 at a time, coalesced, and handed round
+// with shuffles.  Slices of a split row are reduced into plan.slot_partial with 128-bit REDs; the warp that
+// arrives last owns the row's epilogue, so one launch covers everything and power-law rows cannot become the tail.
 template <int LPR, int VPL, int UNROLL>
 __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParams p) {
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
-    constexpr int EPS = RG::GROUPS;  // edges per step
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t row = warp; row < p.N; row += nwarps) {
-        const int64_t beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
-        float4 acc[VPL];
-        RG::zero(acc);
-        for (int64_t base = beg; base < end; base += 32) {
-            const int cnt = (int)min((int64_t)32, end - base);
-            int c = 0;
-            float w = 0.f;
-            if (lane < cnt) {
-                c = __ldg(p.col + base + lane);
-                w = __ldg(p.val + base + lane);
-            }
-            for (int j = 0; j < cnt; j += EPS * UNROLL) {
-                float4 x[UNROLL][VPL];
-                float ww[UNROLL];
+    if ((int)blockIdx.x < p.row_blocks) {
+        const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int64_t nwarps = (int64_t)p.row_blocks * (blockDim.x >> 5);
+        for (int64_t row = warp; row < p.N; row += nwarps) {
+            const int64_t beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
+            if (end - beg > p.plan.long_threshold) continue;      // split rows are handled below
+            float4 acc[VPL];
+            RG::zero(acc);
+            spmm_accumulate<LPR, VPL, UNROLL>(p, beg, end, lane, sub, grp, acc);
+            if (grp == 0) {
 #pragma unroll
-                for (int u = 0; u < UNROLL; ++u) {
-                    const int e = j + u * EPS + grp;
-                    const int cc = __shfl_sync(0xffffffffu, c, e & 31);
-                    ww[u] = __shfl_sync(0xffffffffu, w, e & 31);
-                    if (e < cnt) {
-                        RG::load(p.X + (int64_t)cc * D, sub, x[u]);
-                    } else {
-                        RG::zero(x[u]);
-                        ww[u] = 0.f;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-                    for (int v = 0; v < VPL; ++v) acc[v] = fma4(ww[u], x[u][v], acc[v]);
+                for (int v = 0; v < VPL; ++v) spmm_row_epilogue(p, row * D + 4 * (sub + v * LPR), acc[v]);
             }
         }
-        // fold the 32/LPR partial rows held by the lane groups
+    } else {
+        const int64_t warp = (int64_t)(blockIdx.x - p.row_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int64_t nwarps = (int64_t)(gridDim.x - p.row_blocks) * (blockDim.x >> 5);
+        for (int64_t ch = warp; ch < p.plan.n_chunks; ch += nwarps) {
+            const int64_t beg = __ldg(p.plan.chunk_beg + ch);
+            const int64_t end = beg + __ldg(p.plan.chunk_len + ch);
+            const int slot = __ldg(p.plan.chunk_slot + ch);
+            float4 acc[VPL];
+            RG::zero(acc);
+            spmm_accumulate<LPR, VPL, UNROLL>(p, beg, end, lane, sub, grp, acc);
+            float *part = p.plan.slot_partial + (int64_t)slot * D;
+            if (grp == 0) {
 #pragma unroll
-        for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                acc[v].x += __shfl_xor_sync(0xffffffffu, acc[v].x, o);
-                acc[v].y += __shfl_xor_sync(0xffffffffu, acc[v].y, o);
-                acc[v].z += __shfl_xor_sync(0xffffffffu, acc[v].z, o);
-                acc[v].w += __shfl_xor_sync(0xffffffffu, acc[v].w, o);
+                for (int v = 0; v < VPL; ++v) red_add_v4(part + 4 * (sub + v * LPR), acc[v]);
             }
-        if (grp == 0) {
+            // last slice to arrive finishes the row
+            __threadfence();
+            __syncwarp();
+            int prev = 0;
+            if (lane == 0) prev = atomicAdd(p.plan.slot_arrivals + slot, 1);
+            prev = __shfl_sync(0xffffffffu, prev, 0);
+            if (prev == __ldg(p.plan.slot_chunks + slot) - 1) {
+                __threadfence();
+                const int64_t row = __ldg(p.plan.chunk_row + ch);
+                if (grp == 0) {
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-                const int64_t off = row * D + 4 * (sub + v * LPR);
-                float4 y = acc[v];
-                if (p.add) {
-                    float4 *ap = reinterpret_cast<float4 *>(p.add + off);
-                    y = add4(y, *ap);
-                    if (p.zero_add) *ap = f4_zero();
+                    for (int v = 0; v < VPL; ++v) {
+                        float4 *pp = reinterpret_cast<float4 *>(part + 4 * (sub + v * LPR));
+                        const float4 y = __ldcg(pp);
+                        __stcg(pp, f4_zero());                   // scratch and counter are left ready for reuse
+                        spmm_row_epilogue(p, row * D + 4 * (sub + v * LPR), y);
+                    }
                 }
-                if (p.Y) *reinterpret_cast<float4 *>(p.Y + off) = y;
-                if (p.acc_out) {
-                    const float4 a = add4(*reinterpret_cast<const float4 *>(p.acc_in + off), y);
-                    // ATen's mean is sum().div_(count): a true division, not a multiply by the reciprocal
-                    *reinterpret_cast<float4 *>(p.acc_out + off) =
-                        p.acc_div == 1.0f ? a
-                                          : make_float4(a.x / p.acc_div, a.y / p.acc_div, a.z / p.acc_div,
-                                                        a.w / p.acc_div);
-                }
+                if (lane == 0) p.plan.slot_arrivals[slot] = 0;
             }
         }
     }
@@ -108,20 +159,7 @@ __global__ void __launch_bounds__(256) csr_spmm_generic_kernel(SpmmParams p, int
             float4 acc = f4_zero();
             for (int64_t e = beg; e < end; ++e)
                 acc = fma4(__ldg(p.val + e), ldg4(p.X + (int64_t)__ldg(p.col + e) * D + 4 * v), acc);
-            const int64_t off = row * D + 4 * v;
-            if (p.add) {
-                float4 *ap = reinterpret_cast<float4 *>(p.add + off);
-                acc = add4(acc, *ap);
-                if (p.zero_add) *ap = f4_zero();
-            }
-            if (p.Y) *reinterpret_cast<float4 *>(p.Y + off) = acc;
-            if (p.acc_out) {
-                const float4 a = add4(*reinterpret_cast<const float4 *>(p.acc_in + off), acc);
-                *reinterpret_cast<float4 *>(p.acc_out + off) =
-                    p.acc_div == 1.0f
-                        ? a
-                        : make_float4(a.x / p.acc_div, a.y / p.acc_div, a.z / p.acc_div, a.w / p.acc_div);
-            }
+            spmm_row_epilogue(p, row * D + 4 * v, acc);
         }
     }
 }
@@ -147,7 +185,7 @@ using namespace wr;
 
 extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D,
                            const float *X, float *Y, float *add, int zero_add, const float *acc_in,
-                           float *acc_out, float acc_div, void *stream) {
+                           float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream) {
     if (!rowptr || !col || !val || !X) return WR_E_NULL;
     if (!Y && !acc_out) return WR_E_NULL;
     if (acc_out && !acc_in) return WR_E_NULL;
@@ -157,18 +195,31 @@ extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const floa
         (acc_in && !wr_aligned16(acc_in)) || (acc_out && !wr_aligned16(acc_out)))
         return WR_E_ALIGN;
     if (X == Y || X == acc_out) return WR_E_SIZE;
-    SpmmParams p{rowptr, col, val, N, X, Y, add, zero_add, acc_in, acc_out, acc_div};
+    SpmmParams p{rowptr, col, val, N, X, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0};
+    p.plan.long_threshold = INT64_MAX;
+    const bool fast = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
+    if (host_plan && fast && host_plan->n_chunks > 0) {
+        const wr_spmm_plan &q = *host_plan;
+        if (!q.chunk_row || !q.chunk_beg || !q.chunk_len || !q.chunk_slot || !q.slot_chunks || !q.slot_arrivals ||
+            !q.slot_partial)
+            return WR_E_NULL;
+        if (q.long_threshold < 1 || q.n_long < 1 || !wr_aligned16(q.slot_partial)) return WR_E_SIZE;
+        p.plan = q;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int64_t g = (N + 7) / 8;
     if (g > 16 * kSMs) g = 16 * kSMs;
-    const int grid = (int)g;
+    p.row_blocks = (int)g;
+    int64_t gc = (p.plan.n_chunks + 7) / 8;
+    if (gc > 16 * kSMs) gc = 16 * kSMs;
+    const int grid = (int)(g + gc);
     switch (D) {
         case 16: csr_spmm_kernel<4, 1, 2><<<grid, 256, 0, st>>>(p); break;
         case 32: csr_spmm_kernel<8, 1, 2><<<grid, 256, 0, st>>>(p); break;
-        case 64: csr_spmm_kernel<16, 1, 4><<<grid, 256, 0, st>>>(p); break;
+        case 64: csr_spmm_kernel<16, 1, 8><<<grid, 256, 0, st>>>(p); break;
         case 128: csr_spmm_kernel<32, 1, 4><<<grid, 256, 0, st>>>(p); break;
         case 256: csr_spmm_kernel<32, 2, 2><<<grid, 256, 0, st>>>(p); break;
-        default: csr_spmm_generic_kernel<<<grid, 256, 0, st>>>(p, D);
+        default: csr_spmm_generic_kernel<<<p.row_blocks, 256, 0, st>>>(p, D);
     }
     WR_CHECK_LAUNCH();
     return WR_OK;

@@ -392,21 +392,29 @@ extern "C" int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_
     return WR_OK;
 }
 
-extern "C" int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, float l2, float beta1,
-                                float beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
+extern "C" int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, float l2, double beta1,
+                                double beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
                                 void *stream) {
     if (!P || !M || !V || !G) return WR_E_NULL;
     if (n_elems <= 0) return WR_E_SIZE;
     if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
     // torch evaluates 1-beta in Python double and hands the fp32 kernels the rounded value
-    AdamScalars s{l2, (float)(1.0 - (double)beta1), beta2, (float)(1.0 - (double)beta2), eps, step_size, bc2_sqrt};
+    AdamScalars s{l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, bc2_sqrt};
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n4 = n_elems >> 2;
     if (n4 > 0) {
-        // 4 independent 16 B loads x 4 streams in flight per thread; grid sized to a whole number of waves
-        const int grid = grid_for(n4, 256 * 4, 8 * kSMs);
-        adam_sweep_kernel<4><<<grid, 256, 0, st>>>((float4 *)P, (float4 *)M, (float4 *)V, (float4 *)G, n4, s,
-                                                    dev_scalars);
+        // Large tables: 4 independent 16 B loads x 4 arrays in flight per thread, 2 CTAs/SM, whole waves.
+        // Small (cache-sized) tables are latency-bound: one float4 per array per thread, as many CTAs as it takes,
+        // so that every load of the sweep is issued in the first microsecond.
+        if (n4 >= (int64_t)8 * kSMs * 256 * 4) {
+            const int grid = grid_for(n4, 256 * 4, 8 * kSMs);
+            adam_sweep_kernel<4><<<grid, 256, 0, st>>>((float4 *)P, (float4 *)M, (float4 *)V, (float4 *)G, n4, s,
+                                                        dev_scalars);
+        } else {
+            const int grid = grid_for(n4, 256, 8 * kSMs);
+            adam_sweep_kernel<1><<<grid, 256, 0, st>>>((float4 *)P, (float4 *)M, (float4 *)V, (float4 *)G, n4, s,
+                                                        dev_scalars);
+        }
         WR_CHECK_LAUNCH();
     }
     if (n_elems & 3) {

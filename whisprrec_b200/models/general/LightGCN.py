@@ -78,6 +78,7 @@ class LightGCN(GeneralModel):
         self.adj_col = torch.from_numpy(col).to(dev)
         self.adj_val = torch.empty(len(col), dtype=torch.float32, device=dev)
         _lib.csr_norm_weights(self.adj_rowptr, self.adj_col, torch.from_numpy(dinv).to(dev), self.adj_val)
+        self.adj_plan = _lib.SpmmPlan(rowptr, t.D, dev)     # slices of the long (popular-item) rows
         self.pool = torch.empty_like(t.P)            # mean_k E^k
         self.layer = [torch.empty_like(t.P), torch.empty_like(t.P)]
         self.pool_grad = torch.zeros_like(t.P)       # dL/d(pool); re-zeroed by the last backward SpMM
@@ -105,7 +106,7 @@ class LightGCN(GeneralModel):
             y = self.layer[(k - 1) & 1]
             _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, x, Y=y if k < L else None,
                           acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
-                          acc_div=float(L + 1) if k == L else 1.0)
+                          acc_div=float(L + 1) if k == L else 1.0, plan=self.adj_plan)
             x = y
 
     def forward(self):
@@ -132,7 +133,8 @@ class LightGCN(GeneralModel):
                 last = k == L
                 y = t.G if last else self.layer[(k - 1) & 1]
                 # the fused re-zeroing of g is only safe when g is not also the SpMM input (L >= 2)
-                _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, h, Y=y, add=g, zero_add=last and L > 1)
+                _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, h, Y=y, add=g, zero_add=last and L > 1,
+                              plan=self.adj_plan)
                 h = y
             if L == 1:
                 g.zero_()
