@@ -128,12 +128,18 @@ int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int
  * scores_out: optional dense fp32 [R, n_items] copy of S, unmasked -- what full_predict returns; NULL on the
  *             fast path (the point of the fusion is not to write it).
  * precision 0: fp32 FMA chains over d = 0..D-1 for every score (target included), so comparisons are
- * consistent.  precision 1: bf16 operands on the tcgen05 tensor cores, fp32 accumulation (looser parity).
+ * consistent.  precision 1: bf16 operands on the tcgen05 tensor cores (TMA-fed, TMEM accumulators), fp32
+ * accumulation; D in {64, 128}; ranks only (topk_idx must be NULL); needs `scratch`; looser parity (operands are
+ * rounded to bf16, the target's own column is excluded explicitly).
  */
 int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                       int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
                       int k, int precision, int32_t *topk_idx, float *topk_val, int32_t *rank, float *target,
-                      float *scores_out, void *ws, void *stream);
+                      float *scores_out, void *scratch, void *ws, void *stream);
+
+/* Bytes of 1024-byte-aligned device scratch wr_eval_rank_topk needs for `precision` (0 for precision 0): the bf16
+ * copies of the gathered user rows and of the item table that the TMA descriptors point at. */
+size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int precision);
 
 /* wr_metrics: BaseRunner.evaluate_method (BaseRunner.py:76-88) from the ranks; float64 means.
  *   hr[i] = mean(rank <= ks[i]);  ndcg[i] = mean((rank <= ks[i]) / log2(rank + 1))

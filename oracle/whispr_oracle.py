@@ -314,6 +314,16 @@ def full_scores(Uemb, Iemb, user):
     return torch.matmul(_t(Uemb).index_select(0, _t(user, torch.int64)), _t(Iemb).t())
 
 
+def bf16_round(x):
+    """fp32 -> bf16 (round to nearest even) -> fp32: the operand rounding of the tensor-core scoring mode."""
+    return _t(x).to(torch.float32).bfloat16().float()
+
+
+def full_scores_bf16(Uemb, Iemb, user):
+    """Scores of the bf16 scoring mode: bf16-rounded operands, products and sums in fp32."""
+    return torch.matmul(bf16_round(Uemb).index_select(0, _t(user, torch.int64)), bf16_round(Iemb).t())
+
+
 def history_csr(n_users, train_pairs, residual_pairs):
     """Sorted union of train and residual (dev+test) items per user as CSR (BaseRunner.py:246-255)."""
     allp = np.concatenate([np.asarray(train_pairs, dtype=np.int64).reshape(-1, 2),

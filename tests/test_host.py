@@ -51,8 +51,10 @@ def test_argument_errors_need_no_gpu():
     assert lib.wr_bpr_fwd_bwd(16, 16, 16, 16, 16, 8, 6, 4, 4, 1e-10, 1.0, 16, 16, 16, 0, 16, None) == -3   # D=6
     assert lib.wr_bpr_fwd_bwd(16, 16, 16, 16, 16, 0, 8, 4, 4, 1e-10, 1.0, 16, 16, 16, 0, 16, None) == -2   # B=0
     assert lib.wr_bpr_fwd_bwd(16, 20, 16, 16, 16, 8, 8, 4, 4, 1e-10, 1.0, 16, 16, 16, 0, 16, None) == -5   # align
-    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 33, 0, 16, 16, 16, 16, None, 16, None) == -4
-    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 0, 7, None, None, 16, 16, None, 16, None) == -6
+    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 33, 0, 16, 16, 16, 16, None, None, 16, None) == -4
+    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 0, 7, None, None, 16, 16, None, None, 16, None) == -6
+    assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 32, 16, 16, 0, 1, None, None, 16, 16, None, 1024, 16, None) == -3   # tensor-core path: D in {64,128}
+    assert lib.wr_eval_scratch_bytes(1000, 5000, 64, 0) == 0 and lib.wr_eval_scratch_bytes(1000, 5000, 64, 1) >= (1000 + 5000) * 128
 
 
 def test_product_refuses_cpu_tensors():

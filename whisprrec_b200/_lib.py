@@ -31,7 +31,8 @@ SIGNATURES = {
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
     'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
-                                 _p]),
+                                 _p, _p]),
+    'wr_eval_scratch_bytes': (_sz, [_i64, _i64, _int, _int]),
     'wr_metrics': (_int, [_p, _i64, _c.POINTER(_int), _int, _p, _p, _p]),
     'wr_gather_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
     'wr_scatter_add_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
@@ -218,10 +219,17 @@ def eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k=0, precision
     tki = torch.empty((R, k), dtype=I32, device=dev) if k > 0 else None
     tkv = torch.empty((R, k), dtype=F32, device=dev) if k > 0 else None
     sc = torch.empty((R, Iemb.shape[0]), dtype=F32, device=dev) if scores else None
+    nbytes = load().wr_eval_scratch_bytes(R, Iemb.shape[0], D, precision)
+    scratch = None
+    if nbytes:
+        scratch = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-scratch.data_ptr()) % 1024
+        scratch = scratch[off:off + nbytes]
     check(load().wr_eval_rank_topk(ptr(Uemb, F32), ptr(Iemb, F32), ptr(user, I64), ptr(pos, I64), R,
                                    Uemb.shape[0], Iemb.shape[0], D, ptr(hist_ptr, I64), ptr(hist_idx, I32),
                                    k, precision, ptr(tki, I32), ptr(tkv, F32), ptr(rank, I32), ptr(target, F32),
-                                   ptr(sc, F32), ws.ptr, stream_ptr()))
+                                   ptr(sc, F32), None if scratch is None else scratch.data_ptr(), ws.ptr,
+                                   stream_ptr()))
     return rank, target, tki, tkv, sc
 
 

@@ -314,19 +314,30 @@ static int launch_eval(EvalParams &p, cudaStream_t st, int row_tiles) {
 
 using namespace wr;
 
+// eval_tcgen05.cu
+int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
+                    int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
+                    int32_t *rank, float *target, float *scores_out, void *scratch, WrWorkspace *ws, cudaStream_t st);
+
 extern "C" int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos,
                                  int64_t R, int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr,
                                  const int32_t *hist_idx, int k, int precision, int32_t *topk_idx, float *topk_val,
-                                 int32_t *rank, float *target, float *scores_out, void *ws, void *stream) {
+                                 int32_t *rank, float *target, float *scores_out, void *scratch, void *ws,
+                                 void *stream) {
     if (!Uemb || !Iemb || !user || !pos || !hist_ptr || !hist_idx || !rank || !target || !ws) return WR_E_NULL;
     if ((topk_idx == nullptr) != (topk_val == nullptr)) return WR_E_NULL;
     if (R <= 0 || n_users <= 0 || n_items <= 0 || n_items > INT32_MAX) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
     if (topk_idx && (k < 1 || k > EV_KMAX)) return WR_E_TOPK;
     if (!wr_aligned16(Uemb) || !wr_aligned16(Iemb)) return WR_E_ALIGN;
-    if (precision != 0) return WR_E_PRECISION;
     cudaStream_t st = (cudaStream_t)stream;
     const bool topk = topk_idx != nullptr;
+    if (precision == 1) {
+        if (topk) return WR_E_PRECISION;      // top-k lists come from the fp32 path
+        return wr_eval_rank_tc(Uemb, Iemb, user, pos, R, n_users, n_items, D, hist_ptr, hist_idx, rank, target,
+                               scores_out, scratch, (WrWorkspace *)ws, st);
+    }
+    if (precision != 0) return WR_E_PRECISION;
     EvalParams p{Uemb, Iemb, user, pos, R, n_users, n_items, hist_ptr, hist_idx, topk ? k : 1,
                  topk_idx, topk_val, rank, target, scores_out, 1, 0, 0, (WrWorkspace *)ws};
     p.n_tiles = (int)((n_items + EV_TI - 1) / EV_TI);

@@ -1,0 +1,433 @@
+// Full-ranking evaluation on the 5th-generation tensor cores (precision = 1).
+//
+//   S[128 x 256 tile] = U_bf16[rows, D] . I_bf16[items, D]^T     tcgen05.mma, cta_group::1, M=128 N=256 K=16,
+//                                                                fp32 accumulators in TMEM (2 x 256 columns)
+// A CTA owns 128 eval rows and walks the item tiles in ascending order.  Warp roles:
+//   warp 0      TMA producer  (A once, then a ring of B stages; SWIZZLE_128B boxes of 64 bf16 = 128 B rows)
+//   warp 1      MMA issuer    (one elected lane; smem descriptors advanced 32 B per K=16 step)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4-11  epilogue: tcgen05.ld 32 columns at a time, history mask from the sorted per-user CSR (one cursor
+//               per row, the tiles arrive in item order), count of items beating the target -- while the MMA of
+//               the next tile fills the other accumulator.  The score matrix never leaves TMEM.
+// Operands are rounded to bf16 once per evaluation (pack kernels below); the target score is the fp32 FMA chain
+// over the same bf16-rounded operands.  Parity with the fp32 path is therefore "looser": see tests.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace wr {
+
+struct TcParams {
+    const int64_t *user, *pos;
+    int64_t R, n_users, n_items;
+    const int64_t *hist_ptr;
+    const int32_t *hist_idx;
+    const float *target;        // [R] target scores (written by pack_users_kernel)
+    const uint8_t *row_ok;      // [R] 1 if the row's ids were in range
+    int32_t *rank;
+    float *scores;              // optional dense [R, n_items] dump of the tensor-core scores (tests)
+    int splits, tiles_per_split, n_tiles;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
+    const uint32_t addr = smem_u32(smem);
+    uint64_t d = (uint64_t)((addr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+    d |= (uint64_t)(1024u >> 4) << 32;                  // stride byte offset, bits [32,46)
+    d |= 1ull << 46;                                    // descriptor version (Blackwell)
+    d |= 2ull << 61;                                    // layout: SWIZZLE_128B
+    return d;
+}
+// kind::f16, A = B = bf16, D = fp32, both K-major, M x N as given.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// operand packing: fp32 tables -> bf16 (round to nearest even), eval rows gathered, target scores
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_items_bf16_kernel(const float *__restrict__ I, int64_t n4, __nv_bfloat16 *out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (int64_t)gridDim.x * blockDim.x) {
+        const float4 x = ldg4(I + 4 * t);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t *>(&lo);
+        o.y = *reinterpret_cast<uint32_t *>(&hi);
+        reinterpret_cast<uint2 *>(out)[t] = o;
+    }
+}
+
+// one warp per eval row: A[r] = bf16(U[user_r]); target[r] = sum_d bf16(U[u,d]) * bf16(I[pos,d]) (fp32 FMA chain)
+__global__ void __launch_bounds__(256) pack_users_kernel(const float *__restrict__ U, const float *__restrict__ I,
+                                                          const int64_t *user, const int64_t *pos, int64_t R,
+                                                          int64_t n_users, int64_t n_items, int D, __nv_bfloat16 *A,
+                                                          float *target, uint8_t *row_ok, WrWorkspace *ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const int64_t u = user[r], it = pos[r];
+        const bool ok = (uint64_t)u < (uint64_t)n_users && (uint64_t)it < (uint64_t)n_items;
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            float a = 0.f, b = 0.f;
+            if (ok) {
+                a = __bfloat162float(__float2bfloat16_rn(U[u * D + d]));
+                b = __bfloat162float(__float2bfloat16_rn(I[it * D + d]));
+            }
+            A[r * D + d] = __float2bfloat16_rn(a);
+            s = fmaf(a, b, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            target[r] = s;
+            row_ok[r] = ok ? 1 : 0;
+            if (!ok) atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the scoring kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128, TC_BN = 256, TC_THREADS = 384;
+
+template <int D>
+struct TcCfg {
+    static constexpr int KB = D / 64;                      // 64-element (128 B) K blocks
+    static constexpr int A_BYTES = TC_BM * D * 2;
+    static constexpr int B_BYTES = TC_BN * D * 2;
+    static constexpr int STAGES = D == 64 ? 4 : 2;
+    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/ + 2 * TC_BM * 4;
+};
+
+template <int D>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    using C = TcCfg<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + C::A_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + C::STAGES * C::B_BYTES);
+    uint64_t *full = bars, *empty = bars + C::STAGES, *a_full = bars + 2 * C::STAGES;
+    uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
+    int *cnt_s = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [2][128]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
+    const int t0 = blockIdx.y * p.tiles_per_split;
+    const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(a_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tm_full[s], 1);
+            mbar_init(&tm_empty[s], 256);       // every epilogue thread arrives
+        }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA producer ----------------
+            mbar_expect_tx(a_full, C::A_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < C::KB; ++kb)
+                tma_load_2d(&tmA, a_full, sA + kb * (TC_BM * 128), kb * 64, (int)row0);
+            for (int t = t0, it = 0; t < t1; ++t, ++it) {
+                const int stage = it % C::STAGES;
+                const uint32_t ph = (it / C::STAGES) & 1;
+                mbar_wait(&empty[stage], ph ^ 1);
+                mbar_expect_tx(&full[stage], C::B_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < C::KB; ++kb)
+                    tma_load_2d(&tmB, &full[stage], sB + stage * C::B_BYTES + kb * (TC_BN * 128), kb * 64, t * TC_BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---------------- MMA issuer ----------------
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            for (int t = t0, it = 0; t < t1; ++t, ++it) {
+                const int stage = it % C::STAGES, acc = it & 1;
+                const uint32_t ph = (it / C::STAGES) & 1, aph = (it >> 1) & 1;
+                mbar_wait(&tm_empty[acc], aph ^ 1);          // epilogue has drained this accumulator
+                mbar_wait(&full[stage], ph);                 // TMA has landed this stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+#pragma unroll
+                for (int kb = 0; kb < C::KB; ++kb) {
+                    const uint64_t a0 = umma_desc_sw128(sA + kb * (TC_BM * 128));
+                    const uint64_t b0 = umma_desc_sw128(sB + stage * C::B_BYTES + kb * (TC_BN * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)             // K = 16 bf16 = 32 B per instruction: +2 in the >>4 address field
+                        umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty[stage]);                  // frees the smem stage when the MMAs retire
+                umma_commit(&tm_full[acc]);                  // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue: 8 warps, TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 ----------------
+        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        const int rl = quarter * 32 + lane;
+        const int64_t r = row0 + rl;
+        bool live = false;
+        float st = 0.f;
+        int64_t cur = 0, hend = 0;
+        int32_t posj = -1;
+        if (r < p.R && p.row_ok[r]) {
+            live = true;
+            st = p.target[r];
+            const int64_t u = p.user[r];
+            posj = (int32_t)p.pos[r];
+            cur = p.hist_ptr[u];
+            hend = p.hist_ptr[u + 1];
+            const int32_t first = (int32_t)min((int64_t)t0 * TC_BN, (int64_t)INT32_MAX);
+            int64_t lo = cur, hi = hend;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (p.hist_idx[mid] < first) lo = mid + 1; else hi = mid;
+            }
+            cur = lo;
+        }
+        int cnt = 0;
+        for (int t = t0, it = 0; t < t1; ++t, ++it) {
+            const int acc = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            mbar_wait(&tm_full[acc], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = half * 128 + c * 32;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + col0), v);
+                const int64_t j0 = (int64_t)t * TC_BN + col0;
+                // history / out-of-table / own-target columns of this 32-column chunk
+                uint32_t m = 0;
+                if (!live) {
+                    m = 0xffffffffu;
+                } else {
+                    while (cur < hend) {
+                        const int64_t h = (int64_t)__ldg(p.hist_idx + cur) - j0;
+                        if (h >= 32) break;
+                        if (h >= 0) m |= 1u << h;
+                        ++cur;
+                    }
+                    const int64_t lim = p.n_items - j0;
+                    if (lim < 32) m |= lim <= 0 ? 0xffffffffu : (0xffffffffu << lim);
+                    const int64_t pj = (int64_t)posj - j0;
+                    if (pj >= 0 && pj < 32) m |= 1u << pj;
+                }
+                tmem_ld_wait();
+                uint32_t gt = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) gt |= (__uint_as_float(v[i]) > st ? 1u : 0u) << i;
+                cnt += __popc(gt & ~m);
+                if (p.scores && r < p.R) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (j0 + i < p.n_items) p.scores[r * p.n_items + j0 + i] = __uint_as_float(v[i]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tm_empty[acc]);
+        }
+        cnt_s[half * TC_BM + rl] = cnt;
+        asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
+        if (half == 0 && r < p.R) {
+            const int total = cnt_s[rl] + cnt_s[TC_BM + rl];
+            if (p.splits == 1) p.rank[r] = 1 + total;
+            else atomicAdd(&p.rank[r], total);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+__global__ void fill_rank_kernel(int32_t *x, int64_t n, int32_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] = v;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (!sym || q != cudaDriverEntryPointSuccess) return (int)cudaErrorNotSupported;
+        fn = (EncodeTiledFn)sym;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+template <int D>
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         TcCfg<D>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    eval_tc_rank_kernel<D><<<dim3(row_tiles, p.splits), TC_THREADS, TcCfg<D>::SMEM, st>>>(ma, mb, p);
+    return (int)cudaGetLastError();
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace wr
+
+using namespace wr;
+
+extern "C" size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int precision) {
+    if (precision != 1 || R <= 0 || n_items <= 0 || D <= 0) return 0;
+    return align_up((size_t)R * D * 2, 1024) + align_up((size_t)n_items * D * 2, 1024) + align_up((size_t)R, 1024) + 1024;
+}
+
+// precision-1 body of wr_eval_rank_topk (eval_kernels.cu dispatches here)
+int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
+                    int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
+                    int32_t *rank, float *target, float *scores_out, void *scratch, WrWorkspace *ws, cudaStream_t st) {
+    if (D != 64 && D != 128) return WR_E_DIM;
+    if (!scratch) return WR_E_NULL;
+    if ((reinterpret_cast<uintptr_t>(scratch) & 1023u) != 0) return WR_E_ALIGN;
+    uint8_t *base = static_cast<uint8_t *>(scratch);
+    __nv_bfloat16 *A = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *Bm = reinterpret_cast<__nv_bfloat16 *>(base + align_up((size_t)R * D * 2, 1024));
+    uint8_t *row_ok = base + align_up((size_t)R * D * 2, 1024) + align_up((size_t)n_items * D * 2, 1024);
+
+    const int64_t n4 = n_items * D / 4;
+    pack_items_bf16_kernel<<<(int)min((int64_t)8 * kSMs, (n4 + 255) / 256), 256, 0, st>>>(Iemb, n4, Bm);
+    WR_CHECK_LAUNCH();
+    pack_users_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, Iemb, user, pos, R, n_users,
+                                                                                n_items, D, A, target, row_ok, ws);
+    WR_CHECK_LAUNCH();
+
+    CUtensorMap ma, mb;
+    int rc = make_map(&ma, A, R, D, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&mb, Bm, n_items, D, TC_BN);
+    if (rc) return rc;
+
+    TcParams p{user, pos, R, n_users, n_items, hist_ptr, hist_idx, target, row_ok, rank, scores_out, 1, 0, 0};
+    p.n_tiles = (int)((n_items + TC_BN - 1) / TC_BN);
+    const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
+    if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
+    const int row_tiles = (int)row_tiles64;
+    int splits = 1;
+    if (row_tiles < kSMs) splits = (kSMs + row_tiles - 1) / row_tiles;   // one CTA per SM (512 TMEM columns each)
+    if (splits > p.n_tiles) splits = p.n_tiles;
+    if (splits > 65535) splits = 65535;
+    p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+    p.splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+    if (p.splits > 1) {
+        fill_rank_kernel<<<(int)min((int64_t)kSMs * 4, (R + 255) / 256), 256, 0, st>>>(rank, R, 1);
+        WR_CHECK_LAUNCH();
+    }
+    return D == 64 ? launch_tc<64>(ma, mb, p, row_tiles, st) : launch_tc<128>(ma, mb, p, row_tiles, st);
+}
