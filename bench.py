@@ -344,6 +344,38 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
         out['eval_fp32_top10'] = {'users_per_s': R / (med * 1e-3), 'ms': med}
     except Exception as e:  # noqa: BLE001
         out['eval_fp32'] = {'error': repr(e)}
+    _, tensor_peak, _ = peaks()
+    try:    # the same dev split on the tcgen05 path (bf16 operands, fp32 accumulate; includes the bf16 packing kernels)
+        fn = lambda: _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, precision=1)
+        fn(); torch.cuda.synchronize()
+        med, _ = timed(fn, 10, flush)
+        tf = 2.0 * R * nI * D / (med * 1e-3) / 1e12
+        out['eval_tcgen05'] = {'users_per_s': R / (med * 1e-3), 'rows': R, 'items': nI, 'ms': med, 'tflops': tf,
+                               'frac_of_bf16_peak': tf / tensor_peak}
+    except Exception as e:  # noqa: BLE001
+        out['eval_tcgen05'] = {'error': repr(e)}
+    try:    # BASELINE.json configs[4]-shaped sweep point: many rows x 1M items, where the GEMM dominates
+        for d in (64, 128):
+            nUs, nIs, Rs = 200_000, 1_000_000, 262_144
+            g = torch.Generator(device=dev); g.manual_seed(3407)
+            Ub = torch.randn((nUs, d), device=dev, generator=g) / d ** 0.5
+            Ib = torch.randn((nIs, d), device=dev, generator=g)
+            us = torch.randint(0, nUs, (Rs,), device=dev, generator=g)
+            ps = torch.randint(0, nIs, (Rs,), device=dev, generator=g)
+            hl = 50
+            hp_ = torch.arange(0, (nUs + 1) * hl, hl, device=dev, dtype=torch.int64)
+            hi_ = torch.sort(torch.randint(0, nIs, (nUs, hl), device=dev, generator=g), dim=1).values.to(torch.int32).reshape(-1).contiguous()
+            ws2 = _lib.Workspace(dev)
+            fn = lambda: _lib.eval_rank_topk(Ub, Ib, us, ps, hp_, hi_, ws2, precision=1)
+            fn(); torch.cuda.synchronize()
+            med, _ = timed(fn, 3)
+            tf = 2.0 * Rs * nIs * d / (med * 1e-3) / 1e12
+            out['eval_tcgen05_262144x1M_d%d' % d] = {'users_per_s': Rs / (med * 1e-3), 'ms': med, 'tflops': tf,
+                                                      'frac_of_bf16_peak': tf / tensor_peak,
+                                                      'peak_tflops': tensor_peak}
+            del Ub, Ib, us, ps, hp_, hi_
+    except Exception as e:  # noqa: BLE001
+        out['eval_tcgen05_sweep'] = {'error': repr(e)}
     try:    # LightGCN L=2 on the same graph (BASELINE.json configs[2])
         lg, lrun, ldata = make_model(corpus, dev, 'LightGCN', gcn_layers=2)
         batches = lrun.epoch_batches(ldata['train'])

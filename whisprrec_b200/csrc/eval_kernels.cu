@@ -326,7 +326,7 @@ extern "C" int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int
                                  void *stream) {
     if (!Uemb || !Iemb || !user || !pos || !hist_ptr || !hist_idx || !rank || !target || !ws) return WR_E_NULL;
     if ((topk_idx == nullptr) != (topk_val == nullptr)) return WR_E_NULL;
-    if (R <= 0 || n_users <= 0 || n_items <= 0 || n_items > INT32_MAX) return WR_E_SIZE;
+    if (R <= 0 || n_users <= 0 || n_items <= 0 || n_items > INT32_MAX - 1024) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
     if (topk_idx && (k < 1 || k > EV_KMAX)) return WR_E_TOPK;
     if (!wr_aligned16(Uemb) || !wr_aligned16(Iemb)) return WR_E_ALIGN;

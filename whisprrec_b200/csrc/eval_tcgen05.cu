@@ -6,13 +6,14 @@
 //   warp 0      TMA producer  (A once, then a ring of B stages; SWIZZLE_128B boxes of 64 bf16 = 128 B rows)
 //   warp 1      MMA issuer    (one elected lane; smem descriptors advanced 32 B per K=16 step)
 //   warp 2      TMEM allocator / deallocator
-//   warps 4-11  epilogue: tcgen05.ld 32 columns at a time, history mask from the sorted per-user CSR (one cursor
+//   warps 4-19  epilogue: tcgen05.ld 32 columns at a time, history mask from the sorted per-user CSR (one cursor
 //               per row, the tiles arrive in item order), count of items beating the target -- while the MMA of
 //               the next tile fills the other accumulator.  The score matrix never leaves TMEM.
 // Operands are rounded to bf16 once per evaluation (pack kernels below); the target score is the fp32 FMA chain
 // over the same bf16-rounded operands.  Parity with the fp32 path is therefore "looser": see tests.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -163,7 +164,9 @@ __global__ void __launch_bounds__(256) pack_users_kernel(const float *__restrict
 // ---------------------------------------------------------------------------------------------------------
 // the scoring kernel
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TC_BM = 128, TC_BN = 256, TC_THREADS = 384;
+constexpr int TC_BM = 128, TC_BN = 256;
+constexpr int TC_EPI_WARPS = 16;                       // 4 per TMEM lane quarter, 64 accumulator columns each
+constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;
 
 template <int D>
 struct TcCfg {
@@ -171,10 +174,10 @@ struct TcCfg {
     static constexpr int A_BYTES = TC_BM * D * 2;
     static constexpr int B_BYTES = TC_BN * D * 2;
     static constexpr int STAGES = D == 64 ? 4 : 2;
-    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/ + 2 * TC_BM * 4;
+    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/ + 4 * TC_BM * 4;
 };
 
-template <int D>
+template <int D, int VARIANT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     using C = TcCfg<D>;
@@ -186,7 +189,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t *full = bars, *empty = bars + C::STAGES, *a_full = bars + 2 * C::STAGES;
     uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
-    int *cnt_s = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [2][128]
+    int *cnt_s = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [4][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
@@ -201,7 +204,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_init(a_full, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tm_full[s], 1);
-            mbar_init(&tm_empty[s], 256);       // every epilogue thread arrives
+            mbar_init(&tm_empty[s], TC_EPI_WARPS * 32);   // every epilogue thread arrives
         }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
@@ -259,14 +262,16 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue: 8 warps, TMEM lane quarter = warp % 4, column half = (warp - 4) / 4 ----------------
-        const int quarter = warp & 3, half = (warp - 4) >> 2;
+        // ---------------- epilogue: 16 warps, TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 ----------------
+        const int quarter = warp & 3, grp = (warp - 4) >> 2;
         const int rl = quarter * 32 + lane;
         const int64_t r = row0 + rl;
         bool live = false;
         float st = 0.f;
         int64_t cur = 0, hend = 0;
         int32_t posj = -1;
+        int32_t next_h = INT32_MAX;                       // next history item of this row, cached in a register
+        const int32_t n_items = (int32_t)p.n_items;
         if (r < p.R && p.row_ok[r]) {
             live = true;
             st = p.target[r];
@@ -281,6 +286,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (p.hist_idx[mid] < first) lo = mid + 1; else hi = mid;
             }
             cur = lo;
+            if (cur < hend) next_h = __ldg(p.hist_idx + cur);
         }
         int cnt = 0;
         for (int t = t0, it = 0; t < t1; ++t, ++it) {
@@ -289,45 +295,88 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_wait(&tm_full[acc], aph);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = half * 128 + c * 32;
+            for (int c = 0; c < 2; ++c) {
+                const int col0 = grp * 64 + c * 32;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + col0), v);
-                const int64_t j0 = (int64_t)t * TC_BN + col0;
-                // history / out-of-table / own-target columns of this 32-column chunk
+                const int32_t j0 = t * TC_BN + col0;
+                // columns of this chunk that must not count: history, past the table, the target itself
                 uint32_t m = 0;
                 if (!live) {
                     m = 0xffffffffu;
                 } else {
-                    while (cur < hend) {
-                        const int64_t h = (int64_t)__ldg(p.hist_idx + cur) - j0;
-                        if (h >= 32) break;
-                        if (h >= 0) m |= 1u << h;
+                    while (next_h < j0 + 32) {
+                        if (next_h >= j0) m |= 1u << (next_h - j0);
                         ++cur;
+                        next_h = cur < hend ? __ldg(p.hist_idx + cur) : INT32_MAX;
                     }
-                    const int64_t lim = p.n_items - j0;
-                    if (lim < 32) m |= lim <= 0 ? 0xffffffffu : (0xffffffffu << lim);
-                    const int64_t pj = (int64_t)posj - j0;
-                    if (pj >= 0 && pj < 32) m |= 1u << pj;
+                    if (j0 + 32 > n_items) m |= j0 >= n_items ? 0xffffffffu : (0xffffffffu << (n_items - j0));
+                    const uint32_t pj = (uint32_t)(posj - j0);
+                    if (pj < 32u) m |= 1u << pj;
                 }
                 tmem_ld_wait();
-                uint32_t gt = 0;
+                if (m == 0) {
+                    // fast path, 2 instructions per score.  VARIANT 0: FSETP + predicated integer add (both ALU pipe);
+                    // 1: FSETP (ALU) + predicated FADD (FMA pipe); 2: FFMA.SAT + FADD (FMA pipe only):
+                    // sat(v*2^100 - st*2^100) is exactly [v > st]; 3: even columns as 1, odd columns as 2.
+                    if (VARIANT == 0) {
+                        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#define WR_CNT(acc_, i_)                                                                                      \
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, %2;\n\t@q add.s32 %0, %0, 1;\n\t}"                          \
+        : "+r"(acc_)                                                                                          \
+        : "f"(__uint_as_float(v[i_])), "f"(st))
 #pragma unroll
-                for (int i = 0; i < 32; ++i) gt |= (__uint_as_float(v[i]) > st ? 1u : 0u) << i;
-                cnt += __popc(gt & ~m);
+                        for (int i = 0; i < 32; i += 4) {
+                            WR_CNT(c0, i);
+                            WR_CNT(c1, i + 1);
+                            WR_CNT(c2, i + 2);
+                            WR_CNT(c3, i + 3);
+                        }
+#undef WR_CNT
+                        cnt += (c0 + c1) + (c2 + c3);
+                    } else {
+                        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+                        const float big = 1.2676506e30f;                 // 2^100
+                        const float nst = -st * big;
+#define WR_CNTP(acc_, i_)                                                                                     \
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %1, %2;\n\t@q add.f32 %0, %0, 0f3F800000;\n\t}"                 \
+        : "+f"(acc_)                                                                                          \
+        : "f"(__uint_as_float(v[i_])), "f"(st))
+#define WR_CNTF(acc_, i_)                                                                                     \
+    {                                                                                                         \
+        float t_;                                                                                             \
+        asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(t_) : "f"(__uint_as_float(v[i_])), "f"(big), "f"(nst));  \
+        acc_ += t_;                                                                                           \
+    }
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (VARIANT == 1) { WR_CNTP(f0, i); WR_CNTP(f1, i + 1); WR_CNTP(f2, i + 2); WR_CNTP(f3, i + 3); }
+                            if (VARIANT == 2) { WR_CNTF(f0, i); WR_CNTF(f1, i + 1); WR_CNTF(f2, i + 2); WR_CNTF(f3, i + 3); }
+                            if (VARIANT == 3) { WR_CNTP(f0, i); WR_CNTF(f1, i + 1); WR_CNTP(f2, i + 2); WR_CNTF(f3, i + 3); }
+                        }
+#undef WR_CNTP
+#undef WR_CNTF
+                        cnt += (int)((f0 + f1) + (f2 + f3));
+                    }
+                } else {
+                    uint32_t gt = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) gt |= (__uint_as_float(v[i]) > st ? 1u : 0u) << i;
+                    cnt += __popc(gt & ~m);
+                }
                 if (p.scores && r < p.R) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (j0 + i < p.n_items) p.scores[r * p.n_items + j0 + i] = __uint_as_float(v[i]);
+                        if (j0 + i < n_items) p.scores[r * p.n_items + j0 + i] = __uint_as_float(v[i]);
                 }
             }
             tc_fence_before();
             mbar_arrive(&tm_empty[acc]);
         }
-        cnt_s[half * TC_BM + rl] = cnt;
-        asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
-        if (half == 0 && r < p.R) {
-            const int total = cnt_s[rl] + cnt_s[TC_BM + rl];
+        cnt_s[grp * TC_BM + rl] = cnt;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // the epilogue warps only
+        if (grp == 0 && r < p.R) {
+            const int total = cnt_s[rl] + cnt_s[TC_BM + rl] + cnt_s[2 * TC_BM + rl] + cnt_s[3 * TC_BM + rl];
             if (p.splits == 1) p.rank[r] = 1 + total;
             else atomicAdd(&p.rank[r], total);
         }
@@ -369,13 +418,28 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int D>
-static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int D, int VARIANT>
+static int launch_tc_v(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          TcCfg<D>::SMEM);
     if (e != cudaSuccess) return (int)e;
-    eval_tc_rank_kernel<D><<<dim3(row_tiles, p.splits), TC_THREADS, TcCfg<D>::SMEM, st>>>(ma, mb, p);
+    eval_tc_rank_kernel<D, VARIANT><<<dim3(row_tiles, p.splits), TC_THREADS, TcCfg<D>::SMEM, st>>>(ma, mb, p);
     return (int)cudaGetLastError();
+}
+
+template <int D>
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("WR_TC_VARIANT");        // tuning knob for the epilogue's counting form
+        variant = e ? atoi(e) : 1;
+    }
+    switch (variant) {
+        case 1: return launch_tc_v<D, 1>(ma, mb, p, row_tiles, st);
+        case 2: return launch_tc_v<D, 2>(ma, mb, p, row_tiles, st);
+        case 3: return launch_tc_v<D, 3>(ma, mb, p, row_tiles, st);
+        default: return launch_tc_v<D, 0>(ma, mb, p, row_tiles, st);
+    }
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
