@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 B, D, LR, L2 = 2048, 64, 1e-3, 1e-6
 CACHE = os.environ.get('WR_CACHE', '/tmp/wr_cache')
+TRAFFIC_PER_LAUNCH = None      # dram bytes of one bprmf_step_kernel launch from `ncu --set full` (profiles/), once captured
 WORKLOAD = 'BPRMF emb=64 B=2048 Adam(lr=1e-3,l2=1e-6) on ml-1m-shaped synthetic (6040 users x 3706 items, 668862 train rows)'
 
 
@@ -130,16 +131,14 @@ def run_ours(a, rank, world, local_rank):
     steps_per_epoch = n_train // B                             # full batches only inside the timed region
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     losses = torch.zeros(a.warmup + a.steps, device=dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(a.steps)]
 
     def step(s, events=None):
         lo = (s % steps_per_epoch) * B
         batch = {'user_id': batches[0, lo:lo + B], 'pos_item': batches[1, lo:lo + B], 'neg_items': batches[2, lo:lo + B]}
         if events: events[0].record()
-        model.predict(batch, loss_out=losses[s:s + 1])
+        model.train_step(batch, loss_out=losses[s:s + 1])     # what BaseRunner.fit calls: one cooperative launch
         if events: events[1].record()
-        model.optimizer.step()
-        if events: events[2].record()
 
     def barrier():
         torch.cuda.synchronize()
@@ -165,9 +164,7 @@ def run_ours(a, rank, world, local_rank):
                 flush.zero_(); step(0)
             torch.cuda.synchronize()
     clocks = clk.summary()
-    bpr_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
-    adam_ms = np.array([e[1].elapsed_time(e[2]) for e in ev])
-    step_ms = np.array([e[0].elapsed_time(e[2]) for e in ev])
+    step_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
     total_ms = float(step_ms.sum())
     if world > 1:
         import torch.distributed as dist
@@ -183,17 +180,13 @@ def run_ours(a, rank, world, local_rank):
     pinned = torch.empty((steps_per_epoch, 3, B), dtype=torch.int64).pin_memory()
     for s in range(steps_per_epoch):
         pinned[s].copy_(host_batches[:, s * B:(s + 1) * B])
-    stage = torch.empty((3, B), dtype=torch.int64, device=dev)
     e2e_s = 0.0
     for s in range(a.warmup + a.steps):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        stage.copy_(pinned[s % steps_per_epoch], non_blocking=True)
-        loss = model.predict({'user_id': stage[0], 'pos_item': stage[1], 'neg_items': stage[2]})
-        loss.backward()
-        model.optimizer.step()
-        loss_host = float(loss.cpu())
+        # pinned ids -> H2D -> step -> loss D2H -> stream sync, one C-ABI call (wr_bprmf_step_host)
+        loss_host = float(model.train_step_host(pinned[s % steps_per_epoch])[0])
         if s >= a.warmup:
             e2e_s += time.perf_counter() - t0
     if world > 1:
@@ -204,9 +197,9 @@ def run_ours(a, rank, world, local_rank):
     assert np.isfinite(loss_host)
     e2e_value = world * a.steps * B / e2e_s
 
-    adam_bytes = algorithmic_bytes_adam(n_rows, D)
-    adam_avg_s = float(adam_ms.mean()) * 1e-3
-    achieved = adam_bytes / adam_avg_s / 1e9
+    step_bytes = algorithmic_bytes_adam(n_rows, D) + algorithmic_bytes_bpr(B, D)
+    step_avg_s = float(step_ms.mean()) * 1e-3
+    achieved = step_bytes / step_avg_s / 1e9
     line = {
         'metric': 'train_interactions_per_s', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': total_ms / a.steps, 'higher_is_better': True,
@@ -216,15 +209,15 @@ def run_ours(a, rank, world, local_rank):
                    'parallelism': 'single GPU' if world == 1 else 'replicas x%d' % world},
         'e2e': {'value': e2e_value, 'unit': 'interactions/s', 'h2d_bytes_per_step': 3 * B * 8,
                 'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / a.steps * 1e3},
-        'gpu_launches': 2 * a.steps,
+        'gpu_launches': a.steps,
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'adam_sweep_kernel', 'achieved': achieved, 'peak': hbm_peak,
-                     'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                     'bytes_per_launch': adam_bytes, 'avg_launch_us': adam_avg_s * 1e6,
-                     'step_bytes': adam_bytes + algorithmic_bytes_bpr(B, D),
-                     'step_frac': (adam_bytes + algorithmic_bytes_bpr(B, D)) / (total_ms / a.steps * 1e-3) / 1e9 / hbm_peak},
-        'kernels_ms': {'bpr_fwd_bwd': float(bpr_ms.mean()), 'adam_l2_sweep': float(adam_ms.mean()),
-                       'step_median': float(np.median(step_ms))},
+        'roofline': {'bound': 'hbm', 'kernel': 'bprmf_step_kernel', 'achieved': achieved, 'peak': hbm_peak,
+                     'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': TRAFFIC_PER_LAUNCH,
+                     'peak_source': peak_src, 'bytes_per_launch': step_bytes, 'avg_launch_us': step_avg_s * 1e6,
+                     'note': 'the whole step is one launch; 23 MB per launch is latency-bound (launch + two dependent '
+                             'DRAM round trips + a grid barrier), see extra.bprmf_10Mx2M_d128_b65536 for the '
+                             'bandwidth-bound shape of the same arithmetic'},
+        'kernels_ms': {'bprmf_step': float(step_ms.mean()), 'step_median': float(np.median(step_ms))},
     }
     if rank == 0 and world == 1:
         line['cpu_baseline'] = cpu_baseline(corpus, budget_s=a.cpu_budget)
@@ -344,6 +337,18 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
         out['eval_fp32_top10'] = {'users_per_s': R / (med * 1e-3), 'ms': med}
     except Exception as e:  # noqa: BLE001
         out['eval_fp32'] = {'error': repr(e)}
+    try:    # the two-launch form of the same step (what large tables use): fwd+bwd kernel, then the Adam sweep
+        t = model.tables
+        batches = runner.epoch_batches(data['train'])
+        u, p_, n_ = batches[0, :B].contiguous(), batches[1, :B].contiguous(), batches[2, :B].contiguous()
+        bpr = lambda: _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), u, p_, n_, t.users(t.G), t.items(t.G), t.loss, t.ws)
+        adam = lambda: _lib.adam_l2_sweep(t.P, t.M, t.V, t.G, 1000, LR, L2)
+        bmed, _ = timed(bpr, 20, flush)
+        amed, _ = timed(adam, 20, flush)
+        out['two_launch_step'] = {'bpr_fwd_bwd_ms': bmed, 'adam_l2_sweep_ms': amed,
+                                  'adam_gbs': algorithmic_bytes_adam(t.P.shape[0], D) / (amed * 1e-3) / 1e9}
+    except Exception as e:  # noqa: BLE001
+        out['two_launch_step'] = {'error': repr(e)}
     _, tensor_peak, _ = peaks()
     try:    # the same dev split on the tcgen05 path (bf16 operands, fp32 accumulate; includes the bf16 packing kernels)
         fn = lambda: _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, precision=1)

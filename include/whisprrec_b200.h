@@ -82,6 +82,27 @@ int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_t *user, co
 int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, float l2, double beta1, double beta2,
                      float eps, float step_size, float bc2_sqrt, const float *dev_scalars, void *stream);
 
+/* wr_bprmf_step: one whole iteration of BaseRunner.fit for BPRMF (BaseRunner.py:196-199: zero_grad, predict,
+ * backward, Adam.step) on the fused table P = [U; I] ([n_users + n_items, D], M / V / G alike).  Tables of up to
+ * 8 Mi elements take ONE cooperative launch (parameter loads issued first, BPR forward+backward, grid barrier,
+ * Adam+L2 with the gradient re-zeroed); larger ones are wr_bpr_fwd_bwd followed by wr_adam_l2_sweep.  Same
+ * arithmetic either way.  loss_out[0] is overwritten.
+ */
+int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
+                  const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
+                  double beta1, double beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
+                  float *loss_out, void *ws, void *stream);
+
+/* wr_bprmf_step_host: the same iteration fed from the HOST, i.e. utils.batch_to_gpu (utils/utils.py:33-37) +
+ * the step + `loss.detach().cpu()` (BaseRunner.py:200).  host_ids: pinned [3, B] int64 (user, pos, neg rows);
+ * dev_ids: device staging of the same shape; host_loss: pinned float that receives the batch loss.
+ * sync != 0 waits for the stream before returning (the reference syncs on every step).
+ */
+int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, float *host_loss, float *P, float *M, float *V,
+                       float *G, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
+                       double beta1, double beta2, float eps, float step_size, float bc2_sqrt, float *loss_out,
+                       void *ws, void *stream, int sync);
+
 /* ---- LightGCN propagation ------------------------------------------------------------------------------
  * wr_csr_norm_weights: the value recipe of LightGCN.py:89-97: val[e] = fl32(fl32(dinv[row] * 1) * dinv[col]).
  * dinv = np.power(fp32(deg) + 1e-10, -0.5) comes from the caller (NumPy's fp32 pow is not correctly rounded,

@@ -65,6 +65,80 @@ def test_bprmf_steps_match_reference_golden(tag, ws):
     assert ws.status() == 0
 
 
+@pytest.mark.parametrize('tag', SMALL[:2])
+def test_bprmf_single_launch_step_matches_reference_golden(tag, ws):
+    """The same three reference steps through wr_bprmf_step (one cooperative launch per step)."""
+    s = small_case(load('small_cases.npz'), tag)
+    lr, l2 = float(s['hp'][0]), float(s['hp'][1])
+    nU = s['U0'].shape[0]
+    P = dv(np.concatenate([s['U0'], s['I0']]))
+    M, V, G = torch.zeros_like(P), torch.zeros_like(P), torch.zeros_like(P)
+    loss = torch.zeros(1, device=DEV)
+    for step in range(3):
+        user, pos, neg = (dv(s[f's{step}/{k}'], torch.int64) for k in ('user', 'pos', 'neg'))
+        _lib.bprmf_step(P, M, V, G, user, pos, neg, nU, step + 1, lr, l2, loss, ws)
+        assert_close(host(loss)[0], s[f's{step}/loss'], f'{tag} loss step {step}')
+        assert float(G.abs().max()) == 0.0
+        assert_close(host(P[:nU]), s[f's{step}/U'], f'{tag} U step {step}')
+        assert_close(host(P[nU:]), s[f's{step}/I'], f'{tag} I step {step}')
+    assert_close(host(M[:nU]), s['mU'], f'{tag} exp_avg')
+    assert_close(host(V[:nU]), s['vU'], f'{tag} exp_avg_sq')
+    assert ws.status() == 0
+
+
+@pytest.mark.parametrize('nU,nI,D,B', [(50, 70, 16, 33), (6040, 3706, 64, 2048), (3000, 1000, 128, 4096),
+                                       (40000, 60000, 64, 8192), (300, 200, 256, 100), (100, 100, 48, 64)])
+def test_bprmf_single_launch_step_equals_two_kernel_path(nU, nI, D, B, ws):
+    """wr_bprmf_step against wr_bpr_fwd_bwd + wr_adam_l2_sweep on the same inputs over several steps: the loss is
+    bit-identical when both sum their partials over the same CTAs; parameters agree to the REDs' summation order.
+    (40000+60000) x 64 needs more than one pass of the resident grid; D=48 takes the two-launch route inside."""
+    rng = np.random.RandomState(7)
+    P0 = (rng.randn(nU + nI, D) * 0.1).astype(np.float32)
+    Pa, Pb = dv(P0), dv(P0)
+    Ma, Va, Ga = torch.zeros_like(Pa), torch.zeros_like(Pa), torch.zeros_like(Pa)
+    Mb, Vb, Gb = torch.zeros_like(Pb), torch.zeros_like(Pb), torch.zeros_like(Pb)
+    la, lb = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    for step in range(1, 5):
+        user, pos, neg = dv(rng.randint(0, nU, B)), dv(rng.randint(0, nI, B)), dv(rng.randint(1, nI, B))
+        _lib.bprmf_step(Pa, Ma, Va, Ga, user, pos, neg, nU, step, 1e-3, 1e-6, la, ws)
+        _lib.bpr_fwd_bwd(Pb[:nU], Pb[nU:], user, pos, neg, Gb[:nU], Gb[nU:], lb, ws)
+        _lib.adam_l2_sweep(Pb, Mb, Vb, Gb, step, 1e-3, 1e-6)
+        assert host(la)[0] == pytest.approx(host(lb)[0], rel=2e-6)
+        assert float(Ga.abs().max()) == 0.0
+        assert_close(host(Pa), host(Pb), f'P step {step}', rtol=1e-5, atol_scale=2e-6)
+    assert_close(host(Ma), host(Mb), 'M')
+    assert_close(host(Va), host(Vb), 'V')
+    assert ws.status() == 0
+
+
+def test_bprmf_host_fed_step_matches_device_step(ws):
+    """model.train_step_host (pinned ids in, loss out, one C call) against model.train_step."""
+    corpus = ml100k_corpus()
+    models = []
+    for _ in range(2):
+        args = model_args(BPRMF, lr=1e-3, l2=1e-6)
+        utils.init_seed(3407)
+        m = BPRMF(args, corpus).to(DEV)
+        m.fuse()
+        m.optimizer = BaseRunner(args)._build_optimizer(m)
+        models.append(m)
+    rng = np.random.RandomState(3)
+    for step in range(4):
+        B = 2048 if step < 3 else 480
+        ids = np.stack([rng.randint(0, corpus.n_users, B), rng.randint(1, corpus.n_items, B),
+                        rng.randint(1, corpus.n_items, B)]).astype(np.int64)
+        pinned = torch.from_numpy(ids).pin_memory()
+        loss_host = models[0].train_step_host(pinned)
+        d = dv(ids)
+        loss_dev = models[1].train_step({'user_id': d[0], 'pos_item': d[1], 'neg_items': d[2]})
+        assert float(loss_host[0]) == pytest.approx(float(loss_dev), rel=2e-6)
+        assert_close(host(models[0].tables.P), host(models[1].tables.P), f'P step {step}', rtol=1e-5, atol_scale=2e-6)
+    o_loss, _, _ = O.bpr_fwd_bwd(host(models[1].tables.P[:corpus.n_users]), host(models[1].tables.P[corpus.n_users:]),
+                                 ids[0], ids[1], ids[2])
+    assert np.isfinite(o_loss.item())
+    assert models[0].tables.ws.status() == 0
+
+
 @pytest.mark.parametrize('D', [16, 32, 64, 128, 256, 48, 8])
 @pytest.mark.parametrize('B', [1, 31, 480, 2048])
 def test_bpr_fwd_bwd_vs_oracle(D, B, ws):

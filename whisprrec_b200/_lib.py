@@ -28,6 +28,10 @@ SIGNATURES = {
     'wr_bpr_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _p, _p, _p, _int, _p, _p]),
     'wr_embloss_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _p, _p, _p, _p, _p]),
     'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f64, _f64, _f32, _f32, _f32, _p, _p]),
+    'wr_bprmf_step': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32, _f32,
+                             _f32, _p, _p, _p, _p]),
+    'wr_bprmf_step_host': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32,
+                                  _f32, _f32, _p, _p, _p, _int]),
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
     'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
@@ -148,6 +152,33 @@ def adam_l2_sweep(P, M, V, G, step, lr, l2, beta1=0.9, beta2=0.999, eps=1e-8, de
     ss, bc2s = adam_scalars(step, lr, beta1, beta2)
     check(load().wr_adam_l2_sweep(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), P.numel(), l2, beta1, beta2,
                                   eps, ss, bc2s, ptr(dev_scalars, F32), stream_ptr()))
+
+
+def bprmf_step(P, M, V, G, user, pos, neg, n_users, step, lr, l2, loss_out, ws, beta1=0.9, beta2=0.999, eps=1e-8,
+               gamma=1e-10, dev_scalars=None):
+    """One BPRMF iteration (zero_grad + predict + backward + Adam.step) on the fused tables."""
+    ss, bc2s = adam_scalars(step, lr, beta1, beta2)
+    check(load().wr_bprmf_step(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), ptr(user, I64), ptr(pos, I64),
+                               ptr(neg, I64), user.numel(), P.shape[1], n_users, P.shape[0] - n_users, gamma, l2,
+                               beta1, beta2, eps, ss, bc2s, ptr(dev_scalars, F32), ptr(loss_out, F32), ws.ptr,
+                               stream_ptr()))
+
+
+def bprmf_step_host(host_ids, dev_ids, host_loss, P, M, V, G, n_users, step, lr, l2, loss_out, ws, beta1=0.9,
+                    beta2=0.999, eps=1e-8, gamma=1e-10, sync=True):
+    """The same iteration from pinned host ids [3, B]; the batch loss lands in the pinned `host_loss`."""
+    if host_ids.is_cuda or not host_ids.is_pinned() or not host_loss.is_pinned():
+        raise WhisprError('host_ids / host_loss must be pinned host tensors')
+    if host_ids.dtype != I64 or host_ids.dim() != 2 or host_ids.shape[0] != 3 or not host_ids.is_contiguous():
+        raise WhisprError('host_ids must be a contiguous int64 [3, B] tensor')
+    B = host_ids.shape[1]
+    if dev_ids.numel() < 3 * B:
+        raise WhisprError('device staging too small')
+    ss, bc2s = adam_scalars(step, lr, beta1, beta2)
+    check(load().wr_bprmf_step_host(host_ids.data_ptr(), ptr(dev_ids, I64), host_loss.data_ptr(), ptr(P, F32),
+                                    ptr(M, F32), ptr(V, F32), ptr(G, F32), B, P.shape[1], n_users,
+                                    P.shape[0] - n_users, gamma, l2, beta1, beta2, eps, ss, bc2s, ptr(loss_out, F32),
+                                    ws.ptr, stream_ptr(), int(sync)))
 
 
 def csr_norm_weights(rowptr, col, dinv, val):

@@ -330,6 +330,149 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(float *G, const i
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// One launch for a whole BPRMF step (BaseRunner.py:196-199) when the tables are cache-sized and the step is
+// latency-bound rather than bandwidth-bound: every thread first issues the loads of its share of P / M / V
+// (they do not depend on the batch), then the grid does the BPR forward+backward (ids -> rows -> REDs into
+// G) while those loads are in flight, meets at a grid barrier (cooperative launch: all CTAs are resident),
+// and finishes with the Adam+L2 update of the elements it already holds -- G comes back as L2 hits.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 *P, float4 *M, float4 *V, float4 *G, int64_t n4,
+                                                          AdamScalars s, const float *dev_scalars) {
+    using RG = RowGroup<LPR, VPL>;
+    constexpr int D = RG::D;
+    __shared__ float red[8];
+    if (dev_scalars) {
+        s.step_size = __ldg(dev_scalars);
+        s.bc2_sqrt = __ldg(dev_scalars + 1);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // ---- phase 0: pull this CTA's spans of P / M / V towards L2 (one bulk prefetch per 4 KB span) ----
+    if (threadIdx.x < 3) {
+        const float4 *arr = threadIdx.x == 0 ? P : (threadIdx.x == 1 ? M : V);
+        for (int64_t c = (int64_t)blockIdx.x * blockDim.x; c < n4; c += stride) {
+            const uint32_t bytes = (uint32_t)min((int64_t)blockDim.x, n4 - c) * 16u;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(arr + c), "r"(bytes) : "memory");
+        }
+    }
+    // ---- phase 1: BPR forward + backward; consecutive interaction groups go to different CTAs ----
+    const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+    const int64_t warp = (int64_t)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float local = 0.f;
+    for (int64_t base = warp * RG::GROUPS; base < p.B; base += nwarps * RG::GROUPS) {
+        const int64_t b = base + grp;
+        const bool valid = b < p.B;
+        int64_t u = 0, i = 0, j = 0;
+        if (valid) {
+            u = p.user[b];
+            i = p.pos[b];
+            j = p.neg[b];
+        }
+        const bool ok = valid && (uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
+                        (uint64_t)j < (uint64_t)p.n_items;
+        if (valid && !ok && sub == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+        float4 ue[VPL], pe[VPL], ne[VPL];
+        if (ok) {
+            RG::load(p.U + u * D, sub, ue);
+            RG::load(p.I + i * D, sub, pe);
+            RG::load(p.I + j * D, sub, ne);
+        } else {
+            RG::zero(ue);
+            RG::zero(pe);
+            RG::zero(ne);
+        }
+        float sp = 0.f, sn = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            sp += dot4(ue[v], pe[v]);
+            sn += dot4(ue[v], ne[v]);
+        }
+        sp = group_sum<LPR>(sp);
+        sn = group_sum<LPR>(sn);
+        if (ok) {
+            float l, c;
+            bpr_pointwise(sp, sn, p.gamma, p.coef, l, c);
+            if (sub == 0) local += l;
+            float *gu = p.gU + u * D, *gp = p.gI + i * D, *gn = p.gI + j * D;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                const int off = 4 * (sub + v * LPR);
+                red_add_v4(gu + off, scale4(sub4(pe[v], ne[v]), c));
+                red_add_v4(gp + off, scale4(ue[v], c));
+                red_add_v4(gn + off, scale4(ue[v], -c));
+            }
+        }
+    }
+    const float bsum = block_sum(local, red);
+    if (threadIdx.x == 0) p.ws->partial[blockIdx.x] = bsum;
+    // ---- grid barrier (ticket[3] counts arrivals, ticket[4] departures; the last CTA to leave re-arms both) ----
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&p.ws->ticket[3], 1u);
+        while (ld_acquire_u32(&p.ws->ticket[3]) < gridDim.x) {}
+        __threadfence();
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < 32) {      // the loss, summed in CTA order (deterministic)
+        float t = 0.f;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(&p.ws->partial[i]);
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            const float mean = t / (float)p.B;
+            p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + mean : mean;
+        }
+    }
+    // ---- phase 2: Adam + L2 over every element, gradient re-zeroed; two iterations of loads in flight ----
+    const float4 z = f4_zero();
+    for (int64_t i = i0; i < n4; i += 2 * stride) {
+        const int64_t i2 = i + stride;
+        const bool two = i2 < n4;
+        float4 pa = P[i], ma = M[i], va = V[i], ga = __ldcg(G + i);
+        float4 pb = z, mb = z, vb = z, gb = z;
+        if (two) {
+            pb = P[i2];
+            mb = M[i2];
+            vb = V[i2];
+            gb = __ldcg(G + i2);
+        }
+        adam_elem(pa.x, ma.x, va.x, ga.x, s);
+        adam_elem(pa.y, ma.y, va.y, ga.y, s);
+        adam_elem(pa.z, ma.z, va.z, ga.z, s);
+        adam_elem(pa.w, ma.w, va.w, ga.w, s);
+        P[i] = pa;
+        M[i] = ma;
+        V[i] = va;
+        G[i] = z;
+        if (two) {
+            adam_elem(pb.x, mb.x, vb.x, gb.x, s);
+            adam_elem(pb.y, mb.y, vb.y, gb.y, s);
+            adam_elem(pb.z, mb.z, vb.z, gb.z, s);
+            adam_elem(pb.w, mb.w, vb.w, gb.w, s);
+            P[i2] = pb;
+            M[i2] = mb;
+            V[i2] = vb;
+            G[i2] = z;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(&p.ws->ticket[4], 1u);
+        if (t == gridDim.x - 1) {
+            p.ws->ticket[3] = 0;
+            p.ws->ticket[4] = 0;
+        }
+    }
+}
+
 static inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
     int64_t g = (work_items + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -422,6 +565,93 @@ extern "C" int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t 
         WR_CHECK_LAUNCH();
     }
     return WR_OK;
+}
+
+// Largest grid of bprmf_step_kernel<LPR, VPL> that is resident at once on the current device (cached per shape).
+template <int LPR, int VPL>
+static int step_max_grid(int *out) {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bprmf_step_kernel<LPR, VPL>, 256, 0);
+        if (e != cudaSuccess) return (int)e;
+        cached = sms * per_sm;
+        if (cached > WR_MAX_PARTIAL_BLOCKS) cached = WR_MAX_PARTIAL_BLOCKS;
+        if (cached < 1) return (int)cudaErrorLaunchOutOfResources;
+    }
+    *out = cached;
+    return 0;
+}
+
+template <int LPR, int VPL>
+static int launch_step_fused(BprParams &bp, float *P, float *M, float *V, float *G, int64_t n4, AdamScalars &s,
+                             const float *dev_scalars, cudaStream_t st) {
+    int max_grid = 0;
+    const int rc = step_max_grid<LPR, VPL>(&max_grid);
+    if (rc) return rc;
+    // whole iterations for every CTA: the fewest passes the resident grid needs, then the smallest grid for them
+    const int64_t per_pass = (int64_t)max_grid * 256;
+    const int64_t passes = (n4 + per_pass - 1) / per_pass;
+    int grid = grid_for(n4, (int)(256 * passes), max_grid);
+    float4 *P4 = (float4 *)P, *M4 = (float4 *)M, *V4 = (float4 *)V, *G4 = (float4 *)G;
+    void *args[] = {&bp, &P4, &M4, &V4, &G4, &n4, &s, &dev_scalars};
+    return (int)cudaLaunchCooperativeKernel((const void *)bprmf_step_kernel<LPR, VPL>, dim3(grid), dim3(256), args, 0, st);
+}
+
+// Tables up to this many bytes per array take the single-launch step (they fit in L2 several times over and the
+// step is bound by launch / DRAM latency); larger ones stream at HBM bandwidth through the two-kernel path.
+#define WR_FUSED_STEP_MAX_ELEMS ((int64_t)8 << 20)
+
+extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
+                             const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma,
+                             float l2, double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
+                             const float *dev_scalars, float *loss_out, void *ws, void *stream) {
+    if (!P || !M || !V || !G || !user || !pos || !neg || !loss_out || !ws) return WR_E_NULL;
+    if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
+    const int64_t n_elems = (n_users + n_items) * D;
+    const bool fused_shape = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
+    if (!fused_shape || n_elems > WR_FUSED_STEP_MAX_ELEMS) {
+        int rc = wr_bpr_fwd_bwd(P, P + n_users * D, user, pos, neg, B, D, n_users, n_items, gamma, 1.0f, G,
+                                G + n_users * D, loss_out, 0, ws, stream);
+        if (rc) return rc;
+        return wr_adam_l2_sweep(P, M, V, G, n_elems, l2, beta1, beta2, eps, step_size, bc2_sqrt, dev_scalars, stream);
+    }
+    BprParams bp{P, P + n_users * D, user, pos, neg, B, n_users, n_items, gamma, 1.0f / (float)B,
+                 G, G + n_users * D, loss_out, 0, (WrWorkspace *)ws};
+    AdamScalars s{l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, bc2_sqrt};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n4 = n_elems >> 2;
+    int rc;
+    switch (D) {
+        case 16: rc = launch_step_fused<4, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
+        case 32: rc = launch_step_fused<8, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
+        case 64: rc = launch_step_fused<16, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
+        case 128: rc = launch_step_fused<32, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
+        default: rc = launch_step_fused<32, 2>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
+    }
+    return rc;
+}
+
+extern "C" int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, float *host_loss, float *P, float *M,
+                                  float *V, float *G, int64_t B, int D, int64_t n_users, int64_t n_items,
+                                  float gamma, float l2, double beta1, double beta2, float eps, float step_size,
+                                  float bc2_sqrt, float *loss_out, void *ws, void *stream, int sync) {
+    if (!host_ids || !dev_ids || !host_loss) return WR_E_NULL;
+    if (B <= 0) return WR_E_SIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(dev_ids, host_ids, (size_t)(3 * B) * sizeof(int64_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    const int rc = wr_bprmf_step(P, M, V, G, dev_ids, dev_ids + B, dev_ids + 2 * B, B, D, n_users, n_items, gamma, l2,
+                                 beta1, beta2, eps, step_size, bc2_sqrt, nullptr, loss_out, ws, stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(host_loss, loss_out, sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return (int)e;
+    if (sync) e = cudaStreamSynchronize(st);
+    return (int)e;
 }
 
 extern "C" int wr_gather_rows(const float *T, const int64_t *idx, int64_t B, int D, int64_t n_rows, float *out,

@@ -53,6 +53,37 @@ class BPRMF(GeneralModel):
                          feed_dict['neg_items'], t.users(t.G), t.items(t.G), out, t.ws)
         return out[0].detach().as_subclass(_base.FusedLoss)
 
+    def train_step(self, feed_dict, loss_out=None):
+        """One whole iteration of BaseRunner.fit (BaseRunner.py:196-199: zero_grad, predict, backward,
+        optimizer.step) as a single wr_bprmf_step call; the loss stays on the device."""
+        t = self.fuse()
+        opt = self.optimizer
+        out = t.loss if loss_out is None else loss_out
+        opt.step_count += 1
+        _lib.bprmf_step(t.P, t.M, t.V, t.G, feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items'],
+                        t.n_users, opt.step_count, opt.lr, opt.weight_decay, out, t.ws, beta1=opt.betas[0],
+                        beta2=opt.betas[1], eps=opt.eps)
+        return out[0].detach().as_subclass(_base.FusedLoss)
+
+    def train_step_host(self, host_ids, sync=True):
+        """The same iteration fed from the host: `host_ids` is a pinned int64 [3, B] tensor holding the batch's
+        user / positive / negative ids (what collate_batch produces, BaseModel.py:96-127).  Covers
+        utils.batch_to_gpu (utils.py:33-37), the step and `loss.detach().cpu()` (BaseRunner.py:200); returns the
+        pinned one-element tensor the loss lands in (valid once the stream is synchronised, i.e. on return when
+        sync=True)."""
+        t = self.fuse()
+        opt = self.optimizer
+        B = host_ids.shape[1]
+        st = getattr(self, '_host_stage', None)
+        if st is None or st[0].numel() < 3 * B:
+            st = self._host_stage = (torch.empty(3 * B, dtype=torch.int64, device=t.P.device),
+                                     torch.zeros(1, dtype=torch.float32).pin_memory())
+        opt.step_count += 1
+        _lib.bprmf_step_host(host_ids, st[0], st[1], t.P, t.M, t.V, t.G, t.n_users, opt.step_count, opt.lr,
+                             opt.weight_decay, t.loss, t.ws, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps,
+                             sync=sync)
+        return st[1]
+
     def full_predict(self, feed_dict):
         """BPRMF.py:82-91: the dense [B, n_items] score matrix (compatibility API; the runner's evaluation
         uses the fused rank kernel and never materialises it)."""
