@@ -177,6 +177,110 @@ int wr_gather_rows(const float *T, const int64_t *idx, int64_t B, int D, int64_t
 int wr_scatter_add_rows(float *G, const int64_t *idx, int64_t B, int D, int64_t n_rows, const float *rows,
                         void *ws, void *stream);
 
+/* ==== one 8 x B200 box: row-sharded tables over NVLink peer memory =====================
+ * One process per GPU.  Every rank owns a slab of device memory (wr_peer_alloc), exports it (wr_peer_export),
+ * and maps every other rank's slab (wr_peer_open): after that a kernel on any GPU can load, store and reduce into
+ * any rank's rows through NVLink 5 / NVSwitch with ordinary global-memory instructions.  There is no index or row
+ * all-to-all: the gather of remote embedding rows and the scatter-add of remote gradient rows happen INSIDE the
+ * BPR kernel (ld.global / red.global.add.v4.f32 on peer addresses), the all-gather of a LightGCN layer happens
+ * inside the SpMM (neighbour rows are read from their owner), and only the step boundary needs an exchange:
+ * wr_peer_barrier.
+ *
+ * Layout: user u lives on rank u % world at local row u / world; item i on rank i % world at local row
+ * rows_u_local + i / world, rows_u_local = ceil(n_users / world).  A rank's shard is therefore one contiguous
+ * [rows_u_local + rows_i_local, D] table (P, and M / V / G alike) that its Adam sweep walks with no communication.
+ * LightGCN node n is user n if n < n_users, else item n - n_users.
+ */
+#define WR_MAX_WORLD 8
+
+typedef struct wr_shards {
+    float *base[WR_MAX_WORLD]; /* base[g]: rank g's shard as mapped in THIS process (base[rank] is local memory) */
+    int32_t world, rank;
+    int64_t n_users, n_items;  /* global */
+    int64_t rows_u_local;      /* ceil(n_users / world) */
+    int64_t rows_i_local;      /* ceil(n_items / world) */
+} wr_shards;
+
+int wr_peer_alloc(size_t bytes, void **out_dev_ptr);                 /* cudaMalloc'd, zero-filled, IPC-exportable */
+int wr_peer_free(void *dev_ptr);
+int wr_peer_export(void *dev_ptr, unsigned char host_handle[64]);    /* cudaIpcGetMemHandle */
+int wr_peer_open(const unsigned char host_handle[64], void **out_dev_ptr); /* cudaIpcOpenMemHandle, peer access on */
+int wr_peer_close(void *dev_ptr);
+
+/* wr_peer_barrier: all ranks' streams meet.  Everything a rank's stream did before its call (including REDs into
+ * peer memory) is visible to every rank's stream after its call.  host_flags[g]: rank g's array of WR_MAX_WORLD
+ * uint32 (zeroed once); epoch: 1, 2, 3, ... -- the same on every rank, never reused.
+ * If n_values > 0 (<= WR_PEER_VALUES) the barrier doubles as an all-reduce(sum) of that many floats: rank r deposits
+ * values_in[0..n) in host_slots[g] on every rank g and, past the barrier, sums_out[v] = sum over ranks, added in
+ * rank order (deterministic, identical on every rank).  host_slots[g]: rank g's array of 2 * WR_MAX_WORLD *
+ * WR_PEER_VALUES floats (double-buffered by epoch parity).
+ * The ranks MUST run on different GPUs (a spin-wait between processes sharing one GPU can deadlock the device).
+ */
+#define WR_PEER_VALUES 4
+int wr_peer_barrier(uint32_t *const host_flags[WR_MAX_WORLD], int world, int rank, uint32_t epoch,
+                    float *const host_slots[WR_MAX_WORLD], const float *values_in, int n_values, float *sums_out,
+                    void *stream);
+
+/* wr_bpr_fwd_bwd_sharded: wr_bpr_fwd_bwd on this rank's slice of the global batch against sharded tables.
+ * T: the embedding shards read (P for BPRMF, the pooled table for LightGCN); Gd: the gradient shards reduced into
+ * (remote rows over NVLink).  B: rows in this rank's slice; B_global: rows in the whole batch (the mean and the
+ * gradient scale use it).  loss_out[0] = this rank's share, sum_b(loss_b) / B_global -- summed over ranks by
+ * wr_peer_barrier it is the batch loss.
+ */
+int wr_bpr_fwd_bwd_sharded(const wr_shards *host_T, const wr_shards *host_Gd, const int64_t *user,
+                           const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D, float gamma,
+                           float grad_scale, float *loss_out, void *ws, void *stream);
+
+/* wr_embloss_sumsq_sharded / wr_embloss_scatter_sharded: the two halves of wr_embloss_fwd_bwd; the three squared
+ * norms are batch-global, so the ranks' sums meet (wr_peer_barrier carries them) between the halves.
+ *   sumsq_out[0..3)  = this rank's sums of squares of its gathered user / pos / neg ego rows
+ *   scatter: g[row] += reg_weight / B_global * row / sqrt(sumsq_global[.]);  if loss_out != NULL,
+ *            loss_out[0] += reg_weight * (sum of the three norms) / B_global   (identical on every rank)
+ */
+int wr_embloss_sumsq_sharded(const wr_shards *host_T, const int64_t *user, const int64_t *pos, const int64_t *neg,
+                             int64_t B, int D, float *sumsq_out, void *ws, void *stream);
+int wr_embloss_scatter_sharded(const wr_shards *host_T, const wr_shards *host_Gd, const int64_t *user,
+                               const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D,
+                               float reg_weight, const float *sumsq_global, float *loss_out, void *ws,
+                               void *stream);
+
+/* wr_gather_rows_sharded: out[b] = row idx[b] of the sharded user (which = 0) or item (which = 1) table, read
+ * from its owner.  Used by the evaluation to fetch the user rows and the target-item rows of a batch. */
+int wr_gather_rows_sharded(const wr_shards *host_T, int which, const int64_t *idx, int64_t B, int D, float *out,
+                           void *ws, void *stream);
+
+/* wr_csr_spmm_sharded: wr_csr_spmm for this rank's rows of the adjacency (local row l is node l * world + rank of
+ * the user block for l < rows_u_local, else of the item block), column ids GLOBAL node ids; X rows are read from
+ * their owners through host_X (the fused "all-gather of the layer output + SpMM": no gathered copy of X ever
+ * exists); Y / add / acc_in / acc_out are this rank's local [n_local, D] slabs.
+ */
+int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_local, int D,
+                        const wr_shards *host_X, float *Y, float *add, int zero_add, const float *acc_in,
+                        float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream);
+
+/* wr_eval_rank_topk_shard: wr_eval_rank_topk against ONE item shard.
+ *   Urows   [R, D]  the eval rows' user embeddings, already gathered (wr_gather_rows_sharded)
+ *   target  [R]     INPUT: the target scores (wr_rowdot over the gathered rows; precision 1: over bf16-rounded rows)
+ *   Iemb    [n_items_local, D] this rank's item rows;  hist_ptr / hist_idx: per USER (indexed by user[r]), holding
+ *                   only this shard's items as LOCAL indices, ascending;  pos_local[r]: local index of the target
+ *                   if this shard owns it, else -1
+ *   rank[r] = 1 + #{local j not in hist : score > target[r]}   =>   global rank = 1 + sum over shards (rank - 1)
+ *   topk_idx: LOCAL indices (global item = local * world + shard).
+ */
+int wr_eval_rank_topk_shard(const float *Urows, const float *Iemb, const int64_t *user, const int64_t *pos_local,
+                            int64_t R, int64_t n_users, int64_t n_items_local, int D, const int64_t *hist_ptr,
+                            const int32_t *hist_idx, int k, int precision, const float *target, int32_t *topk_idx,
+                            float *topk_val, int32_t *rank, void *scratch, void *ws, void *stream);
+
+/* wr_rowdot: out[r] = sum_d A[r,d] * B[r,d] as the fp32 FMA chain d = 0..D-1 the scoring kernels use
+ * (round_bf16 != 0: operands rounded to bf16 first, as precision 1 does). */
+int wr_rowdot(const float *A, const float *B, int64_t R, int D, int round_bf16, float *out, void *stream);
+
+/* wr_topk_merge: final k-way merge of the shards' candidates.  val / idx: [world, R, k] (idx already GLOBAL item
+ * ids, unfilled slots -1 / -inf); out: the k best per row, best first, ties to the lower id. */
+int wr_topk_merge(const float *val, const int32_t *idx, int world, int64_t R, int k, float *out_val,
+                  int32_t *out_idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,22 @@ SIGNATURES = {
     'wr_metrics': (_int, [_p, _i64, _c.POINTER(_int), _int, _p, _p, _p]),
     'wr_gather_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
     'wr_scatter_add_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
+    # ---- row-sharded tables over NVLink peer memory ----
+    'wr_peer_alloc': (_int, [_sz, _c.POINTER(_p)]),
+    'wr_peer_free': (_int, [_p]),
+    'wr_peer_export': (_int, [_p, _c.c_char_p]),
+    'wr_peer_open': (_int, [_c.c_char_p, _c.POINTER(_p)]),
+    'wr_peer_close': (_int, [_p]),
+    'wr_peer_barrier': (_int, [_p, _int, _int, _c.c_uint32, _p, _p, _int, _p, _p]),
+    'wr_bpr_fwd_bwd_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_embloss_sumsq_sharded': (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _p]),
+    'wr_embloss_scatter_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _p, _p, _p, _p]),
+    'wr_gather_rows_sharded': (_int, [_p, _int, _p, _i64, _int, _p, _p, _p]),
+    'wr_csr_spmm_sharded': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
+    'wr_eval_rank_topk_shard': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p,
+                                       _p, _p, _p]),
+    'wr_rowdot': (_int, [_p, _p, _i64, _int, _int, _p, _p]),
+    'wr_topk_merge': (_int, [_p, _p, _int, _i64, _int, _p, _p, _p]),
 }
 
 _lib = None
@@ -284,3 +300,147 @@ def gather_rows(T, idx, ws, out=None):
 def scatter_add_rows(G, idx, rows, ws):
     check(load().wr_scatter_add_rows(ptr(G, F32), ptr(idx, I64), idx.numel(), G.shape[1], G.shape[0],
                                      ptr(rows, F32), ws.ptr, stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------------------
+# row-sharded tables over NVLink peer memory (include/whisprrec_b200.h, "one 8 x B200 box")
+# ------------------------------------------------------------------------------------------------------
+MAX_WORLD, PEER_VALUES = 8, 4
+
+
+class ShardsStruct(ctypes.Structure):
+    """Mirror of `wr_shards`."""
+    _fields_ = [('base', _p * MAX_WORLD), ('world', _c.c_int32), ('rank', _c.c_int32), ('n_users', _i64),
+                ('n_items', _i64), ('rows_u_local', _i64), ('rows_i_local', _i64)]
+
+
+class PeerBlock:
+    """A zero-filled cudaMalloc'd block that other processes on the box can map (cudaIpc*)."""
+
+    def __init__(self, nbytes, device):
+        self.device, self.nbytes = torch.device(device), int(nbytes)
+        out = _p()
+        with torch.cuda.device(self.device):
+            check(load().wr_peer_alloc(self.nbytes, ctypes.byref(out)))
+        self.ptr = out.value
+        self._opened = []
+
+    def handle(self):
+        buf = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            check(load().wr_peer_export(self.ptr, buf))
+        return buf.raw
+
+    def open_peer(self, handle):
+        out = _p()
+        with torch.cuda.device(self.device):
+            check(load().wr_peer_open(handle, ctypes.byref(out)))
+        self._opened.append(out.value)
+        return out.value
+
+    def tensor(self, offset, shape, dtype):
+        """A torch view of [offset, offset + bytes) of the block (the block owns the memory)."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        assert offset % 16 == 0 and offset + n * itemsize <= self.nbytes
+        typestr = {torch.float32: '<f4', torch.int32: '<i4', torch.uint32: '<u4', torch.int64: '<i8',
+                   torch.uint8: '|u1'}[dtype]
+
+        class _View:
+            __cuda_array_interface__ = {'shape': tuple(int(d) for d in shape), 'typestr': typestr,
+                                        'data': (self.ptr + offset, False), 'version': 2}
+        v = _View()
+        v._owner = self
+        t = torch.as_tensor(v, device=self.device)
+        t._wr_owner = self
+        return t
+
+    def close(self):
+        lib = load()
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                lib.wr_peer_close(p)
+            self._opened = []
+            if self.ptr:
+                lib.wr_peer_free(self.ptr)
+                self.ptr = None
+
+
+def peer_barrier(flag_ptrs, slot_ptrs, world, rank, epoch, values_in=None, sums_out=None):
+    """flag_ptrs / slot_ptrs: lists of `world` raw device pointers (every rank's flag / slot array as mapped here)."""
+    FA = _p * MAX_WORLD
+    fa = FA(*(list(flag_ptrs) + [None] * (MAX_WORLD - world)))
+    sa = FA(*(list(slot_ptrs) + [None] * (MAX_WORLD - world)))
+    n = 0 if values_in is None else values_in.numel()
+    check(load().wr_peer_barrier(ctypes.addressof(fa), world, rank, epoch, ctypes.addressof(sa), ptr(values_in, F32), n,
+                                 ptr(sums_out, F32), stream_ptr()))
+
+
+def bpr_fwd_bwd_sharded(T, Gd, user, pos, neg, B_global, D, loss_out, ws, gamma=1e-10, grad_scale=1.0):
+    check(load().wr_bpr_fwd_bwd_sharded(ctypes.addressof(T), ctypes.addressof(Gd), ptr(user, I64), ptr(pos, I64),
+                                        ptr(neg, I64), user.numel(), B_global, D, gamma, grad_scale,
+                                        ptr(loss_out, F32), ws.ptr, stream_ptr()))
+
+
+def embloss_sumsq_sharded(T, user, pos, neg, D, sumsq_out, ws):
+    check(load().wr_embloss_sumsq_sharded(ctypes.addressof(T), ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
+                                          user.numel(), D, ptr(sumsq_out, F32), ws.ptr, stream_ptr()))
+
+
+def embloss_scatter_sharded(T, Gd, user, pos, neg, B_global, D, reg_weight, sumsq_global, loss_out, ws):
+    check(load().wr_embloss_scatter_sharded(ctypes.addressof(T), ctypes.addressof(Gd), ptr(user, I64), ptr(pos, I64),
+                                            ptr(neg, I64), user.numel(), B_global, D, reg_weight,
+                                            ptr(sumsq_global, F32), ptr(loss_out, F32), ws.ptr, stream_ptr()))
+
+
+def gather_rows_sharded(T, which, idx, D, ws, out=None):
+    if out is None:
+        out = torch.empty((idx.numel(), D), dtype=F32, device=idx.device)
+    check(load().wr_gather_rows_sharded(ctypes.addressof(T), which, ptr(idx, I64), idx.numel(), D, ptr(out, F32),
+                                        ws.ptr, stream_ptr()))
+    return out
+
+
+def csr_spmm_sharded(rowptr, col, val, n_local, D, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None,
+                     acc_div=1.0, plan=None):
+    check(load().wr_csr_spmm_sharded(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), n_local, D, ctypes.addressof(X),
+                                     ptr(Y, F32), ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32),
+                                     acc_div, None if plan is None else plan.ref(), stream_ptr()))
+
+
+def rowdot(A, B, round_bf16=False):
+    out = torch.empty(A.shape[0], dtype=F32, device=A.device)
+    check(load().wr_rowdot(ptr(A, F32), ptr(B, F32), A.shape[0], A.shape[1], int(round_bf16), ptr(out, F32),
+                           stream_ptr()))
+    return out
+
+
+def eval_rank_topk_shard(Urows, Iemb, user, pos_local, n_users, hist_ptr, hist_idx, target, ws, k=0, precision=0):
+    """One item shard: returns (rank int32 [R] = 1 + local count, topk_idx LOCAL int32 [R,k] | None, topk_val | None)."""
+    R, D = user.numel(), Urows.shape[1]
+    dev = Urows.device
+    rank = torch.empty(R, dtype=I32, device=dev)
+    tki = torch.empty((R, k), dtype=I32, device=dev) if k > 0 else None
+    tkv = torch.empty((R, k), dtype=F32, device=dev) if k > 0 else None
+    nbytes = load().wr_eval_scratch_bytes(R, Iemb.shape[0], D, precision)
+    scratch = None
+    if nbytes:
+        scratch = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        off = (-scratch.data_ptr()) % 1024
+        scratch = scratch[off:off + nbytes]
+    check(load().wr_eval_rank_topk_shard(ptr(Urows, F32), ptr(Iemb, F32), ptr(user, I64), ptr(pos_local, I64), R,
+                                         n_users, Iemb.shape[0], D, ptr(hist_ptr, I64), ptr(hist_idx, I32), k,
+                                         precision, ptr(target, F32), ptr(tki, I32), ptr(tkv, F32), ptr(rank, I32),
+                                         None if scratch is None else scratch.data_ptr(), ws.ptr, stream_ptr()))
+    return rank, tki, tkv
+
+
+def topk_merge(val, idx, k):
+    """val / idx: [world, R, k] candidates with GLOBAL item ids -> ([R, k] values, [R, k] ids)."""
+    world, R = val.shape[0], val.shape[1]
+    ov = torch.empty((R, k), dtype=F32, device=val.device)
+    oi = torch.empty((R, k), dtype=I32, device=val.device)
+    check(load().wr_topk_merge(ptr(val, F32), ptr(idx, I32), world, R, k, ptr(ov, F32), ptr(oi, I32), stream_ptr()))
+    return ov, oi

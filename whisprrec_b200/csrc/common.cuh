@@ -22,6 +22,8 @@ struct WrWorkspace {
         if (e__ != cudaSuccess) return (int)e__; \
     } while (0)
 
+int wr_check_shards(const wr_shards *s);   // train_kernels.cu
+
 static inline bool wr_aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 namespace wr {
@@ -107,6 +109,38 @@ struct RowGroup {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) r[v] = f4_zero();
     }
+};
+
+// ---- where a table row lives: one GPU, or the cyclic row shards of a multi-GPU job reached through peer memory ----
+struct LocalTabs {
+    const float *U, *I;
+    float *gU, *gI;
+    __device__ __forceinline__ const float *urow(int64_t u, int D) const { return U + u * D; }
+    __device__ __forceinline__ const float *irow(int64_t i, int D) const { return I + i * D; }
+    __device__ __forceinline__ float *gurow(int64_t u, int D) const { return gU + u * D; }
+    __device__ __forceinline__ float *girow(int64_t i, int D) const { return gI + i * D; }
+};
+
+// user u -> rank u % world, local row u / world; item i -> rank i % world, local row rows_u_local + i / world.
+// Ids are < 2^31 (checked on the host), so the divisions are 32-bit.
+__device__ __forceinline__ float *shard_user_row(const wr_shards &s, int64_t u, int D) {
+    const uint32_t q = (uint32_t)u / (uint32_t)s.world, r = (uint32_t)u - q * (uint32_t)s.world;
+    return s.base[r] + (int64_t)q * D;
+}
+__device__ __forceinline__ float *shard_item_row(const wr_shards &s, int64_t i, int D) {
+    const uint32_t q = (uint32_t)i / (uint32_t)s.world, r = (uint32_t)i - q * (uint32_t)s.world;
+    return s.base[r] + (s.rows_u_local + (int64_t)q) * D;
+}
+__device__ __forceinline__ float *shard_node_row(const wr_shards &s, int64_t n, int D) {
+    return n < s.n_users ? shard_user_row(s, n, D) : shard_item_row(s, n - s.n_users, D);
+}
+
+struct ShardTabs {
+    wr_shards t, g;
+    __device__ __forceinline__ const float *urow(int64_t u, int D) const { return shard_user_row(t, u, D); }
+    __device__ __forceinline__ const float *irow(int64_t i, int D) const { return shard_item_row(t, i, D); }
+    __device__ __forceinline__ float *gurow(int64_t u, int D) const { return shard_user_row(g, u, D); }
+    __device__ __forceinline__ float *girow(int64_t i, int D) const { return shard_item_row(g, i, D); }
 };
 
 }  // namespace wr

@@ -23,6 +23,9 @@ struct EvalParams {
     float *scores;  // optional dense [R, n_items] output (unmasked), the reference's full_predict
     int splits, tiles_per_split, n_tiles;
     WrWorkspace *ws;
+    // item-shard mode (wr_eval_rank_topk_shard): Uemb holds the R gathered user rows, the target scores are an
+    // input (the target item may live on another shard: pos = -1) and `target` is not written
+    const float *target_in;
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -62,7 +65,7 @@ __global__ void __launch_bounds__(256) eval_rank_kernel(EvalParams p) {
         float4 x = f4_zero();
         if (r < p.R) {
             const int64_t u = p.user[r];
-            if ((uint64_t)u < (uint64_t)p.n_users) x = ldg4(p.Uemb + u * D + 4 * v);
+            if ((uint64_t)u < (uint64_t)p.n_users) x = ldg4(p.Uemb + (p.target_in ? r : u) * D + 4 * v);
         }
         *reinterpret_cast<float4 *>(As + i * LD + 4 * v) = x;
     }
@@ -92,17 +95,21 @@ __global__ void __launch_bounds__(256) eval_rank_kernel(EvalParams p) {
         float st = 0.f;
         if (r < p.R) {
             const int64_t u = p.user[r], it = p.pos[r];
-            if ((uint64_t)u < (uint64_t)p.n_users && (uint64_t)it < (uint64_t)p.n_items) {
+            if ((uint64_t)u < (uint64_t)p.n_users && (p.target_in || (uint64_t)it < (uint64_t)p.n_items)) {
                 row_live = true;
-                const float *a = As + tid * LD;
-                const float *b = p.Iemb + it * D;
+                if (p.target_in) {
+                    st = p.target_in[r];
+                } else {
+                    const float *a = As + tid * LD;
+                    const float *b = p.Iemb + it * D;
 #pragma unroll 4
-                for (int v = 0; v < D4; ++v) {
-                    const float4 x = *reinterpret_cast<const float4 *>(a + 4 * v), y = ldg4(b + 4 * v);
-                    st = fmaf(x.x, y.x, st);
-                    st = fmaf(x.y, y.y, st);
-                    st = fmaf(x.z, y.z, st);
-                    st = fmaf(x.w, y.w, st);
+                    for (int v = 0; v < D4; ++v) {
+                        const float4 x = *reinterpret_cast<const float4 *>(a + 4 * v), y = ldg4(b + 4 * v);
+                        st = fmaf(x.x, y.x, st);
+                        st = fmaf(x.y, y.y, st);
+                        st = fmaf(x.z, y.z, st);
+                        st = fmaf(x.w, y.w, st);
+                    }
                 }
                 cur = p.hist_ptr[u];
                 hend = p.hist_ptr[u + 1];
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(256) eval_rank_kernel(EvalParams p) {
                     if (p.hist_idx[mid] < first) lo = mid + 1; else hi = mid;
                 }
                 cur = lo;
-                if (blockIdx.y == 0) p.target[r] = st;
+                if (blockIdx.y == 0 && !p.target_in) p.target[r] = st;
             } else {
                 atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
             }
@@ -317,14 +324,16 @@ using namespace wr;
 // eval_tcgen05.cu
 int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                     int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
-                    int32_t *rank, float *target, float *scores_out, void *scratch, WrWorkspace *ws, cudaStream_t st);
+                    int32_t *rank, float *target, const float *target_in, float *scores_out, void *scratch,
+                    WrWorkspace *ws, cudaStream_t st);
 
-extern "C" int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos,
-                                 int64_t R, int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr,
-                                 const int32_t *hist_idx, int k, int precision, int32_t *topk_idx, float *topk_val,
-                                 int32_t *rank, float *target, float *scores_out, void *scratch, void *ws,
-                                 void *stream) {
-    if (!Uemb || !Iemb || !user || !pos || !hist_ptr || !hist_idx || !rank || !target || !ws) return WR_E_NULL;
+static int eval_rank_topk_impl(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos,
+                               int64_t R, int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr,
+                               const int32_t *hist_idx, int k, int precision, int32_t *topk_idx, float *topk_val,
+                               int32_t *rank, float *target, const float *target_in, float *scores_out,
+                               void *scratch, void *ws, void *stream) {
+    if (!Uemb || !Iemb || !user || !pos || !hist_ptr || !hist_idx || !rank || !ws) return WR_E_NULL;
+    if (!target && !target_in) return WR_E_NULL;
     if ((topk_idx == nullptr) != (topk_val == nullptr)) return WR_E_NULL;
     if (R <= 0 || n_users <= 0 || n_items <= 0 || n_items > INT32_MAX - 1024) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
@@ -335,11 +344,11 @@ extern "C" int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int
     if (precision == 1) {
         if (topk) return WR_E_PRECISION;      // top-k lists come from the fp32 path
         return wr_eval_rank_tc(Uemb, Iemb, user, pos, R, n_users, n_items, D, hist_ptr, hist_idx, rank, target,
-                               scores_out, scratch, (WrWorkspace *)ws, st);
+                               target_in, scores_out, scratch, (WrWorkspace *)ws, st);
     }
     if (precision != 0) return WR_E_PRECISION;
     EvalParams p{Uemb, Iemb, user, pos, R, n_users, n_items, hist_ptr, hist_idx, topk ? k : 1,
-                 topk_idx, topk_val, rank, target, scores_out, 1, 0, 0, (WrWorkspace *)ws};
+                 topk_idx, topk_val, rank, target, scores_out, 1, 0, 0, (WrWorkspace *)ws, target_in};
     p.n_tiles = (int)((n_items + EV_TI - 1) / EV_TI);
     const int64_t row_tiles64 = (R + EV_TR - 1) / EV_TR;
     if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
@@ -366,6 +375,26 @@ extern "C" int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int
     }
 #undef WR_EVAL_CALL
     return rc;
+}
+
+extern "C" int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos,
+                                 int64_t R, int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr,
+                                 const int32_t *hist_idx, int k, int precision, int32_t *topk_idx, float *topk_val,
+                                 int32_t *rank, float *target, float *scores_out, void *scratch, void *ws,
+                                 void *stream) {
+    if (!target) return WR_E_NULL;
+    return eval_rank_topk_impl(Uemb, Iemb, user, pos, R, n_users, n_items, D, hist_ptr, hist_idx, k, precision,
+                               topk_idx, topk_val, rank, target, nullptr, scores_out, scratch, ws, stream);
+}
+
+extern "C" int wr_eval_rank_topk_shard(const float *Urows, const float *Iemb, const int64_t *user,
+                                       const int64_t *pos_local, int64_t R, int64_t n_users, int64_t n_items_local,
+                                       int D, const int64_t *hist_ptr, const int32_t *hist_idx, int k, int precision,
+                                       const float *target, int32_t *topk_idx, float *topk_val, int32_t *rank,
+                                       void *scratch, void *ws, void *stream) {
+    if (!target) return WR_E_NULL;
+    return eval_rank_topk_impl(Urows, Iemb, user, pos_local, R, n_users, n_items_local, D, hist_ptr, hist_idx, k,
+                               precision, topk_idx, topk_val, rank, nullptr, target, nullptr, scratch, ws, stream);
 }
 
 extern "C" int wr_metrics(const int32_t *rank, int64_t R, const int *host_ks, int nk, double *out, void *ws,

@@ -161,6 +161,23 @@ __global__ void __launch_bounds__(256) pack_users_kernel(const float *__restrict
     }
 }
 
+// item-shard mode: the user rows arrive gathered ([R, D], one per eval row) and the target scores are an input
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict__ Urows, const int64_t *user, int64_t R,
+                                                         int64_t n_users, int D, __nv_bfloat16 *A, uint8_t *row_ok,
+                                                         WrWorkspace *ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const bool ok = (uint64_t)user[r] < (uint64_t)n_users;
+        for (int d = lane; d < D; d += 32) A[r * D + d] = __float2bfloat16_rn(ok ? Urows[r * D + d] : 0.f);
+        if (lane == 0) {
+            row_ok[r] = ok ? 1 : 0;
+            if (!ok) atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the scoring kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -456,7 +473,8 @@ extern "C" size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int p
 // precision-1 body of wr_eval_rank_topk (eval_kernels.cu dispatches here)
 int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                     int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
-                    int32_t *rank, float *target, float *scores_out, void *scratch, WrWorkspace *ws, cudaStream_t st) {
+                    int32_t *rank, float *target, const float *target_in, float *scores_out, void *scratch,
+                    WrWorkspace *ws, cudaStream_t st) {
     if (D != 64 && D != 128) return WR_E_DIM;
     if (!scratch) return WR_E_NULL;
     if ((reinterpret_cast<uintptr_t>(scratch) & 1023u) != 0) return WR_E_ALIGN;
@@ -468,8 +486,11 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
     const int64_t n4 = n_items * D / 4;
     pack_items_bf16_kernel<<<(int)min((int64_t)8 * kSMs, (n4 + 255) / 256), 256, 0, st>>>(Iemb, n4, Bm);
     WR_CHECK_LAUNCH();
-    pack_users_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, Iemb, user, pos, R, n_users,
-                                                                                n_items, D, A, target, row_ok, ws);
+    if (target_in)
+        pack_rows_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, user, R, n_users, D, A, row_ok, ws);
+    else
+        pack_users_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, Iemb, user, pos, R, n_users,
+                                                                                    n_items, D, A, target, row_ok, ws);
     WR_CHECK_LAUNCH();
 
     CUtensorMap ma, mb;
@@ -478,7 +499,8 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
     rc = make_map(&mb, Bm, n_items, D, TC_BN);
     if (rc) return rc;
 
-    TcParams p{user, pos, R, n_users, n_items, hist_ptr, hist_idx, target, row_ok, rank, scores_out, 1, 0, 0};
+    TcParams p{user, pos, R, n_users, n_items, hist_ptr, hist_idx, target_in ? target_in : target, row_ok, rank,
+               scores_out, 1, 0, 0};
     p.n_tiles = (int)((n_items + TC_BN - 1) / TC_BN);
     const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
     if (row_tiles64 > INT32_MAX) return WR_E_SIZE;

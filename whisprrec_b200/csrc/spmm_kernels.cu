@@ -4,12 +4,24 @@
 
 namespace wr {
 
-struct SpmmParams {
+// where the rows of X live: this GPU, or the row shards of all GPUs (the layer output is never all-gathered: a
+// neighbour's row is read from its owner over NVLink inside the SpMM)
+struct LocalX {
+    const float *X;
+    __device__ __forceinline__ const float *row(int c, int D) const { return X + (int64_t)c * D; }
+};
+struct ShardX {
+    wr_shards s;
+    __device__ __forceinline__ const float *row(int c, int D) const { return shard_node_row(s, c, D); }
+};
+
+template <class XACC>
+struct SpmmParamsT {
     const int64_t *rowptr;
     const int32_t *col;
     const float *val;
     int64_t N;
-    const float *X;
+    XACC X;
     float *Y;
     float *add;
     int zero_add;
@@ -19,10 +31,11 @@ struct SpmmParams {
     wr_spmm_plan plan;       // by value; long_threshold = INT64_MAX when there is no plan
     int row_blocks;          // CTAs [0, row_blocks) walk rows, the rest walk the chunks of split rows
 };
+using SpmmParams = SpmmParamsT<LocalX>;
 
 // acc += sum_{e in [beg, end)} val[e] * X[col[e]] for the lane's slice of the row (partial over lane groups).
-template <int LPR, int VPL, int UNROLL>
-__device__ __forceinline__ void spmm_accumulate(const SpmmParams &p, int64_t beg, int64_t end, int lane, int sub,
+template <int LPR, int VPL, int UNROLL, class XACC>
+__device__ __forceinline__ void spmm_accumulate(const SpmmParamsT<XACC> &p, int64_t beg, int64_t end, int lane, int sub,
                                                 int grp, float4 (&acc)[VPL]) {
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
@@ -44,7 +57,7 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParams &p, int64_t beg
                 const int cc = __shfl_sync(0xffffffffu, c, e & 31);
                 ww[u] = __shfl_sync(0xffffffffu, w, e & 31);
                 if (e < cnt) {
-                    RG::load(p.X + (int64_t)cc * D, sub, x[u]);
+                    RG::load(p.X.row(cc, D), sub, x[u]);
                 } else {
                     RG::zero(x[u]);
                     ww[u] = 0.f;
@@ -69,7 +82,8 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParams &p, int64_t beg
 }
 
 // y (+ add) -> Y, running layer sum / mean.  Called by the lanes of group 0 with their slice of the finished row.
-__device__ __forceinline__ void spmm_row_epilogue(const SpmmParams &p, int64_t off, float4 y) {
+template <class XACC>
+__device__ __forceinline__ void spmm_row_epilogue(const SpmmParamsT<XACC> &p, int64_t off, float4 y) {
     if (p.add) {
         float4 *ap = reinterpret_cast<float4 *>(p.add + off);
         y = add4(y, *ap);
@@ -89,8 +103,8 @@ __device__ __forceinline__ void spmm_row_epilogue(const SpmmParams &p, int64_t o
 // lane each), UNROLL steps in flight.  Column ids / weights are read 32 at a time, coalesced, and handed round
 // with shuffles.  Slices of a split row are reduced into plan.slot_partial with 128-bit REDs; the warp that
 // arrives last owns the row's epilogue, so one launch covers everything and power-law rows cannot become the tail.
-template <int LPR, int VPL, int UNROLL>
-__global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParams p) {
+template <int LPR, int VPL, int UNROLL, class XACC>
+__global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParamsT<XACC> p) {
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParams p) {
             if (end - beg > p.plan.long_threshold) continue;      // split rows are handled below
             float4 acc[VPL];
             RG::zero(acc);
-            spmm_accumulate<LPR, VPL, UNROLL>(p, beg, end, lane, sub, grp, acc);
+            spmm_accumulate<LPR, VPL, UNROLL, XACC>(p, beg, end, lane, sub, grp, acc);
             if (grp == 0) {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) spmm_row_epilogue(p, row * D + 4 * (sub + v * LPR), acc[v]);
@@ -117,7 +131,7 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParams p) {
             const int slot = __ldg(p.plan.chunk_slot + ch);
             float4 acc[VPL];
             RG::zero(acc);
-            spmm_accumulate<LPR, VPL, UNROLL>(p, beg, end, lane, sub, grp, acc);
+            spmm_accumulate<LPR, VPL, UNROLL, XACC>(p, beg, end, lane, sub, grp, acc);
             float *part = p.plan.slot_partial + (int64_t)slot * D;
             if (grp == 0) {
 #pragma unroll
@@ -148,7 +162,8 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParams p) {
 }
 
 // Any D % 4 == 0.
-__global__ void __launch_bounds__(256) csr_spmm_generic_kernel(SpmmParams p, int D) {
+template <class XACC>
+__global__ void __launch_bounds__(256) csr_spmm_generic_kernel(SpmmParamsT<XACC> p, int D) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(256) csr_spmm_generic_kernel(SpmmParams p, int
         for (int v = lane; v < D4; v += 32) {
             float4 acc = f4_zero();
             for (int64_t e = beg; e < end; ++e)
-                acc = fma4(__ldg(p.val + e), ldg4(p.X + (int64_t)__ldg(p.col + e) * D + 4 * v), acc);
+                acc = fma4(__ldg(p.val + e), ldg4(p.X.row(__ldg(p.col + e), D) + 4 * v), acc);
             spmm_row_epilogue(p, row * D + 4 * v, acc);
         }
     }
@@ -183,19 +198,9 @@ __global__ void __launch_bounds__(256) csr_norm_weights_kernel(const int64_t *__
 
 using namespace wr;
 
-extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D,
-                           const float *X, float *Y, float *add, int zero_add, const float *acc_in,
-                           float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream) {
-    if (!rowptr || !col || !val || !X) return WR_E_NULL;
-    if (!Y && !acc_out) return WR_E_NULL;
-    if (acc_out && !acc_in) return WR_E_NULL;
-    if (N <= 0) return WR_E_SIZE;
-    if (D <= 0 || (D & 3)) return WR_E_DIM;
-    if (!wr_aligned16(X) || (Y && !wr_aligned16(Y)) || (add && !wr_aligned16(add)) ||
-        (acc_in && !wr_aligned16(acc_in)) || (acc_out && !wr_aligned16(acc_out)))
-        return WR_E_ALIGN;
-    if (X == Y || X == acc_out) return WR_E_SIZE;
-    SpmmParams p{rowptr, col, val, N, X, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0};
+template <class XACC>
+static int spmm_launch(SpmmParamsT<XACC> &p, int D, const wr_spmm_plan *host_plan, cudaStream_t st) {
+    p.plan = wr_spmm_plan{};
     p.plan.long_threshold = INT64_MAX;
     const bool fast = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
     if (host_plan && fast && host_plan->n_chunks > 0) {
@@ -206,23 +211,61 @@ extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const floa
         if (q.long_threshold < 1 || q.n_long < 1 || !wr_aligned16(q.slot_partial)) return WR_E_SIZE;
         p.plan = q;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    int64_t g = (N + 7) / 8;
+    int64_t g = (p.N + 7) / 8;
     if (g > 16 * kSMs) g = 16 * kSMs;
     p.row_blocks = (int)g;
     int64_t gc = (p.plan.n_chunks + 7) / 8;
     if (gc > 16 * kSMs) gc = 16 * kSMs;
     const int grid = (int)(g + gc);
     switch (D) {
-        case 16: csr_spmm_kernel<4, 1, 2><<<grid, 256, 0, st>>>(p); break;
-        case 32: csr_spmm_kernel<8, 1, 2><<<grid, 256, 0, st>>>(p); break;
-        case 64: csr_spmm_kernel<16, 1, 8><<<grid, 256, 0, st>>>(p); break;
-        case 128: csr_spmm_kernel<32, 1, 4><<<grid, 256, 0, st>>>(p); break;
-        case 256: csr_spmm_kernel<32, 2, 2><<<grid, 256, 0, st>>>(p); break;
-        default: csr_spmm_generic_kernel<<<p.row_blocks, 256, 0, st>>>(p, D);
+        case 16: csr_spmm_kernel<4, 1, 2, XACC><<<grid, 256, 0, st>>>(p); break;
+        case 32: csr_spmm_kernel<8, 1, 2, XACC><<<grid, 256, 0, st>>>(p); break;
+        case 64: csr_spmm_kernel<16, 1, 8, XACC><<<grid, 256, 0, st>>>(p); break;
+        case 128: csr_spmm_kernel<32, 1, 4, XACC><<<grid, 256, 0, st>>>(p); break;
+        case 256: csr_spmm_kernel<32, 2, 2, XACC><<<grid, 256, 0, st>>>(p); break;
+        default: csr_spmm_generic_kernel<XACC><<<p.row_blocks, 256, 0, st>>>(p, D);
     }
     WR_CHECK_LAUNCH();
     return WR_OK;
+}
+
+static int spmm_check(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D, float *Y,
+                      float *add, const float *acc_in, float *acc_out) {
+    if (!rowptr || !col || !val) return WR_E_NULL;
+    if (!Y && !acc_out) return WR_E_NULL;
+    if (acc_out && !acc_in) return WR_E_NULL;
+    if (N <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if ((Y && !wr_aligned16(Y)) || (add && !wr_aligned16(add)) || (acc_in && !wr_aligned16(acc_in)) ||
+        (acc_out && !wr_aligned16(acc_out)))
+        return WR_E_ALIGN;
+    return WR_OK;
+}
+
+extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D,
+                           const float *X, float *Y, float *add, int zero_add, const float *acc_in,
+                           float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream) {
+    if (!X) return WR_E_NULL;
+    const int rc = spmm_check(rowptr, col, val, N, D, Y, add, acc_in, acc_out);
+    if (rc) return rc;
+    if (!wr_aligned16(X)) return WR_E_ALIGN;
+    if (X == Y || X == acc_out) return WR_E_SIZE;
+    SpmmParams p{rowptr, col, val, N, {X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0};
+    return spmm_launch(p, D, host_plan, (cudaStream_t)stream);
+}
+
+extern "C" int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_local, int D,
+                                   const wr_shards *host_X, float *Y, float *add, int zero_add, const float *acc_in,
+                                   float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream) {
+    if (!host_X) return WR_E_NULL;
+    int rc = wr_check_shards(host_X);
+    if (rc) return rc;
+    rc = spmm_check(rowptr, col, val, n_local, D, Y, add, acc_in, acc_out);
+    if (rc) return rc;
+    if (n_local != host_X->rows_u_local + host_X->rows_i_local) return WR_E_SIZE;
+    if (host_X->base[host_X->rank] == Y || host_X->base[host_X->rank] == acc_out) return WR_E_SIZE;
+    SpmmParamsT<ShardX> p{rowptr, col, val, n_local, {*host_X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0};
+    return spmm_launch(p, D, host_plan, (cudaStream_t)stream);
 }
 
 extern "C" int wr_csr_norm_weights(const int64_t *rowptr, const int32_t *col, const float *dinv, int64_t N,

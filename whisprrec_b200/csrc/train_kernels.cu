@@ -8,15 +8,18 @@ namespace wr {
 // BPR forward + backward.  One group of LPR lanes per interaction; the three rows stay in registers
 // between the dot products and the gradient reductions, so each row is read exactly once.
 // ------------------------------------------------------------------------------------------------------
-struct BprParams {
-    const float *U, *I;
+template <class TABS>
+struct BprParamsT {
+    TABS tabs;
     const int64_t *user, *pos, *neg;
     int64_t B, n_users, n_items;
-    float gamma, coef;  // coef = grad_scale / B
-    float *gU, *gI, *loss_out;
+    float gamma, coef;  // coef = grad_scale / (rows of the whole batch)
+    float loss_div;     // rows of the whole batch (= B on one GPU)
+    float *loss_out;
     int accumulate_loss;
     WrWorkspace *ws;
 };
+using BprParams = BprParamsT<LocalTabs>;
 
 __device__ __forceinline__ void bpr_pointwise(float sp, float sn, float gamma, float coef, float &loss, float &c) {
     // utils/loss.py:38: -log(gamma + sigmoid(pos - neg)); d/ds+ = -(sig (1-sig)) / (gamma + sig)
@@ -28,7 +31,7 @@ __device__ __forceinline__ void bpr_pointwise(float sp, float sn, float gamma, f
 
 // Deterministic epilogue shared by the loss kernels: per-block partials, summed in block order by the last block.
 __device__ __forceinline__ void finish_loss(float local, float *red, bool *flag, WrWorkspace *ws, int slot,
-                                            int64_t B, float *loss_out, int accumulate) {
+                                            float B, float *loss_out, int accumulate) {
     const float bsum = block_sum(local, red);
     if (threadIdx.x == 0) ws->partial[slot * WR_MAX_PARTIAL_BLOCKS + blockIdx.x] = bsum;
     if (last_block_arrives(&ws->ticket[slot], flag)) {
@@ -38,15 +41,15 @@ __device__ __forceinline__ void finish_loss(float local, float *red, bool *flag,
                 t += __ldcg(&ws->partial[slot * WR_MAX_PARTIAL_BLOCKS + i]);
             t = warp_sum(t);
             if (threadIdx.x == 0) {
-                const float mean = t / (float)B;
+                const float mean = t / B;
                 loss_out[0] = accumulate ? loss_out[0] + mean : mean;
             }
         }
     }
 }
 
-template <int LPR, int VPL>
-__global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParams p) {
+template <int LPR, int VPL, class TABS>
+__global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParamsT<TABS> p) {
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
     __shared__ float red[8];
@@ -69,9 +72,9 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParams p) {
         if (valid && !ok && sub == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
         float4 ue[VPL], pe[VPL], ne[VPL];
         if (ok) {
-            RG::load(p.U + u * D, sub, ue);
-            RG::load(p.I + i * D, sub, pe);
-            RG::load(p.I + j * D, sub, ne);
+            RG::load(p.tabs.urow(u, D), sub, ue);
+            RG::load(p.tabs.irow(i, D), sub, pe);
+            RG::load(p.tabs.irow(j, D), sub, ne);
         } else {
             RG::zero(ue);
             RG::zero(pe);
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParams p) {
             float l, c;
             bpr_pointwise(sp, sn, p.gamma, p.coef, l, c);
             if (sub == 0) local += l;
-            float *gu = p.gU + u * D, *gp = p.gI + i * D, *gn = p.gI + j * D;
+            float *gu = p.tabs.gurow(u, D), *gp = p.tabs.girow(i, D), *gn = p.tabs.girow(j, D);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int off = 4 * (sub + v * LPR);
@@ -99,11 +102,12 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParams p) {
             }
         }
     }
-    finish_loss(local, red, &flag, p.ws, 0, p.B, p.loss_out, p.accumulate_loss);
+    finish_loss(local, red, &flag, p.ws, 0, p.loss_div, p.loss_out, p.accumulate_loss);
 }
 
 // Any D % 4 == 0: a warp per interaction, rows re-read for the gradient (they are L1 hits).
-__global__ void __launch_bounds__(256) bpr_fwd_bwd_generic_kernel(BprParams p, int D) {
+template <class TABS>
+__global__ void __launch_bounds__(256) bpr_fwd_bwd_generic_kernel(BprParamsT<TABS> p, int D) {
     __shared__ float red[8];
     __shared__ bool flag;
     const int lane = threadIdx.x & 31;
@@ -119,7 +123,8 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_generic_kernel(BprParams p, i
             if (lane == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
             continue;
         }
-        const float *ur = p.U + u * D, *pr = p.I + i * D, *nr = p.I + j * D;
+        const float *ur = p.tabs.urow(u, D), *pr = p.tabs.irow(i, D), *nr = p.tabs.irow(j, D);
+        float *gu = p.tabs.gurow(u, D), *gp = p.tabs.girow(i, D), *gn = p.tabs.girow(j, D);
         float sp = 0.f, sn = 0.f;
         for (int v = lane; v < D4; v += 32) {
             const float4 a = ldg4(ur + 4 * v);
@@ -133,27 +138,33 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_generic_kernel(BprParams p, i
         if (lane == 0) local += l;
         for (int v = lane; v < D4; v += 32) {
             const float4 a = ldg4(ur + 4 * v), x = ldg4(pr + 4 * v), y = ldg4(nr + 4 * v);
-            red_add_v4(p.gU + u * D + 4 * v, scale4(sub4(x, y), c));
-            red_add_v4(p.gI + i * D + 4 * v, scale4(a, c));
-            red_add_v4(p.gI + j * D + 4 * v, scale4(a, -c));
+            red_add_v4(gu + 4 * v, scale4(sub4(x, y), c));
+            red_add_v4(gp + 4 * v, scale4(a, c));
+            red_add_v4(gn + 4 * v, scale4(a, -c));
         }
     }
-    finish_loss(local, red, &flag, p.ws, 0, p.B, p.loss_out, p.accumulate_loss);
+    finish_loss(local, red, &flag, p.ws, 0, p.loss_div, p.loss_out, p.accumulate_loss);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // EmbLoss: phase 1 sums squares of the gathered ego rows (per occurrence), phase 2 scatters row/||.||.
 // ------------------------------------------------------------------------------------------------------
-struct EmbParams {
-    const float *U0, *I0;
+template <class TABS>
+struct EmbParamsT {
+    TABS tabs;
     const int64_t *user, *pos, *neg;
     int64_t B, n_users, n_items;
     float reg_weight;
-    float *gU0, *gI0, *loss_out;
+    float inv_rows;          // 1 / rows of the whole batch
+    float *loss_out;         // nullable
+    float *sumsq_out;        // sharded: this rank's three sums of squares go here instead of ws->norms
+    const float *sumsq_in;   // sharded: the three GLOBAL sums of squares
     WrWorkspace *ws;
 };
+using EmbParams = EmbParamsT<LocalTabs>;
 
-__global__ void __launch_bounds__(256) embloss_sumsq_kernel(EmbParams p, int D) {
+template <class TABS>
+__global__ void __launch_bounds__(256) embloss_sumsq_kernel(EmbParamsT<TABS> p, int D) {
     __shared__ float red[8];
     __shared__ bool flag;
     const int lane = threadIdx.x & 31;
@@ -169,8 +180,8 @@ __global__ void __launch_bounds__(256) embloss_sumsq_kernel(EmbParams p, int D) 
         const int64_t u = p.user[b], i = p.pos[b], j = p.neg[b];
         if ((uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
             (uint64_t)j < (uint64_t)p.n_items) {
-            const float4 a = ldg4(p.U0 + u * D + 4 * v), x = ldg4(p.I0 + i * D + 4 * v),
-                         y = ldg4(p.I0 + j * D + 4 * v);
+            const float4 a = ldg4(p.tabs.urow(u, D) + 4 * v), x = ldg4(p.tabs.irow(i, D) + 4 * v),
+                         y = ldg4(p.tabs.irow(j, D) + 4 * v);
             su += dot4(a, a);
             sp += dot4(x, x);
             sn += dot4(y, y);
@@ -189,22 +200,42 @@ __global__ void __launch_bounds__(256) embloss_sumsq_kernel(EmbParams p, int D) 
 #pragma unroll
                 for (int q = 0; q < 3; ++q) t[q] += __ldcg(&p.ws->partial[q * WR_MAX_PARTIAL_BLOCKS + i]);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) t[q] = sqrtf(warp_sum(t[q]));
+            for (int q = 0; q < 3; ++q) t[q] = warp_sum(t[q]);
             if (threadIdx.x == 0) {
-                p.ws->norms[0] = t[0];
-                p.ws->norms[1] = t[1];
-                p.ws->norms[2] = t[2];
-                // utils/loss.py:94-98: (sum of the three norms) / B, scaled by reg_weight at LightGCN.py:175
-                p.loss_out[0] += p.reg_weight * ((t[0] + t[1] + t[2]) / (float)p.B);
+                if (p.sumsq_out) {      // the norms are batch-global: the ranks' sums meet before the square root
+                    p.sumsq_out[0] = t[0];
+                    p.sumsq_out[1] = t[1];
+                    p.sumsq_out[2] = t[2];
+                } else {
+                    t[0] = sqrtf(t[0]);
+                    t[1] = sqrtf(t[1]);
+                    t[2] = sqrtf(t[2]);
+                    p.ws->norms[0] = t[0];
+                    p.ws->norms[1] = t[1];
+                    p.ws->norms[2] = t[2];
+                    // utils/loss.py:94-98: (sum of the three norms) / B, scaled by reg_weight at LightGCN.py:175
+                    p.loss_out[0] += p.reg_weight * ((t[0] + t[1] + t[2]) * p.inv_rows);
+                }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(256) embloss_scatter_kernel(EmbParams p, int D) {
+template <class TABS>
+__global__ void __launch_bounds__(256) embloss_scatter_kernel(EmbParamsT<TABS> p, int D) {
     const int D4 = D >> 2;
-    const float k = p.reg_weight / (float)p.B;
-    const float nu = p.ws->norms[0], np_ = p.ws->norms[1], nn = p.ws->norms[2];
+    const float k = p.reg_weight * p.inv_rows;
+    float nu, np_, nn;
+    if (p.sumsq_in) {
+        nu = sqrtf(p.sumsq_in[0]);
+        np_ = sqrtf(p.sumsq_in[1]);
+        nn = sqrtf(p.sumsq_in[2]);
+        if (p.loss_out && blockIdx.x == 0 && threadIdx.x == 0) p.loss_out[0] += p.reg_weight * ((nu + np_ + nn) * p.inv_rows);
+    } else {
+        nu = p.ws->norms[0];
+        np_ = p.ws->norms[1];
+        nn = p.ws->norms[2];
+    }
     const float ku = nu > 0.f ? k / nu : 0.f, kp = np_ > 0.f ? k / np_ : 0.f, kn = nn > 0.f ? k / nn : 0.f;
     const int64_t total = p.B * D4;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -213,9 +244,9 @@ __global__ void __launch_bounds__(256) embloss_scatter_kernel(EmbParams p, int D
         const int64_t u = p.user[b], i = p.pos[b], j = p.neg[b];
         if ((uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
             (uint64_t)j < (uint64_t)p.n_items) {
-            red_add_v4(p.gU0 + u * D + 4 * v, scale4(ldg4(p.U0 + u * D + 4 * v), ku));
-            red_add_v4(p.gI0 + i * D + 4 * v, scale4(ldg4(p.I0 + i * D + 4 * v), kp));
-            red_add_v4(p.gI0 + j * D + 4 * v, scale4(ldg4(p.I0 + j * D + 4 * v), kn));
+            red_add_v4(p.tabs.gurow(u, D) + 4 * v, scale4(ldg4(p.tabs.urow(u, D) + 4 * v), ku));
+            red_add_v4(p.tabs.girow(i, D) + 4 * v, scale4(ldg4(p.tabs.irow(i, D) + 4 * v), kp));
+            red_add_v4(p.tabs.girow(j, D) + 4 * v, scale4(ldg4(p.tabs.irow(j, D) + 4 * v), kn));
         }
     }
 }
@@ -382,9 +413,9 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 
         if (valid && !ok && sub == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
         float4 ue[VPL], pe[VPL], ne[VPL];
         if (ok) {
-            RG::load(p.U + u * D, sub, ue);
-            RG::load(p.I + i * D, sub, pe);
-            RG::load(p.I + j * D, sub, ne);
+            RG::load(p.tabs.urow(u, D), sub, ue);
+            RG::load(p.tabs.irow(i, D), sub, pe);
+            RG::load(p.tabs.irow(j, D), sub, ne);
         } else {
             RG::zero(ue);
             RG::zero(pe);
@@ -402,7 +433,7 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 
             float l, c;
             bpr_pointwise(sp, sn, p.gamma, p.coef, l, c);
             if (sub == 0) local += l;
-            float *gu = p.gU + u * D, *gp = p.gI + i * D, *gn = p.gI + j * D;
+            float *gu = p.tabs.gurow(u, D), *gp = p.tabs.girow(i, D), *gn = p.tabs.girow(j, D);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int off = 4 * (sub + v * LPR);
@@ -428,7 +459,7 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 
         for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(&p.ws->partial[i]);
         t = warp_sum(t);
         if (threadIdx.x == 0) {
-            const float mean = t / (float)p.B;
+            const float mean = t / p.loss_div;
             p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + mean : mean;
         }
     }
@@ -480,9 +511,45 @@ static inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
     return (int)g;
 }
 
+template <class TABS>
+static int launch_bpr(BprParamsT<TABS> &p, int D, cudaStream_t st) {
+#define WR_BPR_CALL(LPR, VPL)                                                              \
+    {                                                                                      \
+        const int per_block = 8 * (32 / LPR);                                              \
+        const int grid = grid_for(p.B, per_block, 8 * kSMs);                               \
+        bpr_fwd_bwd_kernel<LPR, VPL, TABS><<<grid, 256, 0, st>>>(p);                       \
+    }
+    switch (D) {
+        case 16: WR_BPR_CALL(4, 1) break;
+        case 32: WR_BPR_CALL(8, 1) break;
+        case 64: WR_BPR_CALL(16, 1) break;
+        case 128: WR_BPR_CALL(32, 1) break;
+        case 256: WR_BPR_CALL(32, 2) break;
+        default: {
+            const int grid = grid_for(p.B, 8, 8 * kSMs);
+            bpr_fwd_bwd_generic_kernel<TABS><<<grid, 256, 0, st>>>(p, D);
+        }
+    }
+#undef WR_BPR_CALL
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
 }  // namespace wr
 
 using namespace wr;
+
+int wr_check_shards(const wr_shards *s) {
+    if (s->world < 1 || s->world > WR_MAX_WORLD || s->rank < 0 || s->rank >= s->world) return WR_E_SIZE;
+    if (s->n_users <= 0 || s->n_items <= 0 || s->n_users >= INT32_MAX || s->n_items >= INT32_MAX) return WR_E_SIZE;
+    if (s->rows_u_local != (s->n_users + s->world - 1) / s->world) return WR_E_SIZE;
+    if (s->rows_i_local != (s->n_items + s->world - 1) / s->world) return WR_E_SIZE;
+    for (int g = 0; g < s->world; ++g) {
+        if (!s->base[g]) return WR_E_NULL;
+        if (!wr_aligned16(s->base[g])) return WR_E_ALIGN;
+    }
+    return WR_OK;
+}
 
 extern "C" int wr_bpr_fwd_bwd(const float *U, const float *I, const int64_t *user, const int64_t *pos,
                               const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma,
@@ -492,29 +559,24 @@ extern "C" int wr_bpr_fwd_bwd(const float *U, const float *I, const int64_t *use
     if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
     if (!wr_aligned16(U) || !wr_aligned16(I) || !wr_aligned16(gU) || !wr_aligned16(gI)) return WR_E_ALIGN;
-    BprParams p{U, I, user, pos, neg, B, n_users, n_items, gamma, grad_scale / (float)B,
-                gU, gI, loss_out, accumulate_loss, (WrWorkspace *)ws};
-    cudaStream_t st = (cudaStream_t)stream;
-#define WR_BPR_CALL(LPR, VPL)                                                              \
-    {                                                                                      \
-        const int per_block = 8 * (32 / LPR);                                              \
-        const int grid = grid_for(B, per_block, 8 * kSMs);                                 \
-        bpr_fwd_bwd_kernel<LPR, VPL><<<grid, 256, 0, st>>>(p);                             \
-    }
-    switch (D) {
-        case 16: WR_BPR_CALL(4, 1) break;
-        case 32: WR_BPR_CALL(8, 1) break;
-        case 64: WR_BPR_CALL(16, 1) break;
-        case 128: WR_BPR_CALL(32, 1) break;
-        case 256: WR_BPR_CALL(32, 2) break;
-        default: {
-            const int grid = grid_for(B, 8, 8 * kSMs);
-            bpr_fwd_bwd_generic_kernel<<<grid, 256, 0, st>>>(p, D);
-        }
-    }
-#undef WR_BPR_CALL
-    WR_CHECK_LAUNCH();
-    return WR_OK;
+    BprParams p{{U, I, gU, gI}, user, pos, neg, B, n_users, n_items, gamma, grad_scale / (float)B, (float)B,
+                loss_out, accumulate_loss, (WrWorkspace *)ws};
+    return launch_bpr(p, D, (cudaStream_t)stream);
+}
+
+extern "C" int wr_bpr_fwd_bwd_sharded(const wr_shards *host_T, const wr_shards *host_Gd, const int64_t *user,
+                                      const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D,
+                                      float gamma, float grad_scale, float *loss_out, void *ws, void *stream) {
+    if (!host_T || !host_Gd || !user || !pos || !neg || !loss_out || !ws) return WR_E_NULL;
+    int rc = wr_check_shards(host_T);
+    if (rc) return rc;
+    rc = wr_check_shards(host_Gd);
+    if (rc) return rc;
+    if (B <= 0 || B_global < B) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    BprParamsT<ShardTabs> p{{*host_T, *host_Gd}, user, pos, neg, B, host_T->n_users, host_T->n_items, gamma,
+                            grad_scale / (float)B_global, (float)B_global, loss_out, 0, (WrWorkspace *)ws};
+    return launch_bpr(p, D, (cudaStream_t)stream);
 }
 
 extern "C" int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_t *user, const int64_t *pos,
@@ -525,12 +587,46 @@ extern "C" int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_
     if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
     if (!wr_aligned16(U0) || !wr_aligned16(I0) || !wr_aligned16(gU0) || !wr_aligned16(gI0)) return WR_E_ALIGN;
-    EmbParams p{U0, I0, user, pos, neg, B, n_users, n_items, reg_weight, gU0, gI0, loss_out, (WrWorkspace *)ws};
+    EmbParams p{{U0, I0, gU0, gI0}, user, pos, neg, B, n_users, n_items, reg_weight, 1.0f / (float)B, loss_out,
+                nullptr, nullptr, (WrWorkspace *)ws};
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(B * (D / 4), 256, 4 * kSMs);
-    embloss_sumsq_kernel<<<grid, 256, 0, st>>>(p, D);
+    embloss_sumsq_kernel<LocalTabs><<<grid, 256, 0, st>>>(p, D);
     WR_CHECK_LAUNCH();
-    embloss_scatter_kernel<<<grid, 256, 0, st>>>(p, D);
+    embloss_scatter_kernel<LocalTabs><<<grid, 256, 0, st>>>(p, D);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_embloss_sumsq_sharded(const wr_shards *host_T, const int64_t *user, const int64_t *pos,
+                                        const int64_t *neg, int64_t B, int D, float *sumsq_out, void *ws,
+                                        void *stream) {
+    if (!host_T || !user || !pos || !neg || !sumsq_out || !ws) return WR_E_NULL;
+    const int rc = wr_check_shards(host_T);
+    if (rc) return rc;
+    if (B <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    EmbParamsT<ShardTabs> p{{*host_T, *host_T}, user, pos, neg, B, host_T->n_users, host_T->n_items, 0.f, 0.f,
+                            nullptr, sumsq_out, nullptr, (WrWorkspace *)ws};
+    embloss_sumsq_kernel<ShardTabs><<<grid_for(B * (D / 4), 256, 4 * kSMs), 256, 0, (cudaStream_t)stream>>>(p, D);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_embloss_scatter_sharded(const wr_shards *host_T, const wr_shards *host_Gd, const int64_t *user,
+                                          const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global,
+                                          int D, float reg_weight, const float *sumsq_global, float *loss_out,
+                                          void *ws, void *stream) {
+    if (!host_T || !host_Gd || !user || !pos || !neg || !sumsq_global || !ws) return WR_E_NULL;
+    int rc = wr_check_shards(host_T);
+    if (rc) return rc;
+    rc = wr_check_shards(host_Gd);
+    if (rc) return rc;
+    if (B <= 0 || B_global < B) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    EmbParamsT<ShardTabs> p{{*host_T, *host_Gd}, user, pos, neg, B, host_T->n_users, host_T->n_items, reg_weight,
+                            1.0f / (float)B_global, loss_out, nullptr, sumsq_global, (WrWorkspace *)ws};
+    embloss_scatter_kernel<ShardTabs><<<grid_for(B * (D / 4), 256, 4 * kSMs), 256, 0, (cudaStream_t)stream>>>(p, D);
     WR_CHECK_LAUNCH();
     return WR_OK;
 }
@@ -620,8 +716,8 @@ extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64
         if (rc) return rc;
         return wr_adam_l2_sweep(P, M, V, G, n_elems, l2, beta1, beta2, eps, step_size, bc2_sqrt, dev_scalars, stream);
     }
-    BprParams bp{P, P + n_users * D, user, pos, neg, B, n_users, n_items, gamma, 1.0f / (float)B,
-                 G, G + n_users * D, loss_out, 0, (WrWorkspace *)ws};
+    BprParams bp{{P, P + n_users * D, G, G + n_users * D}, user, pos, neg, B, n_users, n_items, gamma,
+                 1.0f / (float)B, (float)B, loss_out, 0, (WrWorkspace *)ws};
     AdamScalars s{l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, bc2_sqrt};
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n4 = n_elems >> 2;

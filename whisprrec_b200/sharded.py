@@ -1,0 +1,352 @@
+"""Row-sharded BPRMF / LightGCN over the GPUs of one box (include/whisprrec_b200.h,
+"one 8 x B200 box").
+
+One process per GPU (torchrun).  `torch.distributed` is only the rendezvous (exchange of the cudaIpc handles) and
+the small evaluation collectives; the training step has NO collective call: every rank maps every other rank's
+tables (NVLink 5 / NVSwitch peer memory) and the kernels read remote embedding rows and reduce remote gradient rows
+themselves, meeting at wr_peer_barrier.
+
+`ShardLayout` is pure host arithmetic (tested on the CPU, also under gloo with world_size 2); `PeerGroup`,
+`ShardedTables` and the step / evaluation drivers need one GPU per rank.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class ShardLayout(object):
+    """user u -> rank u % world, local row u // world;  item i -> rank i % world, local row rows_u_local + i // world.
+
+    A rank's shard is one [n_local, D] table: its user rows first (padded to rows_u_local = ceil(n_users / world)),
+    then its item rows (padded to rows_i_local).  LightGCN node n is user n (n < n_users) or item n - n_users.
+    """
+
+    def __init__(self, n_users, n_items, world, rank):
+        if not (1 <= world <= _lib.MAX_WORLD and 0 <= rank < world):
+            raise ValueError('world must be in [1, %d] and rank in [0, world)' % _lib.MAX_WORLD)
+        self.n_users, self.n_items, self.world, self.rank = int(n_users), int(n_items), int(world), int(rank)
+        self.rows_u_local = (self.n_users + world - 1) // world
+        self.rows_i_local = (self.n_items + world - 1) // world
+        self.n_local = self.rows_u_local + self.rows_i_local
+
+    # ---- ownership ----
+    def local_users(self, rank=None):
+        return np.arange(self.rank if rank is None else rank, self.n_users, self.world, dtype=np.int64)
+
+    def local_items(self, rank=None):
+        return np.arange(self.rank if rank is None else rank, self.n_items, self.world, dtype=np.int64)
+
+    def local_nodes(self, rank=None):
+        """Global node id of every local row (-1 for the padding rows)."""
+        out = np.full(self.n_local, -1, dtype=np.int64)
+        u, i = self.local_users(rank), self.local_items(rank)
+        out[:len(u)] = u
+        out[self.rows_u_local:self.rows_u_local + len(i)] = self.n_users + i
+        return out
+
+    def shard_of_table(self, full, rank=None):
+        """The [n_local, D] shard of a full [n_users + n_items, D] host / device table (padding rows zero)."""
+        nodes = self.local_nodes(rank)
+        out = full.new_zeros((self.n_local, full.shape[1])) if torch.is_tensor(full) else \
+            np.zeros((self.n_local, full.shape[1]), dtype=full.dtype)
+        ok = nodes >= 0
+        if torch.is_tensor(full):
+            out[torch.from_numpy(np.nonzero(ok)[0]).to(full.device)] = full[torch.from_numpy(nodes[ok]).to(full.device)]
+        else:
+            out[ok] = full[nodes[ok]]
+        return out
+
+    # ---- the batch ----
+    def batch_slice(self, n, rank=None):
+        """Contiguous slice [lo, hi) of a global batch of n rows that a rank processes (sizes differ by <= 1)."""
+        r = self.rank if rank is None else rank
+        base, rem = divmod(int(n), self.world)
+        lo = r * base + min(r, rem)
+        return lo, lo + base + (1 if r < rem else 0)
+
+    # ---- evaluation ----
+    def localise_history(self, hist_ptr, hist_idx, rank=None):
+        """Per-user history CSR restricted to one item shard, as ascending LOCAL item indices."""
+        r = self.rank if rank is None else rank
+        hist_ptr, hist_idx = np.asarray(hist_ptr, dtype=np.int64), np.asarray(hist_idx, dtype=np.int64)
+        nnz = int(hist_ptr[-1])
+        idx = hist_idx[:nnz]
+        mine = (idx % self.world) == r
+        users = np.repeat(np.arange(len(hist_ptr) - 1, dtype=np.int64), np.diff(hist_ptr))
+        counts = np.bincount(users[mine], minlength=len(hist_ptr) - 1)
+        ptr = np.zeros(len(hist_ptr), dtype=np.int64)
+        np.cumsum(counts, out=ptr[1:])
+        local = (idx[mine] // self.world).astype(np.int32)
+        if len(local) == 0:
+            local = np.zeros(1, dtype=np.int32)
+        return ptr, local
+
+    def item_local_index(self, items, rank=None):
+        """Local index of each global item id on one shard, -1 where another shard owns it (NumPy or torch)."""
+        r = self.rank if rank is None else rank
+        mine = (items % self.world) == r
+        if torch.is_tensor(items):
+            return torch.where(mine, torch.div(items, self.world, rounding_mode='floor'), torch.full_like(items, -1))
+        return np.where(mine, items // self.world, -1)
+
+    def item_global_index(self, local, rank=None):
+        """Global item id of a shard's local item indices (negative = empty slot, kept)."""
+        r = self.rank if rank is None else rank
+        if torch.is_tensor(local):
+            return torch.where(local >= 0, local * self.world + r, local)
+        return np.where(local >= 0, local * self.world + r, local)
+
+    # ---- LightGCN ----
+    def local_adjacency(self, rowptr, col, dinv=None, rank=None):
+        """This rank's rows of the global node CSR, in local row order; column ids stay GLOBAL node ids.
+
+        Returns (rowptr_local int64 [n_local + 1], col_local int32, src_edge int64) where src_edge maps every local
+        edge to its position in the global `col` (so weights computed once globally can be sliced)."""
+        nodes = self.local_nodes(rank)
+        rowptr = np.asarray(rowptr, dtype=np.int64)
+        deg = np.where(nodes >= 0, rowptr[np.maximum(nodes, 0) + 1] - rowptr[np.maximum(nodes, 0)], 0)
+        lptr = np.zeros(self.n_local + 1, dtype=np.int64)
+        np.cumsum(deg, out=lptr[1:])
+        total = int(lptr[-1])
+        row_of_edge = np.repeat(np.arange(self.n_local, dtype=np.int64), deg)
+        src = rowptr[np.maximum(nodes, 0)][row_of_edge] + (np.arange(total, dtype=np.int64) - lptr[row_of_edge])
+        return lptr, np.asarray(col)[src].astype(np.int32), src
+
+
+def combine_shard_ranks(local_ranks):
+    """global rank = 1 + sum over shards of (rank_shard - 1); `local_ranks`: iterable of integer arrays / tensors."""
+    total = None
+    for r in local_ranks:
+        total = (r - 1) if total is None else total + (r - 1)
+    return total + 1
+
+
+class PeerGroup(object):
+    """The ranks of one box with every rank's peer blocks mapped into every process."""
+
+    def __init__(self, device, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.MAX_WORLD:
+            raise _lib.WhisprError('at most %d ranks (one box)' % _lib.MAX_WORLD)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.WhisprError('PeerGroup needs a CUDA device per rank (no CPU fallback)')
+        self._blocks = []
+        self.epoch = 0
+        sig_bytes = 4 * _lib.MAX_WORLD + 4 * 2 * _lib.MAX_WORLD * _lib.PEER_VALUES
+        self._sig, self._sig_ptrs = self.alloc_bytes((sig_bytes + 255) // 256 * 256)
+        self.flag_ptrs = list(self._sig_ptrs)
+        self.slot_ptrs = [p + 4 * _lib.MAX_WORLD for p in self._sig_ptrs]
+        self._values = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=self.device)
+        self.sums = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=self.device)
+        self.host_sync()
+
+    def alloc_bytes(self, nbytes):
+        """Symmetric allocation: (this rank's PeerBlock, [base pointer of every rank's block as mapped here])."""
+        block = _lib.PeerBlock(nbytes, self.device)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, block.handle(), group=self.group)
+        ptrs = [block.ptr if g == self.rank else block.open_peer(handles[g]) for g in range(self.world)]
+        self._blocks.append(block)
+        return block, ptrs
+
+    def alloc(self, shape, dtype=torch.float32):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = max(256, (n * torch.empty((), dtype=dtype).element_size() + 255) // 256 * 256)
+        block, ptrs = self.alloc_bytes(nbytes)
+        return block.tensor(0, shape, dtype), ptrs
+
+    def host_sync(self):
+        """Host-side rendezvous (set-up and tear-down only): device work done, then a process-group barrier."""
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)
+
+    def barrier(self, values=None):
+        """Device-side barrier on the current stream; optionally sums up to 4 floats across the ranks (returns a view
+        of the result, valid until the next barrier with values)."""
+        self.epoch += 1
+        if values is None:
+            _lib.peer_barrier(self.flag_ptrs, self.slot_ptrs, self.world, self.rank, self.epoch)
+            return None
+        n = values.numel()
+        _lib.peer_barrier(self.flag_ptrs, self.slot_ptrs, self.world, self.rank, self.epoch, values, self.sums[:n])
+        return self.sums[:n]
+
+    def close(self):
+        self.host_sync()
+        for b in self._blocks:
+            b.close()
+        self._blocks = []
+
+
+class ShardedTables(object):
+    """P / M / V / G shards of one rank plus the `wr_shards` descriptors of every symmetric table."""
+
+    def __init__(self, peers, layout, D):
+        self.peers, self.layout, self.D = peers, layout, int(D)
+        self.P, self.T = self.symmetric()
+        self.G, self.Gd = self.symmetric()
+        dev = peers.device
+        self.M = torch.zeros((layout.n_local, self.D), dtype=torch.float32, device=dev)
+        self.V = torch.zeros_like(self.M)
+        self.ws = _lib.Workspace(dev)
+        self.loss_part = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.step_count = 0
+
+    def symmetric(self):
+        """A zeroed [n_local, D] fp32 table on every rank -> (local tensor, wr_shards describing all of them)."""
+        lay = self.layout
+        t, ptrs = self.peers.alloc((lay.n_local, self.D))
+        s = _lib.ShardsStruct()
+        for g in range(lay.world):
+            s.base[g] = ptrs[g]
+        s.world, s.rank, s.n_users, s.n_items = lay.world, lay.rank, lay.n_users, lay.n_items
+        s.rows_u_local, s.rows_i_local = lay.rows_u_local, lay.rows_i_local
+        return t, s
+
+    def load_full(self, full_user, full_item):
+        """Take this rank's rows of the full (replicated-at-init) tables."""
+        full = torch.cat([full_user, full_item]).to(self.peers.device)
+        self.P.copy_(self.layout.shard_of_table(full))
+        self.peers.host_sync()
+
+    def gather_full(self, shards=None):
+        """Full [n_users, D], [n_items, D] copies of a sharded table (checkpointing / tests)."""
+        lay = self.layout
+        s = self.T if shards is None else shards
+        dev = self.peers.device
+        u = _lib.gather_rows_sharded(s, 0, torch.arange(lay.n_users, device=dev), self.D, self.ws)
+        i = _lib.gather_rows_sharded(s, 1, torch.arange(lay.n_items, device=dev), self.D, self.ws)
+        return u, i
+
+    def item_rows(self, t):
+        lay = self.layout
+        return t[lay.rows_u_local:lay.rows_u_local + len(lay.local_items())]
+
+    def adam(self, lr, l2, betas=(0.9, 0.999), eps=1e-8):
+        self.step_count += 1
+        _lib.adam_l2_sweep(self.P, self.M, self.V, self.G, self.step_count, lr, l2, betas[0], betas[1], eps)
+
+
+def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
+    """One BPRMF iteration on this rank's slice (user, pos, neg) of a global batch of B_global rows.
+
+    fwd+bwd with remote gathers / remote REDs -> barrier (all gradient rows have landed; carries the loss) ->
+    Adam+L2 over the local shard -> barrier (parameters final before anyone gathers again).
+    Returns the batch loss (device scalar view, identical on every rank)."""
+    _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
+    loss = tabs.peers.barrier(tabs.loss_part[:1])
+    tabs.adam(lr, l2)
+    tabs.peers.barrier()
+    return loss
+
+
+class ShardedLightGCN(object):
+    """LightGCN propagation state of one rank: its rows of the adjacency and the symmetric layer / pool buffers."""
+
+    def __init__(self, tabs, rowptr, col, dinv, n_layers, reg_weight):
+        self.tabs, self.L, self.reg_weight = tabs, int(n_layers), float(reg_weight)
+        lay, dev = tabs.layout, tabs.peers.device
+        lptr, lcol, _ = lay.local_adjacency(rowptr, col)
+        nodes = lay.local_nodes()
+        dinv_local = np.where(nodes >= 0, np.asarray(dinv)[np.maximum(nodes, 0)], 0).astype(np.float32)
+        self.rowptr = torch.from_numpy(lptr).to(dev)
+        self.col = torch.from_numpy(lcol if len(lcol) else np.zeros(1, np.int32)).to(dev)
+        # weights: fl32(fl32(dinv[row] * 1) * dinv[col]) -- LightGCN.py:89-97; dinv of a column comes from the full vector
+        d_full = torch.from_numpy(np.asarray(dinv, dtype=np.float32)).to(dev)
+        rows = torch.repeat_interleave(torch.arange(lay.n_local, device=dev), self.rowptr[1:] - self.rowptr[:-1])
+        self.val = (torch.from_numpy(dinv_local).to(dev)[rows] * 1.0) * d_full[self.col[:rows.numel()].long()]
+        if self.val.numel() == 0:
+            self.val = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.plan = _lib.SpmmPlan(lptr, tabs.D, dev)
+        self.pool, self.pool_T = tabs.symmetric()
+        self.pool_grad, self.pool_Gd = tabs.symmetric()
+        self.layer = [tabs.symmetric(), tabs.symmetric()]
+        self.sumsq = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=dev)
+        tabs.peers.host_sync()
+
+    def _spmm(self, X, **kw):
+        t = self.tabs
+        _lib.csr_spmm_sharded(self.rowptr, self.col, self.val, t.layout.n_local, t.D, X, plan=self.plan, **kw)
+        t.peers.barrier()          # every rank's rows of the output exist before anyone reads them as neighbours
+
+    def propagate(self):
+        """LightGCN.py:134-148 on row shards: layer k+1 reads its neighbours' layer-k rows from their owners."""
+        t, L = self.tabs, self.L
+        if L == 0:
+            self.pool.copy_(t.P)
+            t.peers.barrier()
+            return
+        x = t.T
+        for k in range(1, L + 1):
+            y, ys = self.layer[(k - 1) & 1]
+            self._spmm(x, Y=y if k < L else None, acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
+                       acc_div=float(L + 1) if k == L else 1.0)
+            x = ys
+
+    def step(self, user, pos, neg, B_global, lr, l2):
+        """LightGCN.py:150-175 + backward + Adam on this rank's slice of the batch."""
+        t, L = self.tabs, self.L
+        self.propagate()
+        if L == 0:
+            _lib.bpr_fwd_bwd_sharded(t.T, t.Gd, user, pos, neg, B_global, t.D, t.loss_part, t.ws)
+        else:
+            _lib.bpr_fwd_bwd_sharded(self.pool_T, self.pool_Gd, user, pos, neg, B_global, t.D, t.loss_part, t.ws,
+                                     grad_scale=1.0 / (L + 1))
+        _lib.embloss_sumsq_sharded(t.T, user, pos, neg, t.D, t.loss_part[1:], t.ws)
+        sums = t.peers.barrier(t.loss_part)          # pooled gradients landed; loss and the three norms reduced
+        t.loss.copy_(sums[:1])
+        self.sumsq[:3].copy_(sums[1:4])
+        if L > 0:
+            h = self.pool_Gd
+            for k in range(1, L + 1):
+                last = k == L
+                y, ys = (t.G, t.Gd) if last else self.layer[(k - 1) & 1]
+                self._spmm(h, Y=y, add=self.pool_grad, zero_add=last and L > 1)
+                h = ys
+            if L == 1:
+                self.pool_grad.zero_()
+        _lib.embloss_scatter_sharded(t.T, t.Gd, user, pos, neg, B_global, t.D, self.reg_weight, self.sumsq, t.loss,
+                                     t.ws)
+        t.peers.barrier()                            # every gradient row has landed
+        t.adam(lr, l2)
+        t.peers.barrier()
+        return t.loss
+
+
+def sharded_eval(tabs, shards, item_table_local, user, pos, hist_local, k=0, precision=0):
+    """Full-ranking evaluation with the items sharded over the ranks (every rank scores all R rows against its items).
+
+    shards: wr_shards of the table that is scored (P for BPRMF, the pooled table for LightGCN);
+    item_table_local: this rank's item rows of it.  Returns (rank int32 [R], target fp32 [R], topk_idx | None,
+    topk_val | None), identical on every rank.  The exchange is one all-reduce of the per-shard counts and, for the
+    top-k lists, one all-gather of [R, k] candidates followed by the merge kernel."""
+    lay, peers, D = tabs.layout, tabs.peers, tabs.D
+    dist = peers.dist
+    urows = _lib.gather_rows_sharded(shards, 0, user, D, tabs.ws)
+    prows = _lib.gather_rows_sharded(shards, 1, pos, D, tabs.ws)
+    target = _lib.rowdot(urows, prows, round_bf16=(precision == 1))
+    pos_local = lay.item_local_index(pos)
+    rank_local, tki, tkv = _lib.eval_rank_topk_shard(urows, item_table_local, user, pos_local, lay.n_users,
+                                                    hist_local[0], hist_local[1], target, tabs.ws, k=k,
+                                                    precision=precision)
+    counts = rank_local - 1
+    dist.all_reduce(counts, group=peers.group)
+    rank = counts + 1
+    if k <= 0:
+        return rank, target, None, None
+    gi = lay.item_global_index(tki).contiguous()
+    all_i = torch.empty((lay.world,) + tuple(gi.shape), dtype=gi.dtype, device=gi.device)
+    all_v = torch.empty((lay.world,) + tuple(tkv.shape), dtype=tkv.dtype, device=tkv.device)
+    dist.all_gather_into_tensor(all_i, gi, group=peers.group)
+    dist.all_gather_into_tensor(all_v, tkv.contiguous(), group=peers.group)
+    mv, mi = _lib.topk_merge(all_v, all_i, k)
+    return rank, target, mi, mv
