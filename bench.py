@@ -230,6 +230,140 @@ def run_ours(a, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_ours_sharded(a, rank, world, local_rank):
+    """N > 1: the same tables row-sharded over the N GPUs (NVLink peer memory, whisprrec_b200/sharded.py); every
+    step trains one GLOBAL batch of N x 2048 interactions, each rank feeding its 2048-row slice (weak scaling)."""
+    import torch.distributed as dist
+    from whisprrec_b200 import _lib, sharded as S
+    from whisprrec_b200.utils import synthetic
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', device_id=dev)
+    hbm_peak, _, peak_src = peaks()
+    corpus = synthetic.ml1m_shaped_corpus(cache_dir=os.path.join(CACHE, 'r%d' % rank))
+    model, runner, data = make_model(corpus, dev)
+    peers = S.PeerGroup(dev)
+    st = model.shard(peers)
+    batches = runner.epoch_batches(data['train'])              # identical on every rank (same seeds)
+    GB = B * world
+    steps_per_epoch = batches.shape[1] // GB
+    lo_r = rank * B                                            # this rank's slice of every global batch
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    losses = torch.zeros(a.warmup + a.steps, device=dev)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(a.steps)]
+
+    def step(s, events=None):
+        lo = (s % steps_per_epoch) * GB + lo_r
+        u, p, n = batches[0, lo:lo + B], batches[1, lo:lo + B], batches[2, lo:lo + B]
+        if events: events[0].record()
+        loss = model.sharded_train_step(u, p, n, GB, LR, L2)      # one cooperative launch per rank (wr_bprmf_step_sharded)
+        if events: events[1].record()
+        losses[s:s + 1].copy_(loss[:1])
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(a.warmup):
+        flush.zero_()
+        step(s)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        wall0 = time.perf_counter()
+        for s in range(a.steps):
+            flush.zero_()
+            step(a.warmup + s, ev[s])
+        barrier()
+        wall = time.perf_counter() - wall0
+        extra_steps = int(max(0.0, 1.5 - wall) / 2e-4) if wall < 1.5 else 0
+        t_extra = torch.tensor([extra_steps], device=dev)
+        dist.all_reduce(t_extra, op=dist.ReduceOp.MAX)         # every rank runs the same number of steps
+        for s in range(int(t_extra.item())):
+            flush.zero_(); step(0)
+        barrier()
+    clocks = clk.summary()
+    step_ms = np.array([e[0].elapsed_time(e[1]) for e in ev])
+    tt = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    st.ws.raise_on_status()
+    assert np.isfinite(losses.cpu().numpy()).all()
+    value = a.steps * GB / (total_ms * 1e-3)
+
+    # ---- e2e: each rank's slice comes from pinned host memory every step, the loss goes back to the host ----
+    host_batches = batches.cpu()
+    pinned = torch.empty((steps_per_epoch, 3, B), dtype=torch.int64).pin_memory()
+    for s in range(steps_per_epoch):
+        pinned[s].copy_(host_batches[:, s * GB + lo_r:s * GB + lo_r + B])
+    stage = torch.empty((3, B), dtype=torch.int64, device=dev)
+    e2e_s = 0.0
+    for s in range(a.warmup + a.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        stage.copy_(pinned[s % steps_per_epoch], non_blocking=True)
+        loss = model.sharded_train_step(stage[0], stage[1], stage[2], GB, LR, L2)
+        loss_host = float(loss[0])
+        if s >= a.warmup:
+            e2e_s += time.perf_counter() - t0
+    tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e2e_s = float(tt.item())
+    assert np.isfinite(loss_host)
+
+    n_local = st.layout.n_local
+    step_bytes = algorithmic_bytes_adam(n_local, D) + algorithmic_bytes_bpr(B, D)          # per GPU
+    step_avg_s = float(step_ms.mean()) * 1e-3
+    # the multi-launch form of the same step (what shards too large for the single launch use), timed piecewise
+    seg_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(20)]
+    for e in seg_ev:
+        flush.zero_()
+        lo = lo_r
+        u, p, n = batches[0, lo:lo + B], batches[1, lo:lo + B], batches[2, lo:lo + B]
+        peers.barrier()
+        e[0].record()
+        _lib.bpr_fwd_bwd_sharded(st.T, st.Gd, u, p, n, GB, st.D, st.loss_part, st.ws)
+        e[1].record()
+        peers.barrier(st.loss_part[:1])
+        e[2].record()
+        st.adam(LR, L2)
+        e[3].record()
+        peers.barrier()
+        e[4].record()
+    barrier()
+    seg = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in seg_ev])
+    line = {
+        'metric': 'train_interactions_per_s', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': total_ms / a.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'batch_per_gpu': B, 'global_batch': GB, 'embedding_size': D,
+                   'table_rows': int(st.layout.n_users + st.layout.n_items), 'table_rows_per_gpu': int(n_local),
+                   'l2_flush': '512 MB written between timed steps on every GPU',
+                   'parallelism': 'tables row-sharded x%d over NVLink peer memory; one cooperative launch per GPU and '
+                                  'step: remote gathers and gradient REDs, the cross-GPU barriers and the loss '
+                                  'all-reduce all happen inside the kernel (no collective call)' % world},
+        'e2e': {'value': a.steps * GB / e2e_s, 'unit': 'interactions/s', 'h2d_bytes_per_step': 3 * B * 8 * world,
+                'd2h_bytes_per_step': 4 * world, 'ms_per_step': e2e_s / a.steps * 1e3},
+        'gpu_launches': a.steps,
+        'clocks': clocks,
+        'roofline': {'bound': 'hbm', 'kernel': 'bprmf_step_kernel<ShardTabs>', 'achieved': step_bytes / step_avg_s / 1e9,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': step_bytes / step_avg_s / 1e9 / hbm_peak, 'traffic': None,
+                     'peak_source': peak_src, 'bytes_per_launch': step_bytes, 'avg_launch_us': step_avg_s * 1e6,
+                     'note': 'per GPU; (world-1)/world of the gathered rows and gradient REDs cross NVLink; latency-bound '
+                             '(launch + DRAM and NVLink round trips + two cross-GPU meeting points)'},
+        'kernels_ms': {'bprmf_step_sharded': float(step_ms.mean()), 'step_median': float(np.median(step_ms)),
+                       'multi_launch_form': {'bpr_fwd_bwd_sharded': float(seg[:, 0].mean()),
+                                             'barrier_after_scatter': float(seg[:, 1].mean()),
+                                             'adam_l2_sweep': float(seg[:, 2].mean()),
+                                             'barrier_after_adam': float(seg[:, 3].mean())}},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    peers.close()
+    dist.destroy_process_group()
+
+
 def cpu_problem(corpus):
     """The same workload for the CPU arm: reference-initialised tables and one epoch of reference-ordered batches."""
     from whisprrec_b200.main import default_args as model_args
@@ -453,7 +587,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device for the sm_100a arm (there is no CPU fallback); '
                          'use --impl reference for the CPU arm')
-    run_ours(a, rank, world, local_rank)
+    if world > 1:
+        run_ours_sharded(a, rank, world, local_rank)
+    else:
+        run_ours(a, rank, world, local_rank)
 
 
 if __name__ == '__main__':

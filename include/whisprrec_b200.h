@@ -231,6 +231,24 @@ int wr_bpr_fwd_bwd_sharded(const wr_shards *host_T, const wr_shards *host_Gd, co
                            const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D, float gamma,
                            float grad_scale, float *loss_out, void *ws, void *stream);
 
+/* wr_bprmf_step_sharded: wr_bprmf_step on row-sharded tables -- ONE cooperative launch per rank and step, with the
+ * two cross-GPU meeting points inside the kernel: (1) the grid barrier between the BPR phase and the Adam phase is
+ * extended across the GPUs by CTA 0 (every rank's remote gradient REDs have landed, the loss shares are exchanged),
+ * (2) the last CTA to finish the Adam phase tells every peer that this rank's rows are final, and the next step's
+ * kernel waits for that before its first remote gather.  T / Gd: parameter and gradient shards; M / V: this rank's
+ * moment shards; epoch: the step number 1, 2, 3, ... (same on every rank, each used once);
+ * host_flags[g]: rank g's zero-initialised array of 2 * WR_MAX_WORLD uint32; host_slots[g]: rank g's array of
+ * 2 * WR_MAX_WORLD floats.  loss_out[0] = the loss of the GLOBAL batch (identical on every rank).
+ * Supported when wr_bprmf_step_sharded_supported(rows of a shard, D) (cache-sized shards, D in {16,...,256});
+ * otherwise use wr_bpr_fwd_bwd_sharded / wr_peer_barrier / wr_adam_l2_sweep / wr_peer_barrier.
+ */
+int wr_bprmf_step_sharded_supported(int64_t n_local_rows, int D);
+int wr_bprmf_step_sharded(const wr_shards *host_T, const wr_shards *host_Gd, float *M, float *V, const int64_t *user,
+                          const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D, float gamma,
+                          float l2, double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
+                          uint32_t epoch, uint32_t *const host_flags[WR_MAX_WORLD],
+                          float *const host_slots[WR_MAX_WORLD], float *loss_out, void *ws, void *stream);
+
 /* wr_embloss_sumsq_sharded / wr_embloss_scatter_sharded: the two halves of wr_embloss_fwd_bwd; the three squared
  * norms are batch-global, so the ranks' sums meet (wr_peer_barrier carries them) between the halves.
  *   sumsq_out[0..3)  = this rank's sums of squares of its gathered user / pos / neg ego rows

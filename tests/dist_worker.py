@@ -219,6 +219,44 @@ def run_gpu():
         peers.host_sync()
         if rank == 0:
             print(f'dist_worker gpu ok: world {world} nU {nU} nI {nI} D {D} B {B}')
+    # ---------------- the reference-facing classes on sharded tables: one ml-100k epoch against the goldens ----------------
+    from tests.helpers import load, ml100k_corpus, model_args
+    from whisprrec_b200.helpers.BaseRunner import BaseRunner
+    from whisprrec_b200.models.general.BPRMF import BPRMF
+    from whisprrec_b200.models.general.LightGCN import LightGCN
+    from whisprrec_b200.utils import utils
+    import tempfile
+    corpus = ml100k_corpus()
+    for cls, over, gname, tol in [(BPRMF, dict(lr=1e-3, l2=1e-6), 'ml100k_bprmf.npz', 1e-4),
+                                  (LightGCN, dict(lr=2e-3, gcn_layers=2), 'ml100k_lightgcn.npz', 1e-3)]:
+        g = load(gname)
+        args = model_args(cls, **over)
+        args.device = dev
+        args.model_path = os.path.join(tempfile.gettempdir(), 'wr_dist_%s.pt' % cls.__name__)
+        utils.init_seed(3407)
+        model = cls(args, corpus).to(dev)
+        model.fuse()
+        data = {ph: cls.Dataset(model, corpus, ph) for ph in ('train', 'dev', 'test')}
+        runner = BaseRunner(args)
+        model.optimizer = runner._build_optimizer(model)
+        model.shard(peers)
+        mean_loss = runner.fit(data['train'], epoch=1)
+        if 'neg_epoch1' in g.files:
+            assert (data['train'].data['neg_items'] == g['neg_epoch1']).all()
+        assert abs(mean_loss - float(g['epoch_mean_loss'])) <= 1e-4 * abs(float(g['epoch_mean_loss'])), mean_loss
+        res = runner.evaluate(data['dev'], [10, 20], ['NDCG', 'HR'])
+        for k, v in zip(g['dev_metric_keys'], g['dev_metric_vals']):
+            assert abs(res[str(k)] - float(v)) <= 2e-3, (k, res[str(k)], float(v))
+        model.save_model()
+        ue, ie = model._embedding_pair()
+        assert_close(host(ue.weight[:64]), g['after_user_rows'], 'U after a sharded epoch', rtol=tol, atol_scale=tol)
+        assert_close(host(ie.weight[:64]), g['after_item_rows'], 'I after a sharded epoch', rtol=tol, atol_scale=tol)
+        model.load_model()
+        res2 = runner.evaluate(data['dev'], [10, 20], ['NDCG', 'HR'])
+        assert res2 == res
+        peers.host_sync()
+        if rank == 0:
+            print(f'dist_worker gpu ok: world {world} {cls.__name__} ml-100k epoch, dev', res)
     peers.close()
     dist.destroy_process_group()
 

@@ -48,6 +48,9 @@ SIGNATURES = {
     'wr_peer_close': (_int, [_p]),
     'wr_peer_barrier': (_int, [_p, _int, _int, _c.c_uint32, _p, _p, _int, _p, _p]),
     'wr_bpr_fwd_bwd_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_bprmf_step_sharded_supported': (_int, [_i64, _int]),
+    'wr_bprmf_step_sharded': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _f64, _f64, _f32, _f32,
+                                     _f32, _c.c_uint32, _p, _p, _p, _p, _p]),
     'wr_embloss_sumsq_sharded': (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _p]),
     'wr_embloss_scatter_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _p, _p, _p, _p]),
     'wr_gather_rows_sharded': (_int, [_p, _int, _p, _i64, _int, _p, _p, _p]),
@@ -382,6 +385,26 @@ def bpr_fwd_bwd_sharded(T, Gd, user, pos, neg, B_global, D, loss_out, ws, gamma=
     check(load().wr_bpr_fwd_bwd_sharded(ctypes.addressof(T), ctypes.addressof(Gd), ptr(user, I64), ptr(pos, I64),
                                         ptr(neg, I64), user.numel(), B_global, D, gamma, grad_scale,
                                         ptr(loss_out, F32), ws.ptr, stream_ptr()))
+
+
+def bprmf_step_sharded_supported(n_local_rows, D):
+    return bool(load().wr_bprmf_step_sharded_supported(n_local_rows, D))
+
+
+def bprmf_step_sharded(T, Gd, M, V, user, pos, neg, B_global, D, step, lr, l2, flag_ptrs, slot_ptrs, loss_out, ws,
+                       beta1=0.9, beta2=0.999, eps=1e-8, gamma=1e-10, epoch=None):
+    """One sharded BPRMF step in one cooperative launch.  `step` is Adam's t; `epoch` the synchronisation epoch
+    (1, 2, 3, ... per table set; defaults to `step`)."""
+    epoch = step if epoch is None else epoch
+    world = T.world
+    FA = _p * MAX_WORLD
+    fa = FA(*(list(flag_ptrs) + [None] * (MAX_WORLD - world)))
+    sa = FA(*(list(slot_ptrs) + [None] * (MAX_WORLD - world)))
+    ss, bc2s = adam_scalars(step, lr, beta1, beta2)
+    check(load().wr_bprmf_step_sharded(ctypes.addressof(T), ctypes.addressof(Gd), ptr(M, F32), ptr(V, F32),
+                                       ptr(user, I64), ptr(pos, I64), ptr(neg, I64), user.numel(), B_global, D, gamma,
+                                       l2, beta1, beta2, eps, ss, bc2s, epoch, ctypes.addressof(fa),
+                                       ctypes.addressof(sa), ptr(loss_out, F32), ws.ptr, stream_ptr()))
 
 
 def embloss_sumsq_sharded(T, user, pos, neg, D, sumsq_out, ws):

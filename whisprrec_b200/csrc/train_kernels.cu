@@ -374,9 +374,31 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
     return v;
 }
 
-template <int LPR, int VPL>
-__global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 *P, float4 *M, float4 *V, float4 *G, int64_t n4,
-                                                          AdamScalars s, const float *dev_scalars) {
+// Cross-GPU synchronisation state of the single-launch step on row-sharded tables (world > 1).
+struct StepSync {
+    uint32_t *flags[WR_MAX_WORLD];  // rank g's [2][WR_MAX_WORLD] words: [0][r] = r's gradients have landed (epoch e),
+                                    //                                  [1][r] = r's Adam of step e is complete
+    float *slots[WR_MAX_WORLD];     // rank g's [2 (epoch parity)][WR_MAX_WORLD] loss shares
+    int world, rank;
+    uint32_t epoch;                 // the step number: 1, 2, 3, ... (the same on every rank)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int LPR, int VPL, class TABS>
+__global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, float4 *P, float4 *M, float4 *V, float4 *G,
+                                                             int64_t n4, AdamScalars s, const float *dev_scalars,
+                                                             StepSync sy) {
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
     __shared__ float red[8];
@@ -393,6 +415,12 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 
             const uint32_t bytes = (uint32_t)min((int64_t)blockDim.x, n4 - c) * 16u;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(arr + c), "r"(bytes) : "memory");
         }
+    }
+    if (sy.world > 1) {
+        // remote rows may be gathered only once their owners have finished the previous step's Adam
+        if (threadIdx.x < sy.world)
+            while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + WR_MAX_WORLD + threadIdx.x) - (sy.epoch - 1u)) < 0) {}
+        __syncthreads();
     }
     // ---- phase 1: BPR forward + backward; consecutive interaction groups go to different CTAs ----
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -445,24 +473,57 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 
     }
     const float bsum = block_sum(local, red);
     if (threadIdx.x == 0) p.ws->partial[blockIdx.x] = bsum;
-    // ---- grid barrier (ticket[3] counts arrivals, ticket[4] departures; the last CTA to leave re-arms both) ----
+    // ---- grid barrier (ticket[3] counts arrivals, ticket[4] departures; the last CTA to leave re-arms both).
+    //      Sharded: CTA 0 extends it across the GPUs -- once every local CTA has arrived (all of this GPU's REDs,
+    //      local and remote, are performed) it deposits the loss share with every peer, publishes this rank's
+    //      arrival, waits for every peer's, and only then opens the gate (ticket[5]) for the local CTAs. ----
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        if (sy.world > 1) __threadfence_system(); else __threadfence();
         atomicAdd(&p.ws->ticket[3], 1u);
-        while (ld_acquire_u32(&p.ws->ticket[3]) < gridDim.x) {}
-        __threadfence();
-    }
-    __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x < 32) {      // the loss, summed in CTA order (deterministic)
-        float t = 0.f;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(&p.ws->partial[i]);
-        t = warp_sum(t);
-        if (threadIdx.x == 0) {
-            const float mean = t / p.loss_div;
-            p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + mean : mean;
+        if (sy.world == 1 || blockIdx.x == 0) {
+            while (ld_acquire_u32(&p.ws->ticket[3]) < gridDim.x) {}
+            __threadfence();
         }
     }
+    float loss_sum = 0.f;
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x < 32) {      // this GPU's loss share, summed in CTA order (deterministic)
+            float t = 0.f;
+            for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += __ldcg(&p.ws->partial[i]);
+            loss_sum = warp_sum(t) / p.loss_div;
+        }
+        if (sy.world > 1) {
+            const int half = (int)(sy.epoch & 1u) * WR_MAX_WORLD;
+            if (threadIdx.x < sy.world) {
+                const int g = threadIdx.x;
+                asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(sy.slots[g] + half + sy.rank), "f"(loss_sum) : "memory");
+                __threadfence_system();
+                st_release_sys(sy.flags[g] + sy.rank, sy.epoch);
+                while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + g) - sy.epoch) < 0) {}
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0.f;
+                for (int g = 0; g < sy.world; ++g) {
+                    float v;
+                    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(sy.slots[sy.rank] + half + g) : "memory");
+                    t += v;
+                }
+                loss_sum = t;
+                __threadfence();
+                st_release_gpu(&p.ws->ticket[5], sy.epoch);     // the gate: every rank's gradients have landed
+            }
+        }
+        if (threadIdx.x == 0) p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + loss_sum : loss_sum;
+    } else if (sy.world > 1) {
+        if (threadIdx.x == 0) {
+            while (ld_acquire_u32(&p.ws->ticket[5]) != sy.epoch) {}
+            __threadfence();
+        }
+    }
+    __syncthreads();
     // ---- phase 2: Adam + L2 over every element, gradient re-zeroed; two iterations of loads in flight ----
     const float4 z = f4_zero();
     for (int64_t i = i0; i < n4; i += 2 * stride) {
@@ -495,11 +556,17 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParams p, float4 
             G[i2] = z;
         }
     }
+    if (sy.world > 1) __syncthreads();          // the departure below speaks for the whole CTA's stores
     if (threadIdx.x == 0) {
+        if (sy.world > 1) __threadfence();
         const uint32_t t = atomicAdd(&p.ws->ticket[4], 1u);
         if (t == gridDim.x - 1) {
             p.ws->ticket[3] = 0;
             p.ws->ticket[4] = 0;
+            if (sy.world > 1) {                 // this rank's rows of P are final: peers may gather them for step e+1
+                __threadfence_system();
+                for (int g = 0; g < sy.world; ++g) st_release_sys(sy.flags[g] + WR_MAX_WORLD + sy.rank, sy.epoch);
+            }
         }
     }
 }
@@ -663,15 +730,16 @@ extern "C" int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t 
     return WR_OK;
 }
 
-// Largest grid of bprmf_step_kernel<LPR, VPL> that is resident at once on the current device (cached per shape).
-template <int LPR, int VPL>
+// Largest grid of bprmf_step_kernel<...> that is resident at once on the current device (cached per instantiation).
+template <int LPR, int VPL, class TABS>
 static int step_max_grid(int *out) {
     static int cached = 0;
     if (!cached) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bprmf_step_kernel<LPR, VPL>, 256, 0);
+        if (e == cudaSuccess)
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bprmf_step_kernel<LPR, VPL, TABS>, 256, 0);
         if (e != cudaSuccess) return (int)e;
         cached = sms * per_sm;
         if (cached > WR_MAX_PARTIAL_BLOCKS) cached = WR_MAX_PARTIAL_BLOCKS;
@@ -681,19 +749,33 @@ static int step_max_grid(int *out) {
     return 0;
 }
 
-template <int LPR, int VPL>
-static int launch_step_fused(BprParams &bp, float *P, float *M, float *V, float *G, int64_t n4, AdamScalars &s,
-                             const float *dev_scalars, cudaStream_t st) {
+template <int LPR, int VPL, class TABS>
+static int launch_step_fused(BprParamsT<TABS> &bp, float *P, float *M, float *V, float *G, int64_t n4, AdamScalars &s,
+                             const float *dev_scalars, StepSync &sy, cudaStream_t st) {
     int max_grid = 0;
-    const int rc = step_max_grid<LPR, VPL>(&max_grid);
+    const int rc = step_max_grid<LPR, VPL, TABS>(&max_grid);
     if (rc) return rc;
     // whole iterations for every CTA: the fewest passes the resident grid needs, then the smallest grid for them
     const int64_t per_pass = (int64_t)max_grid * 256;
     const int64_t passes = (n4 + per_pass - 1) / per_pass;
     int grid = grid_for(n4, (int)(256 * passes), max_grid);
     float4 *P4 = (float4 *)P, *M4 = (float4 *)M, *V4 = (float4 *)V, *G4 = (float4 *)G;
-    void *args[] = {&bp, &P4, &M4, &V4, &G4, &n4, &s, &dev_scalars};
-    return (int)cudaLaunchCooperativeKernel((const void *)bprmf_step_kernel<LPR, VPL>, dim3(grid), dim3(256), args, 0, st);
+    void *args[] = {&bp, &P4, &M4, &V4, &G4, &n4, &s, &dev_scalars, &sy};
+    return (int)cudaLaunchCooperativeKernel((const void *)bprmf_step_kernel<LPR, VPL, TABS>, dim3(grid), dim3(256), args,
+                                            0, st);
+}
+
+template <class TABS>
+static int dispatch_step_fused(BprParamsT<TABS> &bp, int D, float *P, float *M, float *V, float *G, int64_t n4,
+                               AdamScalars &s, const float *dev_scalars, StepSync &sy, cudaStream_t st) {
+    switch (D) {
+        case 16: return launch_step_fused<4, 1, TABS>(bp, P, M, V, G, n4, s, dev_scalars, sy, st);
+        case 32: return launch_step_fused<8, 1, TABS>(bp, P, M, V, G, n4, s, dev_scalars, sy, st);
+        case 64: return launch_step_fused<16, 1, TABS>(bp, P, M, V, G, n4, s, dev_scalars, sy, st);
+        case 128: return launch_step_fused<32, 1, TABS>(bp, P, M, V, G, n4, s, dev_scalars, sy, st);
+        case 256: return launch_step_fused<32, 2, TABS>(bp, P, M, V, G, n4, s, dev_scalars, sy, st);
+        default: return WR_E_DIM;
+    }
 }
 
 // Tables up to this many bytes per array take the single-launch step (they fit in L2 several times over and the
@@ -719,17 +801,46 @@ extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64
     BprParams bp{{P, P + n_users * D, G, G + n_users * D}, user, pos, neg, B, n_users, n_items, gamma,
                  1.0f / (float)B, (float)B, loss_out, 0, (WrWorkspace *)ws};
     AdamScalars s{l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, bc2_sqrt};
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n4 = n_elems >> 2;
-    int rc;
-    switch (D) {
-        case 16: rc = launch_step_fused<4, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
-        case 32: rc = launch_step_fused<8, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
-        case 64: rc = launch_step_fused<16, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
-        case 128: rc = launch_step_fused<32, 1>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
-        default: rc = launch_step_fused<32, 2>(bp, P, M, V, G, n4, s, dev_scalars, st); break;
+    StepSync sy{};
+    sy.world = 1;
+    return dispatch_step_fused(bp, D, P, M, V, G, n_elems >> 2, s, dev_scalars, sy, (cudaStream_t)stream);
+}
+
+extern "C" int wr_bprmf_step_sharded_supported(int64_t n_local_rows, int D) {
+    const bool fused_shape = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
+    return fused_shape && n_local_rows > 0 && n_local_rows * D <= WR_FUSED_STEP_MAX_ELEMS;
+}
+
+extern "C" int wr_bprmf_step_sharded(const wr_shards *host_T, const wr_shards *host_Gd, float *M, float *V,
+                                     const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B,
+                                     int64_t B_global, int D, float gamma, float l2, double beta1, double beta2,
+                                     float eps, float step_size, float bc2_sqrt, uint32_t epoch,
+                                     uint32_t *const host_flags[WR_MAX_WORLD], float *const host_slots[WR_MAX_WORLD],
+                                     float *loss_out, void *ws, void *stream) {
+    if (!host_T || !host_Gd || !M || !V || !user || !pos || !neg || !host_flags || !host_slots || !loss_out || !ws)
+        return WR_E_NULL;
+    int rc = wr_check_shards(host_T);
+    if (rc) return rc;
+    rc = wr_check_shards(host_Gd);
+    if (rc) return rc;
+    if (B <= 0 || B_global < B || epoch == 0) return WR_E_SIZE;
+    const int64_t n_local = host_T->rows_u_local + host_T->rows_i_local;
+    if (!wr_bprmf_step_sharded_supported(n_local, D)) return WR_E_DIM;
+    if (!wr_aligned16(M) || !wr_aligned16(V)) return WR_E_ALIGN;
+    StepSync sy{};
+    sy.world = host_T->world;
+    sy.rank = host_T->rank;
+    sy.epoch = epoch;
+    for (int g = 0; g < sy.world; ++g) {
+        if (!host_flags[g] || !host_slots[g]) return WR_E_NULL;
+        sy.flags[g] = host_flags[g];
+        sy.slots[g] = host_slots[g];
     }
-    return rc;
+    BprParamsT<ShardTabs> bp{{*host_T, *host_Gd}, user, pos, neg, B, host_T->n_users, host_T->n_items, gamma,
+                             1.0f / (float)B_global, (float)B_global, loss_out, 0, (WrWorkspace *)ws};
+    AdamScalars s{l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, bc2_sqrt};
+    float *P = host_T->base[host_T->rank], *G = host_Gd->base[host_Gd->rank];
+    return dispatch_step_fused(bp, D, P, M, V, G, (n_local * D) >> 2, s, nullptr, sy, (cudaStream_t)stream);
 }
 
 extern "C" int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, float *host_loss, float *P, float *M,

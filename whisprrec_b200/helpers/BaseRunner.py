@@ -190,6 +190,8 @@ class BaseRunner(object):
         starts = list(range(0, n, self.batch_size))
         losses = torch.empty(len(starts), dtype=torch.float32, device=batches.device)
         fused_step = hasattr(model, 'train_step')
+        if model.sharded is not None:
+            return self._fit_sharded(model, batches, starts, losses, t0, t1)
         for s, lo in enumerate(starts):
             hi = min(n, lo + self.batch_size)
             batch = {'user_id': batches[0, lo:hi], 'pos_item': batches[1, lo:hi], 'neg_items': batches[2, lo:hi],
@@ -203,6 +205,26 @@ class BaseRunner(object):
             model.optimizer.step()
         loss_host = losses.cpu().numpy()                    # one sync per epoch
         model.tables.ws.raise_on_status()
+        self.last_epoch_stats = {'host_prep_s': t1 - t0, 'device_s': time() - t1, 'steps': len(starts), 'rows': n}
+        return np.mean(loss_host).item()
+
+    def _fit_sharded(self, model, batches, starts, losses, t0, t1):
+        """The same epoch on row-sharded tables: every rank built the same batches (same seeds) and takes its
+        slice of each; the global batch -- hence the result -- is the single-GPU one."""
+        st = model.sharded
+        n = batches.shape[1]
+        for s, lo in enumerate(starts):
+            hi = min(n, lo + self.batch_size)
+            a, b = st.layout.batch_slice(hi - lo)
+            if b == a:
+                raise NotImplementedError('a batch smaller than the number of ranks')
+            loss = model.sharded_train_step(batches[0, lo + a:lo + b], batches[1, lo + a:lo + b],
+                                            batches[2, lo + a:lo + b], hi - lo, self.learning_rate, self.l2)
+            losses[s:s + 1].copy_(loss[:1])
+        if model.optimizer is not None:
+            model.optimizer.step_count = st.step_count
+        loss_host = losses.cpu().numpy()
+        st.ws.raise_on_status()
         self.last_epoch_stats = {'host_prep_s': t1 - t0, 'device_s': time() - t1, 'steps': len(starts), 'rows': n}
         return np.mean(loss_host).item()
 
@@ -236,6 +258,16 @@ class BaseRunner(object):
         if not model.test_all:
             raise KeyError('neg_items')                      # what the reference hits with --test_all 0
         (user, pos), (hptr, hidx) = self._eval_inputs(dataset)
+        if model.sharded is not None:
+            from .. import sharded as S
+            st = model.sharded
+            if getattr(model, '_dev_hist_local', None) is None:
+                lp, li = st.layout.localise_history(*dataset.corpus.history_csr())
+                model._dev_hist_local = (torch.from_numpy(lp).to(user.device), torch.from_numpy(li).to(user.device))
+            shards, items_local = model.sharded_eval_tables()
+            rank, target, tki, tkv = S.sharded_eval(st, shards, items_local, user, pos, model._dev_hist_local, k=k,
+                                                    precision=self.eval_precision)
+            return rank, target, tki, tkv, None
         ue, ie = model.eval_tables()
         out = _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, k=k,
                                   precision=self.eval_precision)

@@ -108,11 +108,25 @@ def run(args, model_class, reader_class, runner_class, reader_name):
 
     utils.init_seed(args.random_seed)
 
-    os.environ['CUDA_VISIBLE_DEVICES'] = args.gpu
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world == 1:
+        os.environ['CUDA_VISIBLE_DEVICES'] = args.gpu
     if args.gpu == '' or not torch.cuda.is_available():
         raise RuntimeError('whisprrec_b200 needs a CUDA (sm_100) device: it has no CPU path. '
                            'Run the reference for a CPU run.')
-    args.device = torch.device('cuda')
+    peers = None
+    if world > 1:
+        # torchrun --nproc-per-node G main.py ...: one rank per GPU of the box, tables row-sharded over them
+        import torch.distributed as dist
+        from . import sharded
+        args.device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+        torch.cuda.set_device(args.device)
+        dist.init_process_group('nccl', device_id=args.device)
+        peers = sharded.PeerGroup(args.device)
+        if peers.rank != 0:
+            logging.getLogger().setLevel(logging.WARNING)
+    else:
+        args.device = torch.device('cuda')
     logging.info('Device: {}'.format(args.device))
 
     corpus_path = os.path.join(args.path, args.dataset, reader_name + '.pkl')
@@ -135,6 +149,9 @@ def run(args, model_class, reader_class, runner_class, reader_name):
 
     data_dict = {phase: model_class.Dataset(model, corpus, phase) for phase in ('train', 'dev', 'test')}
     runner = runner_class(args)
+    if peers is not None:
+        model.fuse()
+        model.shard(peers)                       # every rank holds the same seed-initialised tables at this point
     if args.load > 0:
         model.load_model()
     if args.train > 0:

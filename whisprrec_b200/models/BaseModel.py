@@ -104,14 +104,26 @@ class BaseModel(nn.Module):
         pass
 
     def save_model(self, model_path=None):
-        """BaseModel.py:48-53: state_dict only (same keys / shapes / dtype as the reference)."""
+        """BaseModel.py:48-53: state_dict only (same keys / shapes / dtype as the reference).  Sharded: the rows
+        are collected from their owners first and rank 0 writes the file."""
         model_path = self.model_path if model_path is None else model_path
+        st = getattr(self, 'sharded', None)
+        if st is not None:
+            self.unshard()
+            if st.peers.rank != 0:
+                return
         utils.check_dir(model_path)
         torch.save(self.state_dict(), model_path)
 
     def load_model(self, model_path=None):
         model_path = self.model_path if model_path is None else model_path
+        st = getattr(self, 'sharded', None)
+        if st is not None:
+            st.peers.host_sync()                 # rank 0 has finished writing
         self.load_state_dict(torch.load(model_path))
+        if st is not None:
+            t = self.tables
+            st.load_full(t.users(t.P), t.items(t.P))
         logging.info('Load model from ' + model_path)
 
     def count_variables(self):
@@ -192,6 +204,44 @@ class GeneralModel(BaseModel):
 
     def _on_fused(self):
         pass
+
+    # ---- one box, several GPUs: row-sharded tables over NVLink peer memory (whisprrec_b200/sharded.py) ----
+    sharded = None
+
+    def shard(self, peers):
+        """Distribute the (replicated-at-init) tables over the ranks of `peers`; from here on fit() / evaluate()
+        run the sharded kernels.  Every rank must call this with identically initialised parameters."""
+        from .. import sharded as S
+        t = self.fuse()
+        lay = S.ShardLayout(t.n_users, t.n_items, peers.world, peers.rank)
+        st = S.ShardedTables(peers, lay, t.D)
+        st.load_full(t.users(t.P), t.items(t.P))
+        st.M.copy_(lay.shard_of_table(t.M))
+        st.V.copy_(lay.shard_of_table(t.V))
+        st.step_count = self.optimizer.step_count if self.optimizer is not None else 0
+        self.sharded = st
+        self._on_sharded()
+        return st
+
+    def _on_sharded(self):
+        pass
+
+    def sharded_train_step(self, user, pos, neg, B_global, lr, l2):
+        """This rank's slice of one global batch; returns the batch loss (device view, same on every rank)."""
+        raise NotImplementedError
+
+    def sharded_eval_tables(self):
+        """(wr_shards of the table to score, this rank's item rows of it)."""
+        st = self.sharded
+        return st.T, st.item_rows(st.P)
+
+    def unshard(self):
+        """Copy the shards back into the full fused tables (checkpointing, hand-over to single-GPU code)."""
+        st, t = self.sharded, self.tables
+        u, i = st.gather_full()
+        t.users(t.P).copy_(u)
+        t.items(t.P).copy_(i)
+        st.peers.barrier()
 
     def build_optimizer(self, name, lr, l2):
         """What BaseRunner._build_optimizer hands back for this model."""

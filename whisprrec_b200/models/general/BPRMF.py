@@ -84,6 +84,10 @@ class BPRMF(GeneralModel):
                              sync=sync)
         return st[1]
 
+    def sharded_train_step(self, user, pos, neg, B_global, lr, l2):
+        from ... import sharded as S
+        return S.bprmf_step(self.sharded, user, pos, neg, B_global, lr, l2)
+
     def full_predict(self, feed_dict):
         """BPRMF.py:82-91: the dense [B, n_items] score matrix (compatibility API; the runner's evaluation
         uses the fused rank kernel and never materialises it)."""

@@ -145,6 +145,19 @@ class LightGCN(GeneralModel):
     def eval_tables(self):
         return self.forward()
 
+    def _on_sharded(self):
+        from ... import sharded as S
+        rowptr, col, dinv = self._adj_host
+        self.sharded_gcn = S.ShardedLightGCN(self.sharded, rowptr, col, dinv, self.gcn_layers, self.reg_weight)
+
+    def sharded_train_step(self, user, pos, neg, B_global, lr, l2):
+        return self.sharded_gcn.step(user, pos, neg, B_global, lr, l2)
+
+    def sharded_eval_tables(self):
+        g, st = self.sharded_gcn, self.sharded
+        g.propagate()
+        return g.pool_T, st.item_rows(g.pool)
+
     def full_predict(self, feed_dict):
         """LightGCN.py:177-187 (compatibility API, dense output; the runner uses the fused rank kernel)."""
         ue, ie = self.forward()

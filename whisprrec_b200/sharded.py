@@ -200,6 +200,12 @@ class ShardedTables(object):
         self.loss_part = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=dev)
         self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self.step_count = 0
+        # synchronisation words of the single-launch step: [2][8] uint32 flags, then [2][8] float loss slots
+        _, sync_ptrs = peers.alloc_bytes(256)
+        self.step_flag_ptrs = list(sync_ptrs)
+        self.step_slot_ptrs = [p + 4 * 2 * _lib.MAX_WORLD for p in sync_ptrs]
+        self.single_launch = _lib.bprmf_step_sharded_supported(layout.n_local, self.D)
+        self._sync_epoch = 0           # last epoch the single-launch step has used on this table set
 
     def symmetric(self):
         """A zeroed [n_local, D] fp32 table on every rank -> (local tensor, wr_shards describing all of them)."""
@@ -223,6 +229,8 @@ class ShardedTables(object):
         lay = self.layout
         s = self.T if shards is None else shards
         dev = self.peers.device
+        self.peers.barrier()           # every rank's stream has finished writing its rows (single-launch steps
+        #                                only tell the NEXT step's kernel, not other readers)
         u = _lib.gather_rows_sharded(s, 0, torch.arange(lay.n_users, device=dev), self.D, self.ws)
         i = _lib.gather_rows_sharded(s, 1, torch.arange(lay.n_items, device=dev), self.D, self.ws)
         return u, i
@@ -239,9 +247,18 @@ class ShardedTables(object):
 def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
     """One BPRMF iteration on this rank's slice (user, pos, neg) of a global batch of B_global rows.
 
+    Cache-sized shards: wr_bprmf_step_sharded, one cooperative launch per rank.  Larger ones:
     fwd+bwd with remote gathers / remote REDs -> barrier (all gradient rows have landed; carries the loss) ->
     Adam+L2 over the local shard -> barrier (parameters final before anyone gathers again).
     Returns the batch loss (device scalar view, identical on every rank)."""
+    if tabs.single_launch:
+        # cache-sized shards: one cooperative launch, both cross-GPU meeting points inside the kernel
+        tabs.step_count += 1
+        tabs._sync_epoch += 1
+        _lib.bprmf_step_sharded(tabs.T, tabs.Gd, tabs.M, tabs.V, user, pos, neg, B_global, tabs.D, tabs.step_count,
+                                lr, l2, tabs.step_flag_ptrs, tabs.step_slot_ptrs, tabs.loss, tabs.ws,
+                                epoch=tabs._sync_epoch)
+        return tabs.loss
     _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
     loss = tabs.peers.barrier(tabs.loss_part[:1])
     tabs.adam(lr, l2)
@@ -331,6 +348,7 @@ def sharded_eval(tabs, shards, item_table_local, user, pos, hist_local, k=0, pre
     top-k lists, one all-gather of [R, k] candidates followed by the merge kernel."""
     lay, peers, D = tabs.layout, tabs.peers, tabs.D
     dist = peers.dist
+    peers.barrier()                    # the table being scored is final on every rank
     urows = _lib.gather_rows_sharded(shards, 0, user, D, tabs.ws)
     prows = _lib.gather_rows_sharded(shards, 1, pos, D, tabs.ws)
     target = _lib.rowdot(urows, prows, round_bf16=(precision == 1))
