@@ -37,6 +37,27 @@ TRAFFIC_PER_LAUNCH = None      # dram bytes of one bprmf_step_kernel launch from
 WORKLOAD = 'BPRMF emb=64 B=2048 Adam(lr=1e-3,l2=1e-6) on ml-1m-shaped synthetic (6040 users x 3706 items, 668862 train rows)'
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: anything a library prints there (NCCL's version banner, torchrun
+    notices) is sent to stderr instead; emit() writes the line to the real stdout."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -224,7 +245,7 @@ def run_ours(a, rank, world, local_rank):
         if not a.no_extras:
             line['extra'] = extras(corpus, dev, model, runner, data, hbm_peak)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -359,7 +380,7 @@ def run_ours_sharded(a, rank, world, local_rank):
                                              'barrier_after_adam': float(seg[:, 3].mean())}},
     }
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     peers.close()
     dist.destroy_process_group()
 
@@ -425,7 +446,7 @@ def run_reference(a, rank):
         dt += d
     value = a.steps * per_step * B / dt
     sample = '%d batches of B=%d per step, model-only (batches pre-assembled), oracle port of the reference' % (per_step, B)
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': 'train_interactions_per_s', 'value': value, 'unit': 'interactions/s',
         'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dt / a.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -433,7 +454,7 @@ def run_reference(a, rank):
         'cpu_baseline': {'value': value, 'unit': 'interactions/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': 'interactions/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-    }))
+    })
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -581,6 +602,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     import logging
     logging.disable(logging.INFO)
+    quiet_stdout()
     if a.impl == 'reference':
         run_reference(a, rank)
         return
