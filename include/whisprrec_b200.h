@@ -150,8 +150,9 @@ int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int
  *             fast path (the point of the fusion is not to write it).
  * precision 0: fp32 FMA chains over d = 0..D-1 for every score (target included), so comparisons are
  * consistent.  precision 1: bf16 operands on the tcgen05 tensor cores (TMA-fed, TMEM accumulators), fp32
- * accumulation; D in {64, 128}; ranks only (topk_idx must be NULL); needs `scratch`; looser parity (operands are
- * rounded to bf16, the target's own column is excluded explicitly).
+ * accumulation; D in {64, 128}; ranks and, if asked for, the top-k lists come out of the same epilogue; needs
+ * `scratch`; looser parity (operands are rounded to bf16, the target's own column is excluded from the count
+ * explicitly).
  */
 int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                       int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,

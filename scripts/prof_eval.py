@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run one full-ranking eval configuration (for ncu / timing): python scripts/prof_eval.py R nI D precision [reps]"""
+"""Run one full-ranking eval configuration (for ncu / timing): python scripts/prof_eval.py R nI D precision [reps [k]]"""
 import os
 import sys
 
@@ -10,6 +10,7 @@ from whisprrec_b200 import _lib  # noqa: E402
 
 R, nI, D, prec = (int(x) for x in sys.argv[1:5])
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 3
+k = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 dev = torch.device('cuda')
 g = torch.Generator(device=dev)
 g.manual_seed(3407)
@@ -26,9 +27,9 @@ ms = []
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    out = _lib.eval_rank_topk(U, I, user, pos, hp, hi, ws, precision=prec)
+    out = _lib.eval_rank_topk(U, I, user, pos, hp, hi, ws, precision=prec, k=k)
     e1.record()
     torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
 tf = 2.0 * R * nI * D / (min(ms) * 1e-3) / 1e12
-print(f'R={R} nI={nI} D={D} precision={prec}: best {min(ms):.3f} ms  {R / (min(ms) * 1e-3):.3e} rows/s  {tf:.1f} TFLOP/s  mean rank {out[0].float().mean().item():.1f}')
+print(f'R={R} nI={nI} D={D} precision={prec} k={k}: best {min(ms):.3f} ms  {R / (min(ms) * 1e-3):.3e} rows/s  {tf:.1f} TFLOP/s  mean rank {out[0].float().mean().item():.1f}')

@@ -472,6 +472,20 @@ def test_eval_tensor_core_path_vs_bf16_oracle(R, nI, D, ws):
     # without the score dump (the production call) the ranks are the same
     rank2 = _lib.eval_rank_topk(dv(U), dv(I), dv(user), dv(pos), dv(hp), dv(hi), ws, precision=1)[0]
     assert torch.equal(rank, rank2)
+    # top-k lists fused into the tcgen05 epilogue: exact against the kernel's own scores (ties to the lower id),
+    # for k = 10 and the largest supported k; the ranks do not change
+    for k in (10, 32):
+        rank3, _, tki, tkv, _ = _lib.eval_rank_topk(dv(U), dv(I), dv(user), dv(pos), dv(hp), dv(hi), ws, k=k,
+                                                    precision=1)
+        assert torch.equal(rank, rank3)
+        want_i, want_v = O.topk_masked(sc, user, hp, hi, k)
+        want_i = np.where(np.isfinite(want_v), want_i, -1)
+        want_i[:, nI:] = -1                                       # fewer than k items in the table
+        got_i, got_v = host(tki), host(tkv)
+        kk = min(k, nI)
+        assert (got_i[:, :kk] == want_i[:, :kk]).all(), f'top-{k} ids'
+        assert (got_v[:, :kk][want_i[:, :kk] >= 0] == want_v[:, :kk][want_i[:, :kk] >= 0]).all(), f'top-{k} values'
+        assert (got_i[:, kk:] == -1).all()
     assert ws.status() == 0
 
 

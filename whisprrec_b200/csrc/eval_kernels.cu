@@ -324,8 +324,8 @@ using namespace wr;
 // eval_tcgen05.cu
 int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                     int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
-                    int32_t *rank, float *target, const float *target_in, float *scores_out, void *scratch,
-                    WrWorkspace *ws, cudaStream_t st);
+                    int32_t *rank, float *target, const float *target_in, float *scores_out, int k, int32_t *topk_idx,
+                    float *topk_val, void *scratch, WrWorkspace *ws, cudaStream_t st);
 
 static int eval_rank_topk_impl(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos,
                                int64_t R, int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr,
@@ -342,9 +342,8 @@ static int eval_rank_topk_impl(const float *Uemb, const float *Iemb, const int64
     cudaStream_t st = (cudaStream_t)stream;
     const bool topk = topk_idx != nullptr;
     if (precision == 1) {
-        if (topk) return WR_E_PRECISION;      // top-k lists come from the fp32 path
         return wr_eval_rank_tc(Uemb, Iemb, user, pos, R, n_users, n_items, D, hist_ptr, hist_idx, rank, target,
-                               target_in, scores_out, scratch, (WrWorkspace *)ws, st);
+                               target_in, scores_out, topk ? k : 0, topk_idx, topk_val, scratch, (WrWorkspace *)ws, st);
     }
     if (precision != 0) return WR_E_PRECISION;
     EvalParams p{Uemb, Iemb, user, pos, R, n_users, n_items, hist_ptr, hist_idx, topk ? k : 1,

@@ -29,7 +29,12 @@ struct TcParams {
     int32_t *rank;
     float *scores;              // optional dense [R, n_items] dump of the tensor-core scores (tests)
     int splits, tiles_per_split, n_tiles;
+    int k;                      // top-k lists (TOPK instantiation only)
+    int32_t *topk_idx;
+    float *topk_val;
 };
+
+constexpr int TC_KMAX = 32;
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers (sm_100a)
@@ -194,7 +199,59 @@ struct TcCfg {
     static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/ + 4 * TC_BM * 4;
 };
 
-template <int D, int VARIANT>
+// Top-k state of one epilogue thread (one row, one 64-column stripe of every tile), in local memory:
+//   - the k best scores seen so far, UNSORTED, with the position of the worst of them; tau = its value.  A new
+//     entry overwrites the worst one and the new worst is found by one pass of k independent loads (no dependent
+//     shift chain: local memory is an L2 round trip away here, the shared memory being given to the operand ring);
+//   - an unsorted buffer that scores beating tau are APPENDED to.
+// The buffers of a warp are folded into the lists together ("compaction", warp-synchronous) when any lane's buffer
+// could overflow on the next chunk, so the insertions of the 32 rows run side by side instead of one lane at a time.
+// After the first tiles a score beats tau about k/m of the time (m = scores seen by the thread).
+constexpr int TC_TOPBUF = 64;
+struct TopState {
+    float lv[TC_KMAX];
+    int32_t li[TC_KMAX];
+    float bv[TC_TOPBUF];
+    int32_t bi[TC_TOPBUF];
+};
+// ordering of candidates: higher value first, lower id first among equal values
+__device__ __forceinline__ bool top_worse(float v, int32_t id, float w, int32_t wid) {
+    return v < w || (v == w && id > wid);
+}
+__device__ __noinline__ void top_compact(TopState &t, int k, int &bcnt, float &tau, int &worst) {
+    const int most = __reduce_max_sync(0xffffffffu, bcnt);
+    for (int i = 0; i < most; ++i) {
+        if (i < bcnt) {
+            const float v = t.bv[i];
+            if (v > tau) {                       // ids arrive ascending: a tie with the worst kept entry loses
+                t.lv[worst] = v;
+                t.li[worst] = t.bi[i];
+                float w = t.lv[0];
+                int32_t wid = t.li[0];
+                int wp = 0;
+                for (int j = 1; j < k; ++j) {
+                    const float x = t.lv[j];
+                    const int32_t xid = t.li[j];
+                    if (top_worse(x, xid, w, wid)) {
+                        w = x;
+                        wid = xid;
+                        wp = j;
+                    }
+                }
+                worst = wp;
+                tau = w;
+            }
+        }
+    }
+    bcnt = 0;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+template <int D, int VARIANT, bool TOPK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     using C = TcCfg<D>;
@@ -306,6 +363,15 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (cur < hend) next_h = __ldg(p.hist_idx + cur);
         }
         int cnt = 0;
+        TopState top;
+        float tau = -INFINITY;
+        int bcnt = 0, worst = 0;
+        if (TOPK) {
+            for (int i = 0; i < p.k; ++i) {
+                top.lv[i] = -INFINITY;
+                top.li[i] = INT32_MAX - i;      // empty slots: worse than anything, distinct, evicted first
+            }
+        }
         for (int t = t0, it = 0; t < t1; ++t, ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
@@ -318,9 +384,9 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + col0), v);
                 const int32_t j0 = t * TC_BN + col0;
                 // columns of this chunk that must not count: history, past the table, the target itself
-                uint32_t m = 0;
+                uint32_t m = 0, m_top = 0;      // m_top: not a candidate (history, past the table); the target is one
                 if (!live) {
-                    m = 0xffffffffu;
+                    m = m_top = 0xffffffffu;
                 } else {
                     while (next_h < j0 + 32) {
                         if (next_h >= j0) m |= 1u << (next_h - j0);
@@ -328,10 +394,39 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         next_h = cur < hend ? __ldg(p.hist_idx + cur) : INT32_MAX;
                     }
                     if (j0 + 32 > n_items) m |= j0 >= n_items ? 0xffffffffu : (0xffffffffu << (n_items - j0));
+                    m_top = m;
                     const uint32_t pj = (uint32_t)(posj - j0);
                     if (pj < 32u) m |= 1u << pj;
                 }
                 tmem_ld_wait();
+                if (TOPK) {
+                    if (m_top != 0) {       // rare: history / table-end columns can never be candidates
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if ((m_top >> i) & 1u) v[i] = 0xff800000u;      // -inf; these columns are in m as well
+                    }
+                    // half an instruction per score (3-input max) finds out whether a group of 8 columns holds a
+                    // candidate; only such a group (rare once tau has settled) pays for 8 predicated appends
+#pragma unroll
+                    for (int g8 = 0; g8 < 32; g8 += 8) {
+                        float mx = fmax3(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1]), __uint_as_float(v[g8 + 2]));
+                        mx = fmax3(mx, __uint_as_float(v[g8 + 3]), __uint_as_float(v[g8 + 4]));
+                        mx = fmax3(mx, __uint_as_float(v[g8 + 5]), __uint_as_float(v[g8 + 6]));
+                        mx = fmaxf(mx, __uint_as_float(v[g8 + 7]));
+                        if (mx > tau) {
+#pragma unroll
+                            for (int i = g8; i < g8 + 8; ++i) {
+                                const float x = __uint_as_float(v[i]);
+                                if (x > tau) {
+                                    top.bv[bcnt] = x;
+                                    top.bi[bcnt] = j0 + i;
+                                    ++bcnt;
+                                }
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, bcnt > TC_TOPBUF - 32)) top_compact(top, p.k, bcnt, tau, worst);
+                }
                 if (m == 0) {
                     // fast path, 2 instructions per score.  VARIANT 0: FSETP + predicated integer add (both ALU pipe);
                     // 1: FSETP (ALU) + predicated FADD (FMA pipe); 2: FFMA.SAT + FADD (FMA pipe only):
@@ -390,12 +485,45 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             mbar_arrive(&tm_empty[acc]);
         }
+        // the four stripe lists of a row meet in the (now idle) B-stage shared memory: [row][stripe][k]
+        float *lv = reinterpret_cast<float *>(sB);
+        int32_t *li = reinterpret_cast<int32_t *>(sB + TC_BM * 4 * TC_KMAX * 4);
+        if (TOPK) {
+            top_compact(top, p.k, bcnt, tau, worst);
+            for (int i = 0; i < p.k; ++i) {
+                lv[(rl * 4 + grp) * TC_KMAX + i] = top.lv[i];
+                li[(rl * 4 + grp) * TC_KMAX + i] = top.li[i];
+            }
+        }
         cnt_s[grp * TC_BM + rl] = cnt;
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // the epilogue warps only
         if (grp == 0 && r < p.R) {
             const int total = cnt_s[rl] + cnt_s[TC_BM + rl] + cnt_s[2 * TC_BM + rl] + cnt_s[3 * TC_BM + rl];
             if (p.splits == 1) p.rank[r] = 1 + total;
             else atomicAdd(&p.rank[r], total);
+            if (TOPK) {
+                // the row's 4k candidates (unsorted) -> its k best in order: k selection passes, taken slots marked
+                const int n = 4 * TC_KMAX;
+                for (int s = 0; s < p.k; ++s) {
+                    int best = -1;
+                    float bv = 0.f;
+                    int32_t bi = 0;
+                    for (int o = 0; o < n; ++o) {
+                        if ((o & (TC_KMAX - 1)) >= p.k) continue;
+                        const int32_t id = li[rl * n + o];
+                        if (id < 0 || id >= INT32_MAX - TC_KMAX) continue;      // taken / empty
+                        const float x = lv[rl * n + o];
+                        if (best < 0 || top_worse(bv, bi, x, id)) {
+                            best = o;
+                            bv = x;
+                            bi = id;
+                        }
+                    }
+                    if (best >= 0) li[rl * n + best] = -1;
+                    p.topk_val[r * p.k + s] = best >= 0 ? bv : -INFINITY;
+                    p.topk_idx[r * p.k + s] = best >= 0 ? bi : -1;
+                }
+            }
         }
     }
     tc_fence_before();
@@ -435,12 +563,14 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int D, int VARIANT>
+template <int D, int VARIANT, bool TOPK>
 static int launch_tc_v(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TcCfg<D>::SMEM);
+    constexpr int smem = TcCfg<D>::SMEM;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D, VARIANT, TOPK>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    eval_tc_rank_kernel<D, VARIANT><<<dim3(row_tiles, p.splits), TC_THREADS, TcCfg<D>::SMEM, st>>>(ma, mb, p);
+    eval_tc_rank_kernel<D, VARIANT, TOPK><<<dim3(row_tiles, p.splits), TC_THREADS, smem, st>>>(ma, mb, p);
     return (int)cudaGetLastError();
 }
 
@@ -451,11 +581,12 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, 
         const char *e = getenv("WR_TC_VARIANT");        // tuning knob for the epilogue's counting form
         variant = e ? atoi(e) : 1;
     }
+    if (p.topk_idx) return launch_tc_v<D, 1, true>(ma, mb, p, row_tiles, st);
     switch (variant) {
-        case 1: return launch_tc_v<D, 1>(ma, mb, p, row_tiles, st);
-        case 2: return launch_tc_v<D, 2>(ma, mb, p, row_tiles, st);
-        case 3: return launch_tc_v<D, 3>(ma, mb, p, row_tiles, st);
-        default: return launch_tc_v<D, 0>(ma, mb, p, row_tiles, st);
+        case 1: return launch_tc_v<D, 1, false>(ma, mb, p, row_tiles, st);
+        case 2: return launch_tc_v<D, 2, false>(ma, mb, p, row_tiles, st);
+        case 3: return launch_tc_v<D, 3, false>(ma, mb, p, row_tiles, st);
+        default: return launch_tc_v<D, 0, false>(ma, mb, p, row_tiles, st);
     }
 }
 
@@ -473,8 +604,8 @@ extern "C" size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int p
 // precision-1 body of wr_eval_rank_topk (eval_kernels.cu dispatches here)
 int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                     int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
-                    int32_t *rank, float *target, const float *target_in, float *scores_out, void *scratch,
-                    WrWorkspace *ws, cudaStream_t st) {
+                    int32_t *rank, float *target, const float *target_in, float *scores_out, int k, int32_t *topk_idx,
+                    float *topk_val, void *scratch, WrWorkspace *ws, cudaStream_t st) {
     if (D != 64 && D != 128) return WR_E_DIM;
     if (!scratch) return WR_E_NULL;
     if ((reinterpret_cast<uintptr_t>(scratch) & 1023u) != 0) return WR_E_ALIGN;
@@ -500,13 +631,15 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
     if (rc) return rc;
 
     TcParams p{user, pos, R, n_users, n_items, hist_ptr, hist_idx, target_in ? target_in : target, row_ok, rank,
-               scores_out, 1, 0, 0};
+               scores_out, 1, 0, 0, k, topk_idx, topk_val};
     p.n_tiles = (int)((n_items + TC_BN - 1) / TC_BN);
     const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
     if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
     const int row_tiles = (int)row_tiles64;
     int splits = 1;
-    if (row_tiles < kSMs) splits = (kSMs + row_tiles - 1) / row_tiles;   // one CTA per SM (512 TMEM columns each)
+    // few rows: split the item range over CTAs, one CTA per SM (512 TMEM columns each); rank counts merge with integer
+    // atomics.  Top-k lists are per CTA, so that mode keeps a row's items in one CTA.
+    if (row_tiles < kSMs && !topk_idx) splits = (kSMs + row_tiles - 1) / row_tiles;
     if (splits > p.n_tiles) splits = p.n_tiles;
     if (splits > 65535) splits = 65535;
     p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
