@@ -103,6 +103,24 @@ int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, float *host_lo
                        double beta1, double beta2, float eps, float step_size, float bc2_sqrt, float *loss_out,
                        void *ws, void *stream, int sync);
 
+/* wr_bprmf_ctx_*: the host-fed iteration without a copy engine or a stream synchronisation in the loop.  The context
+ * keeps the table pointers and hyper-parameters; wr_bprmf_ctx_step takes the batch ids in MAPPED PINNED host memory
+ * ([3, B] int64; e.g. a torch `.pin_memory()` tensor), launches the step kernel on them directly (the H2D transfer is
+ * the kernel's own loads over PCIe) and waits on a sequence word the kernel raises in mapped host memory:
+ * wait = 1 returns when the whole step is complete (raised by the last CTA to leave); wait = 2 returns as soon as the
+ * batch loss is out, which is before the Adam phase, so the host prepares and launches the next step while the update
+ * of this one completes (the stream still orders the kernels); wait = 0 does not wait.  adam_t: Adam's step count t
+ * (1, 2, ...); step_size / bias correction are evaluated here in double exactly as torch does.  The id buffer may be
+ * reused once the call has returned with wait != 0.  Returns WR_E_ALIGN if host_ids is not mapped pinned memory.
+ */
+typedef struct wr_bprmf_ctx wr_bprmf_ctx;
+int wr_bprmf_ctx_create(float *P, float *M, float *V, float *G, int64_t n_users, int64_t n_items, int D, float gamma,
+                        double lr, float l2, double beta1, double beta2, float eps, void *ws, void *stream,
+                        wr_bprmf_ctx **out);
+int wr_bprmf_ctx_step(wr_bprmf_ctx *ctx, const int64_t *host_ids, int64_t B, int64_t adam_t, int wait,
+                      float *host_loss_out);
+int wr_bprmf_ctx_destroy(wr_bprmf_ctx *ctx);
+
 /* ---- LightGCN propagation ------------------------------------------------------------------------------
  * wr_csr_norm_weights: the value recipe of LightGCN.py:89-97: val[e] = fl32(fl32(dinv[row] * 1) * dinv[col]).
  * dinv = np.power(fp32(deg) + 1e-10, -0.5) comes from the caller (NumPy's fp32 pow is not correctly rounded,

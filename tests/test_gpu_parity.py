@@ -128,11 +128,23 @@ def test_bprmf_host_fed_step_matches_device_step(ws):
         ids = np.stack([rng.randint(0, corpus.n_users, B), rng.randint(1, corpus.n_items, B),
                         rng.randint(1, corpus.n_items, B)]).astype(np.int64)
         pinned = torch.from_numpy(ids).pin_memory()
-        loss_host = models[0].train_step_host(pinned)
+        loss_host = models[0].train_step_host(pinned)           # mapped-memory path (wr_bprmf_ctx_step)
         d = dv(ids)
         loss_dev = models[1].train_step({'user_id': d[0], 'pos_item': d[1], 'neg_items': d[2]})
-        assert float(loss_host[0]) == pytest.approx(float(loss_dev), rel=2e-6)
+        assert isinstance(loss_host, float) and loss_host == pytest.approx(float(loss_dev), rel=2e-6)
         assert_close(host(models[0].tables.P), host(models[1].tables.P), f'P step {step}', rtol=1e-5, atol_scale=2e-6)
+        # the copy-engine form of the same call (wr_bprmf_step_host) on a third copy of the state
+        if step == 0:
+            t2 = models[1].tables
+            P3, M3, V3, G3 = (torch.zeros_like(t2.P) for _ in range(4))
+            utils.init_seed(3407)
+            m3 = BPRMF(model_args(BPRMF, lr=1e-3, l2=1e-6), corpus).to(DEV)
+            P3.copy_(m3.fuse().P)
+            stage, pl = torch.empty(3 * 2048, dtype=torch.int64, device=DEV), torch.zeros(1).pin_memory()
+            dl, ws3 = torch.zeros(1, device=DEV), _lib.Workspace(DEV)
+        _lib.bprmf_step_host(pinned, stage, pl, P3, M3, V3, G3, corpus.n_users, step + 1, 1e-3, 1e-6, dl, ws3)
+        assert float(pl[0]) == pytest.approx(loss_host, rel=2e-6)
+        assert_close(host(P3), host(models[0].tables.P), f'P (copy-engine form) step {step}', rtol=1e-5, atol_scale=2e-6)
     o_loss, _, _ = O.bpr_fwd_bwd(host(models[1].tables.P[:corpus.n_users]), host(models[1].tables.P[corpus.n_users:]),
                                  ids[0], ids[1], ids[2])
     assert np.isfinite(o_loss.item())

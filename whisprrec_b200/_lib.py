@@ -32,6 +32,10 @@ SIGNATURES = {
                              _f32, _p, _p, _p, _p]),
     'wr_bprmf_step_host': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32,
                                   _f32, _f32, _p, _p, _p, _int]),
+    'wr_bprmf_ctx_create': (_int, [_p, _p, _p, _p, _i64, _i64, _int, _f32, _f64, _f32, _f64, _f64, _f32, _p, _p,
+                                   _c.POINTER(_p)]),
+    'wr_bprmf_ctx_step': (_int, [_p, _p, _i64, _i64, _int, _c.POINTER(_f32)]),
+    'wr_bprmf_ctx_destroy': (_int, [_p]),
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
     'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
@@ -198,6 +202,38 @@ def bprmf_step_host(host_ids, dev_ids, host_loss, P, M, V, G, n_users, step, lr,
                                     ptr(M, F32), ptr(V, F32), ptr(G, F32), B, P.shape[1], n_users,
                                     P.shape[0] - n_users, gamma, l2, beta1, beta2, eps, ss, bc2s, ptr(loss_out, F32),
                                     ws.ptr, stream_ptr(), int(sync)))
+
+
+class BprmfContext:
+    """wr_bprmf_ctx: the host-fed BPRMF step (pinned ids in, loss out) with everything constant bound once."""
+
+    def __init__(self, P, M, V, G, n_users, lr, l2, ws, beta1=0.9, beta2=0.999, eps=1e-8, gamma=1e-10):
+        self._keep = (P, M, V, G, ws)
+        self._h = _p()
+        self._loss = _f32(0.0)
+        self._step = load().wr_bprmf_ctx_step
+        check(load().wr_bprmf_ctx_create(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), n_users,
+                                         P.shape[0] - n_users, P.shape[1], gamma, lr, l2, beta1, beta2, eps, ws.ptr,
+                                         stream_ptr(), ctypes.byref(self._h)))
+
+    def step(self, host_ids_ptr, B, adam_t, wait=1):
+        """host_ids_ptr: address of a pinned [3, B] int64 buffer.  wait: 1 = until the step is complete, 2 = until
+        the loss is out (the Adam phase may still be running), 0 = not at all.  Returns the batch loss (float)."""
+        rc = self._step(self._h, host_ids_ptr, B, adam_t, int(wait), ctypes.byref(self._loss))
+        if rc:
+            check(rc)
+        return self._loss.value
+
+    def close(self):
+        if self._h:
+            load().wr_bprmf_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
 
 def csr_norm_weights(rowptr, col, dinv, val):

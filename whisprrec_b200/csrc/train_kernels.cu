@@ -1,5 +1,8 @@
 // Training-step kernels: fused BPR forward+backward, EmbLoss, dense Adam+L2 sweep, row gather / scatter-add.
 // See include/whisprrec_b200.h for the reference lines each entry point replaces.
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace wr {
@@ -381,6 +384,9 @@ struct StepSync {
     float *slots[WR_MAX_WORLD];     // rank g's [2 (epoch parity)][WR_MAX_WORLD] loss shares
     int world, rank;
     uint32_t epoch;                 // the step number: 1, 2, 3, ... (the same on every rank)
+    uint32_t *notify;               // optional word in mapped host memory, set to notify_value ...
+    uint32_t notify_value;
+    int notify_early;               // ... as soon as the loss is out (1) / when the whole step is complete (0)
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
@@ -516,7 +522,13 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
                 st_release_gpu(&p.ws->ticket[5], sy.epoch);     // the gate: every rank's gradients have landed
             }
         }
-        if (threadIdx.x == 0) p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + loss_sum : loss_sum;
+        if (threadIdx.x == 0) {
+            p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + loss_sum : loss_sum;
+            if (sy.notify && sy.notify_early) {   // the host may read the loss (and reuse the id buffer) during the Adam phase
+                __threadfence_system();
+                st_release_sys(sy.notify, sy.notify_value);
+            }
+        }
     } else if (sy.world > 1) {
         if (threadIdx.x == 0) {
             while (ld_acquire_u32(&p.ws->ticket[5]) != sy.epoch) {}
@@ -556,13 +568,18 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
             G[i2] = z;
         }
     }
-    if (sy.world > 1) __syncthreads();          // the departure below speaks for the whole CTA's stores
+    const bool announce = sy.world > 1 || (sy.notify && !sy.notify_early);
+    if (announce) __syncthreads();              // the departure below speaks for the whole CTA's stores
     if (threadIdx.x == 0) {
-        if (sy.world > 1) __threadfence();
+        if (announce) __threadfence();
         const uint32_t t = atomicAdd(&p.ws->ticket[4], 1u);
         if (t == gridDim.x - 1) {
             p.ws->ticket[3] = 0;
             p.ws->ticket[4] = 0;
+            if (sy.notify && !sy.notify_early) {    // every CTA has left: the step is complete (their departures were
+                __threadfence_system();            // fenced), tell the host
+                st_release_sys(sy.notify, sy.notify_value);
+            }
             if (sy.world > 1) {                 // this rank's rows of P are final: peers may gather them for step e+1
                 __threadfence_system();
                 for (int g = 0; g < sy.world; ++g) st_release_sys(sy.flags[g] + WR_MAX_WORLD + sy.rank, sy.epoch);
@@ -859,6 +876,121 @@ extern "C" int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, flo
     if (e != cudaSuccess) return (int)e;
     if (sync) e = cudaStreamSynchronize(st);
     return (int)e;
+}
+
+// ---- host-fed step with no copy engine and no stream synchronisation in the loop ----------------------------------
+struct wr_bprmf_ctx {
+    float *P, *M, *V, *G;
+    int64_t n_users, n_items;
+    int D;
+    float gamma, l2, eps;
+    double beta1, beta2, lr;
+    void *ws;
+    cudaStream_t stream;
+    float *host_loss;          // mapped pinned: [0] = loss
+    uint32_t *host_flag;       // mapped pinned: last step whose loss has been delivered
+    float *dev_loss;           // device word for the copy-engine path (large tables)
+    uint32_t seq;
+    const void *checked[4];    // id buffers already verified to be mapped pinned memory
+};
+
+extern "C" int wr_bprmf_ctx_create(float *P, float *M, float *V, float *G, int64_t n_users, int64_t n_items, int D,
+                                   float gamma, double lr, float l2, double beta1, double beta2, float eps, void *ws,
+                                   void *stream, wr_bprmf_ctx **out) {
+    if (!P || !M || !V || !G || !ws || !out) return WR_E_NULL;
+    if (n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    wr_bprmf_ctx *c = new wr_bprmf_ctx{P, M, V, G, n_users, n_items, D, gamma, l2, eps, beta1, beta2, lr, ws,
+                                       (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, {nullptr, nullptr, nullptr, nullptr}};
+    void *h = nullptr;
+    cudaError_t e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        memset(h, 0, 64);
+        c->host_loss = (float *)h;
+        c->host_flag = (uint32_t *)h + 8;
+        e = cudaMalloc((void **)&c->dev_loss, sizeof(float));
+    }
+    if (e != cudaSuccess) {
+        if (h) cudaFreeHost(h);
+        delete c;
+        return (int)e;
+    }
+    *out = c;
+    return WR_OK;
+}
+
+extern "C" int wr_bprmf_ctx_destroy(wr_bprmf_ctx *c) {
+    if (!c) return WR_E_NULL;
+    cudaStreamSynchronize(c->stream);
+    cudaFreeHost(c->host_loss);
+    cudaFree(c->dev_loss);
+    delete c;
+    return WR_OK;
+}
+
+static int ctx_ids_are_mapped(wr_bprmf_ctx *c, const void *p) {
+    for (int i = 0; i < 4; ++i)
+        if (c->checked[i] == p) return 1;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer != p) return 0;   // pinned, and the same address on the device
+    c->checked[c->seq & 3] = p;
+    return 1;
+}
+
+extern "C" int wr_bprmf_ctx_step(wr_bprmf_ctx *c, const int64_t *host_ids, int64_t B, int64_t adam_t, int wait,
+                                 float *host_loss_out) {
+    if (!c || !host_ids) return WR_E_NULL;
+    if (B <= 0 || adam_t <= 0) return WR_E_SIZE;
+    // torch/optim/adam.py evaluates these in Python floats (C doubles, libm pow): the same calls here
+    const float step_size = (float)(c->lr / (1.0 - pow(c->beta1, (double)adam_t)));
+    const float bc2_sqrt = (float)pow(1.0 - pow(c->beta2, (double)adam_t), 0.5);
+    const int64_t n_elems = (c->n_users + c->n_items) * c->D;
+    const int D = c->D;
+    const bool fused_shape = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
+    if (!ctx_ids_are_mapped(c, host_ids)) return WR_E_ALIGN;
+    ++c->seq;
+    if (!fused_shape || n_elems > WR_FUSED_STEP_MAX_ELEMS) {
+        // large tables: the kernels read the ids straight from the mapped buffer too; the loss comes back by copy
+        int rc = wr_bprmf_step(c->P, c->M, c->V, c->G, host_ids, host_ids + B, host_ids + 2 * B, B, D, c->n_users,
+                               c->n_items, c->gamma, c->l2, c->beta1, c->beta2, c->eps, step_size, bc2_sqrt, nullptr,
+                               c->dev_loss, c->ws, c->stream);
+        if (rc) return rc;
+        cudaError_t e = cudaMemcpyAsync(c->host_loss, c->dev_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && wait) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return (int)e;
+        if (wait && host_loss_out) *host_loss_out = c->host_loss[0];
+        return WR_OK;
+    }
+    BprParams bp{{c->P, c->P + c->n_users * D, c->G, c->G + c->n_users * D}, host_ids, host_ids + B, host_ids + 2 * B,
+                 B, c->n_users, c->n_items, c->gamma, 1.0f / (float)B, (float)B, c->host_loss, 0, (WrWorkspace *)c->ws};
+    AdamScalars s{c->l2, (float)(1.0 - c->beta1), (float)c->beta2, (float)(1.0 - c->beta2), c->eps, step_size, bc2_sqrt};
+    StepSync sy{};
+    sy.world = 1;
+    sy.notify = c->host_flag;
+    sy.notify_value = c->seq;
+    sy.notify_early = wait == 2;
+    const int rc = dispatch_step_fused(bp, D, c->P, c->M, c->V, c->G, n_elems >> 2, s, nullptr, sy, c->stream);
+    if (rc) return rc;
+    if (!wait) return WR_OK;
+    // the kernel raises the flag as soon as the loss is written (before its Adam phase); poll it, and look at the
+    // stream now and then so that a faulted launch cannot spin us forever
+    volatile uint32_t *flag = c->host_flag;
+    for (uint32_t spins = 0; *flag != c->seq; ++spins) {
+        if ((spins & 0xffffu) == 0xffffu) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
+            if (q == cudaSuccess && *flag != c->seq) return (int)cudaErrorUnknown;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (host_loss_out) *host_loss_out = *(volatile float *)c->host_loss;
+    return WR_OK;
 }
 
 extern "C" int wr_gather_rows(const float *T, const int64_t *idx, int64_t B, int D, int64_t n_rows, float *out,

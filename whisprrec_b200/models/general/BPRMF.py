@@ -65,24 +65,25 @@ class BPRMF(GeneralModel):
                         beta2=opt.betas[1], eps=opt.eps)
         return out[0].detach().as_subclass(_base.FusedLoss)
 
-    def train_step_host(self, host_ids, sync=True):
+    def train_step_host(self, host_ids, wait=1):
         """The same iteration fed from the host: `host_ids` is a pinned int64 [3, B] tensor holding the batch's
         user / positive / negative ids (what collate_batch produces, BaseModel.py:96-127).  Covers
-        utils.batch_to_gpu (utils.py:33-37), the step and `loss.detach().cpu()` (BaseRunner.py:200); returns the
-        pinned one-element tensor the loss lands in (valid once the stream is synchronised, i.e. on return when
-        sync=True)."""
-        t = self.fuse()
+        utils.batch_to_gpu (utils.py:33-37), the step and `loss.detach().cpu()` (BaseRunner.py:200) in one C call
+        (wr_bprmf_ctx_step): the kernel reads the ids from the pinned buffer itself and drops the loss into mapped
+        host memory, so there is no copy-engine hop and no stream synchronisation.  wait=1: returns when the step is
+        complete; wait=2: as soon as the loss is out (its Adam phase overlaps the host's next batch).  Returns the
+        batch loss as a float."""
+        ctx = getattr(self, '_host_ctx', None)
         opt = self.optimizer
-        B = host_ids.shape[1]
-        st = getattr(self, '_host_stage', None)
-        if st is None or st[0].numel() < 3 * B:
-            st = self._host_stage = (torch.empty(3 * B, dtype=torch.int64, device=t.P.device),
-                                     torch.zeros(1, dtype=torch.float32).pin_memory())
+        if ctx is None or ctx._keep[0] is not self.tables.P:       # first call, or the tables were re-fused
+            t = self.fuse()
+            ctx = self._host_ctx = _lib.BprmfContext(t.P, t.M, t.V, t.G, t.n_users, opt.lr, opt.weight_decay, t.ws,
+                                                     beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps)
+        if host_ids.dtype != torch.int64 or host_ids.dim() != 2 or host_ids.shape[0] != 3 or \
+                not host_ids.is_contiguous() or host_ids.is_cuda:
+            raise _lib.WhisprError('host_ids must be a contiguous pinned int64 [3, B] host tensor')
         opt.step_count += 1
-        _lib.bprmf_step_host(host_ids, st[0], st[1], t.P, t.M, t.V, t.G, t.n_users, opt.step_count, opt.lr,
-                             opt.weight_decay, t.loss, t.ws, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps,
-                             sync=sync)
-        return st[1]
+        return ctx.step(host_ids.data_ptr(), host_ids.shape[1], opt.step_count, wait)
 
     def sharded_train_step(self, user, pos, neg, B_global, lr, l2):
         from ... import sharded as S
