@@ -286,6 +286,12 @@ int wr_embloss_scatter_sharded(const wr_shards *host_T, const wr_shards *host_Gd
 int wr_gather_rows_sharded(const wr_shards *host_T, int which, const int64_t *idx, int64_t B, int D, float *out,
                            void *ws, void *stream);
 
+/* wr_allgather_shards: dst[g] = rank g's shard for every g != rank (dst: local [world, n_local, D] fp32), pulled over
+ * NVLink with one streaming kernel.  Together with a wr_shards whose base[g] points at dst[g] (and base[rank] at the own
+ * shard) this turns wr_csr_spmm_sharded into "all-gather, then SpMM against a local copy": on power-law graphs the
+ * neighbour rows are re-read many times, and only local memory gets those re-reads served by the L2. */
+int wr_allgather_shards(const wr_shards *host_src, float *dst, int D, void *stream);
+
 /* wr_csr_spmm_sharded: wr_csr_spmm for this rank's rows of the adjacency (local row l is node l * world + rank of
  * the user block for l < rows_u_local, else of the item block), column ids GLOBAL node ids; X rows are read from
  * their owners through host_X (the fused "all-gather of the layer output + SpMM": no gathered copy of X ever

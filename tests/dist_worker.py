@@ -188,34 +188,35 @@ def run_gpu():
             assert np.mean(host(got_tc[0]) != host(want_tc[0])) < 2e-3, 'sharded tensor-core ranks'
 
         # ---------------- LightGCN: L = 2 sharded steps against the oracle on the whole batch ----------------
-        L, reg = 2, 1e-5
-        rowptr, col, val = O.build_norm_adj_csr(nU, nI, pairs[:, 0], pairs[:, 1])
-        dinv = O.deg_inv_sqrt(np.diff(rowptr))
-        tabs2 = S.ShardedTables(peers, lay, D)
-        tabs2.load_full(d(U), d(I))
-        lg = S.ShardedLightGCN(tabs2, rowptr, col, dinv, L, reg)
-        A = O.csr_to_torch(rowptr, col, val, nU + nI)
-        oU, oI = torch.from_numpy(U.copy()), torch.from_numpy(I.copy())
-        om = [torch.zeros_like(oU), torch.zeros_like(oU), torch.zeros_like(oI), torch.zeros_like(oI)]
-        for step in range(1, 3):
-            sel = rng.randint(0, len(pairs), B)
-            user, pos, neg = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64), rng.randint(1, nI, B).astype(np.int64)
-            lo, hi = lay.batch_slice(B)
-            loss = lg.step(d(user[lo:hi]), d(pos[lo:hi]), d(neg[lo:hi]), B, 1e-3, 0.0)
-            o_loss, ogU, ogI = O.lightgcn_fwd_bwd(A, oU, oI, user, pos, neg, L, reg)
-            O.adam_l2_step(oU, om[0], om[1], ogU, step, 1e-3, 0.0)
-            O.adam_l2_step(oI, om[2], om[3], ogI, step, 1e-3, 0.0)
-            assert abs(float(loss[0]) - float(o_loss)) <= 1e-5 * abs(float(o_loss)), (float(loss[0]), float(o_loss))
-            gu, gi = tabs2.gather_full()
-            assert_close(host(gu), oU.numpy(), f'sharded LightGCN U step {step}', rtol=1e-4, atol_scale=1e-4)
-            assert_close(host(gi), oI.numpy(), f'sharded LightGCN I step {step}', rtol=1e-4, atol_scale=1e-4)
-            peers.barrier()
-        lg.propagate()
-        pu, pi = tabs2.gather_full(lg.pool_T)
-        o_pool = O.lightgcn_propagate(A, torch.cat([oU, oI]), L).numpy()
-        assert_close(host(pu), o_pool[:nU], 'sharded pooled users', rtol=1e-4, atol_scale=1e-4)
-        assert_close(host(pi), o_pool[nU:], 'sharded pooled items', rtol=1e-4, atol_scale=1e-4)
-        assert tabs2.ws.status() == 0
+        for gather_first in (False, True):     # neighbour rows read in place over NVLink / all-gathered first
+            L, reg = 2, 1e-5
+            rowptr, col, val = O.build_norm_adj_csr(nU, nI, pairs[:, 0], pairs[:, 1])
+            dinv = O.deg_inv_sqrt(np.diff(rowptr))
+            tabs2 = S.ShardedTables(peers, lay, D)
+            tabs2.load_full(d(U), d(I))
+            lg = S.ShardedLightGCN(tabs2, rowptr, col, dinv, L, reg, gather_first=gather_first)
+            A = O.csr_to_torch(rowptr, col, val, nU + nI)
+            oU, oI = torch.from_numpy(U.copy()), torch.from_numpy(I.copy())
+            om = [torch.zeros_like(oU), torch.zeros_like(oU), torch.zeros_like(oI), torch.zeros_like(oI)]
+            for step in range(1, 3):
+                sel = rng.randint(0, len(pairs), B)
+                user, pos, neg = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64), rng.randint(1, nI, B).astype(np.int64)
+                lo, hi = lay.batch_slice(B)
+                loss = lg.step(d(user[lo:hi]), d(pos[lo:hi]), d(neg[lo:hi]), B, 1e-3, 0.0)
+                o_loss, ogU, ogI = O.lightgcn_fwd_bwd(A, oU, oI, user, pos, neg, L, reg)
+                O.adam_l2_step(oU, om[0], om[1], ogU, step, 1e-3, 0.0)
+                O.adam_l2_step(oI, om[2], om[3], ogI, step, 1e-3, 0.0)
+                assert abs(float(loss[0]) - float(o_loss)) <= 1e-5 * abs(float(o_loss)), (float(loss[0]), float(o_loss))
+                gu, gi = tabs2.gather_full()
+                assert_close(host(gu), oU.numpy(), f'sharded LightGCN U step {step}', rtol=1e-4, atol_scale=1e-4)
+                assert_close(host(gi), oI.numpy(), f'sharded LightGCN I step {step}', rtol=1e-4, atol_scale=1e-4)
+                peers.barrier()
+            lg.propagate()
+            pu, pi = tabs2.gather_full(lg.pool_T)
+            o_pool = O.lightgcn_propagate(A, torch.cat([oU, oI]), L).numpy()
+            assert_close(host(pu), o_pool[:nU], 'sharded pooled users', rtol=1e-4, atol_scale=1e-4)
+            assert_close(host(pi), o_pool[nU:], 'sharded pooled items', rtol=1e-4, atol_scale=1e-4)
+            assert tabs2.ws.status() == 0
         peers.host_sync()
         if rank == 0:
             print(f'dist_worker gpu ok: world {world} nU {nU} nI {nI} D {D} B {B}')

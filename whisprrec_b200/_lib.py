@@ -58,6 +58,7 @@ SIGNATURES = {
     'wr_embloss_sumsq_sharded': (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _p]),
     'wr_embloss_scatter_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _p, _p, _p, _p]),
     'wr_gather_rows_sharded': (_int, [_p, _int, _p, _i64, _int, _p, _p, _p]),
+    'wr_allgather_shards': (_int, [_p, _p, _int, _p]),
     'wr_csr_spmm_sharded': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk_shard': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p,
                                        _p, _p, _p]),
@@ -460,6 +461,10 @@ def gather_rows_sharded(T, which, idx, D, ws, out=None):
     check(load().wr_gather_rows_sharded(ctypes.addressof(T), which, ptr(idx, I64), idx.numel(), D, ptr(out, F32),
                                         ws.ptr, stream_ptr()))
     return out
+
+
+def allgather_shards(src, dst, D):
+    check(load().wr_allgather_shards(ctypes.addressof(src), ptr(dst, F32), D, stream_ptr()))
 
 
 def csr_spmm_sharded(rowptr, col, val, n_local, D, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None,

@@ -70,6 +70,26 @@ __global__ void __launch_bounds__(256) gather_rows_sharded_kernel(wr_shards s, c
     }
 }
 
+// All-gather of a sharded table by PULL: every peer's shard is streamed over NVLink (128-bit loads, 8 in flight per
+// thread) into slot g of the local [world, n4] buffer; the own slot is skipped (readers use the shard in place).
+__global__ void __launch_bounds__(256) allgather_shards_kernel(wr_shards s, float4 *__restrict__ dst, int64_t n4) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int g0 = 1; g0 < s.world; ++g0) {
+        const int g = (s.rank + g0) % s.world;          // every rank starts with a different peer: links evenly loaded
+        const float4 *src = reinterpret_cast<const float4 *>(s.base[g]);
+        float4 *out = dst + (int64_t)g * n4;
+        int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < n4; i += 8 * stride) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcs(src + i + u * stride);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) out[i + u * stride] = v[u];
+        }
+        for (; i < n4; i += stride) out[i] = __ldcs(src + i);
+    }
+}
+
 __device__ __forceinline__ float bf16_rn(float x) {
     uint32_t u = __float_as_uint(x);
     if ((u & 0x7f800000u) == 0x7f800000u) return x;       // inf / nan unchanged
@@ -209,6 +229,22 @@ extern "C" int wr_gather_rows_sharded(const wr_shards *host_T, int which, const 
         gather_rows_sharded_kernel<0><<<(int)g, 256, 0, st>>>(*host_T, idx, B, D, out, (WrWorkspace *)ws);
     else
         gather_rows_sharded_kernel<1><<<(int)g, 256, 0, st>>>(*host_T, idx, B, D, out, (WrWorkspace *)ws);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_allgather_shards(const wr_shards *host_src, float *dst, int D, void *stream) {
+    if (!host_src || !dst) return WR_E_NULL;
+    const int rc = wr_check_shards(host_src);
+    if (rc) return rc;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(dst)) return WR_E_ALIGN;
+    if (host_src->world == 1) return WR_OK;
+    const int64_t n4 = (host_src->rows_u_local + host_src->rows_i_local) * (D / 4);
+    int64_t g = (n4 + 256 * 8 - 1) / (256 * 8);
+    if (g > 16 * kSMs) g = 16 * kSMs;
+    if (g < 1) g = 1;
+    allgather_shards_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(*host_src, reinterpret_cast<float4 *>(dst), n4);
     WR_CHECK_LAUNCH();
     return WR_OK;
 }

@@ -41,6 +41,87 @@ def build_norm_adj_csr(n_users, n_items, train_ptr, train_idx):
     return rowptr, col, dinv
 
 
+def build_norm_adj_device(n_users, n_items, users, items):
+    """The same CSR + weights built on the device from (user, item) id tensors (int64, distinct pairs): the graph
+    construction of LightGCN.py:54-97 for graphs the host builder cannot hold (10^8 - 10^9 edges).
+
+    Returns (rowptr int64 [N+1], col int32 [2E], val fp32 [2E], dinv fp32 [N]), columns ascending inside a row.
+    `dinv` uses torch's fp32 pow on the device; NumPy's (used for reference-exact small graphs) may differ in the last
+    bit, so parity tests against the reference go through build_norm_adj_csr."""
+    dev = users.device
+    U, I = int(n_users), int(n_items)
+    N = U + I
+    order = torch.argsort(users * I + items)                       # user-major, items ascending
+    u_sorted, i_sorted = users[order], items[order]
+    del order
+    order_i = torch.argsort(items * U + users)                     # item-major, users ascending
+    iu_sorted = users[order_i]
+    del order_i
+    deg = torch.cat([torch.bincount(users, minlength=U), torch.bincount(items, minlength=I)])
+    rowptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=rowptr[1:])
+    col = torch.cat([(U + i_sorted).to(torch.int32), iu_sorted.to(torch.int32)])
+    del u_sorted, i_sorted, iu_sorted
+    dinv = torch.pow(deg.to(torch.float32) + 1e-10, -0.5)
+    dinv[torch.isinf(dinv)] = 0.
+    val = torch.empty(col.numel(), dtype=torch.float32, device=dev)
+    _lib.csr_norm_weights(rowptr, col, dinv, val)
+    return rowptr, col, val, dinv
+
+
+class PropagationEngine(object):
+    """LightGCN on fused tables: adjacency (device CSR), layer / pool buffers, and the step built from wr_csr_spmm,
+    wr_bpr_fwd_bwd and wr_embloss_fwd_bwd.  Used by the model class below and by scripts/bench_lightgcn_scale.py."""
+
+    def __init__(self, tables, rowptr, col, val, rowptr_host, n_layers, reg_weight):
+        t = self.tables = tables
+        self.L, self.reg_weight = int(n_layers), float(reg_weight)
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.plan = _lib.SpmmPlan(rowptr_host, t.D, t.P.device)       # slices of the long (popular-item) rows
+        self.pool = torch.empty_like(t.P)            # mean_k E^k
+        self.layer = [torch.empty_like(t.P), torch.empty_like(t.P)]
+        self.pool_grad = torch.zeros_like(t.P)       # dL/d(pool); re-zeroed by the last backward SpMM
+
+    def propagate(self):
+        """LightGCN.py:134-148: L SpMMs with the running layer sum (and the final /(L+1)) in their epilogue."""
+        t, L = self.tables, self.L
+        if L == 0:
+            self.pool.copy_(t.P)
+            return
+        x = t.P
+        for k in range(1, L + 1):
+            y = self.layer[(k - 1) & 1]
+            _lib.csr_spmm(self.rowptr, self.col, self.val, x, Y=y if k < L else None,
+                          acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
+                          acc_div=float(L + 1) if k == L else 1.0, plan=self.plan)
+            x = y
+
+    def fwd_bwd(self, user, pos, neg, out):
+        """LightGCN.py:150-175 and its backward: propagate, BPR on pooled rows, adjoint propagation, EmbLoss.
+        The gradient lands in tables.G, the loss in out[0]."""
+        t, L = self.tables, self.L
+        self.propagate()
+        if L == 0:
+            _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws)
+        else:
+            g = self.pool_grad
+            _lib.bpr_fwd_bwd(t.users(self.pool), t.items(self.pool), user, pos, neg, t.users(g), t.items(g), out,
+                             t.ws, grad_scale=1.0 / (L + 1))
+            # pool = 1/(L+1) sum_k A^k E0 with A symmetric  =>  dE0 = H_0,  H_L = g,  H_{k-1} = g + A H_k
+            h = g
+            for k in range(1, L + 1):
+                last = k == L
+                y = t.G if last else self.layer[(k - 1) & 1]
+                # the fused re-zeroing of g is only safe when g is not also the SpMM input (L >= 2)
+                _lib.csr_spmm(self.rowptr, self.col, self.val, h, Y=y, add=g, zero_add=last and L > 1,
+                              plan=self.plan)
+                h = y
+            if L == 1:
+                g.zero_()
+        _lib.embloss_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws,
+                             self.reg_weight)
+
+
 class LightGCN(GeneralModel):
     reader = 'BaseReader'
     runner = 'BaseRunner'
@@ -78,11 +159,15 @@ class LightGCN(GeneralModel):
         self.adj_col = torch.from_numpy(col).to(dev)
         self.adj_val = torch.empty(len(col), dtype=torch.float32, device=dev)
         _lib.csr_norm_weights(self.adj_rowptr, self.adj_col, torch.from_numpy(dinv).to(dev), self.adj_val)
-        self.adj_plan = _lib.SpmmPlan(rowptr, t.D, dev)     # slices of the long (popular-item) rows
-        self.pool = torch.empty_like(t.P)            # mean_k E^k
-        self.layer = [torch.empty_like(t.P), torch.empty_like(t.P)]
-        self.pool_grad = torch.zeros_like(t.P)       # dL/d(pool); re-zeroed by the last backward SpMM
+        self.engine = PropagationEngine(t, self.adj_rowptr, self.adj_col, self.adj_val, rowptr, self.gcn_layers,
+                                        self.reg_weight)
         self._fresh = False
+
+    # buffers of the engine under the names the tests / bench use
+    adj_plan = property(lambda self: self.engine.plan)
+    pool = property(lambda self: self.engine.pool)
+    layer = property(lambda self: self.engine.layer)
+    pool_grad = property(lambda self: self.engine.pool_grad)
 
     @property
     def norm_adj(self):
@@ -95,19 +180,8 @@ class LightGCN(GeneralModel):
         return self.fuse().P
 
     def _propagate(self):
-        """LightGCN.py:134-148: L SpMMs with the running layer sum (and the final /(L+1)) in their epilogue."""
-        t = self.fuse()
-        L = self.gcn_layers
-        if L == 0:
-            self.pool.copy_(t.P)
-            return
-        x = t.P
-        for k in range(1, L + 1):
-            y = self.layer[(k - 1) & 1]
-            _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, x, Y=y if k < L else None,
-                          acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
-                          acc_div=float(L + 1) if k == L else 1.0, plan=self.adj_plan)
-            x = y
+        self.fuse()
+        self.engine.propagate()
 
     def forward(self):
         self._propagate()
@@ -115,31 +189,10 @@ class LightGCN(GeneralModel):
         return t.users(self.pool), t.items(self.pool)
 
     def predict(self, feed_dict, loss_out=None):
-        """LightGCN.py:150-175 and its backward: propagate, BPR on pooled rows, adjoint propagation, EmbLoss."""
+        """LightGCN.py:150-175 and its backward (PropagationEngine.fwd_bwd)."""
         t = self.fuse()
         out = t.loss if loss_out is None else loss_out
-        user, pos, neg = feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items']
-        L = self.gcn_layers
-        self._propagate()
-        if L == 0:
-            _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws)
-        else:
-            g = self.pool_grad
-            _lib.bpr_fwd_bwd(t.users(self.pool), t.items(self.pool), user, pos, neg, t.users(g), t.items(g), out,
-                             t.ws, grad_scale=1.0 / (L + 1))
-            # pool = 1/(L+1) sum_k A^k E0 with A symmetric  =>  dE0 = H_0,  H_L = g,  H_{k-1} = g + A H_k
-            h = g
-            for k in range(1, L + 1):
-                last = k == L
-                y = t.G if last else self.layer[(k - 1) & 1]
-                # the fused re-zeroing of g is only safe when g is not also the SpMM input (L >= 2)
-                _lib.csr_spmm(self.adj_rowptr, self.adj_col, self.adj_val, h, Y=y, add=g, zero_add=last and L > 1,
-                              plan=self.adj_plan)
-                h = y
-            if L == 1:
-                g.zero_()
-        _lib.embloss_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws,
-                             self.reg_weight)
+        self.engine.fwd_bwd(feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items'], out)
         return out[0].detach().as_subclass(_base.FusedLoss)
 
     def eval_tables(self):

@@ -269,29 +269,62 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
 class ShardedLightGCN(object):
     """LightGCN propagation state of one rank: its rows of the adjacency and the symmetric layer / pool buffers."""
 
-    def __init__(self, tabs, rowptr, col, dinv, n_layers, reg_weight):
+    def __init__(self, tabs, rowptr, col, dinv, n_layers, reg_weight, gather_first=None):
+        """rowptr / col / dinv: the GLOBAL node CSR structure and d^-1/2 (NumPy arrays or device tensors; every rank
+        passes the same).  The rank's rows are cut out on the device."""
         self.tabs, self.L, self.reg_weight = tabs, int(n_layers), float(reg_weight)
         lay, dev = tabs.layout, tabs.peers.device
-        lptr, lcol, _ = lay.local_adjacency(rowptr, col)
-        nodes = lay.local_nodes()
-        dinv_local = np.where(nodes >= 0, np.asarray(dinv)[np.maximum(nodes, 0)], 0).astype(np.float32)
-        self.rowptr = torch.from_numpy(lptr).to(dev)
-        self.col = torch.from_numpy(lcol if len(lcol) else np.zeros(1, np.int32)).to(dev)
-        # weights: fl32(fl32(dinv[row] * 1) * dinv[col]) -- LightGCN.py:89-97; dinv of a column comes from the full vector
-        d_full = torch.from_numpy(np.asarray(dinv, dtype=np.float32)).to(dev)
-        rows = torch.repeat_interleave(torch.arange(lay.n_local, device=dev), self.rowptr[1:] - self.rowptr[:-1])
-        self.val = (torch.from_numpy(dinv_local).to(dev)[rows] * 1.0) * d_full[self.col[:rows.numel()].long()]
-        if self.val.numel() == 0:
-            self.val = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.plan = _lib.SpmmPlan(lptr, tabs.D, dev)
+        as_dev = lambda a, dt: (a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))).to(dev).to(dt)
+        rowptr_d, col_d, dinv_d = as_dev(rowptr, torch.int64), as_dev(col, torch.int32), as_dev(dinv, torch.float32)
+        nodes = torch.from_numpy(lay.local_nodes()).to(dev)                  # -1 on padding rows
+        safe = nodes.clamp(min=0)
+        deg = torch.where(nodes >= 0, rowptr_d[safe + 1] - rowptr_d[safe], torch.zeros_like(safe))
+        lptr = torch.zeros(lay.n_local + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(deg, 0, out=lptr[1:])
+        total = int(lptr[-1].item())
+        rows = torch.repeat_interleave(torch.arange(lay.n_local, device=dev), deg)
+        src = rowptr_d[safe][rows] + (torch.arange(total, device=dev) - lptr[:-1][rows])
+        self.rowptr = lptr
+        self.col = col_d[src].contiguous() if total else torch.zeros(1, dtype=torch.int32, device=dev)
+        # weights: fl32(fl32(dinv[row] * 1) * dinv[col]) -- LightGCN.py:89-97
+        d_row = torch.where(nodes >= 0, dinv_d[safe], torch.zeros_like(dinv_d[safe]))
+        self.val = ((d_row[rows] * 1.0) * dinv_d[self.col[:total].long()]).contiguous() if total else \
+            torch.zeros(1, dtype=torch.float32, device=dev)
+        del rows, src
+        self.plan = _lib.SpmmPlan(lptr.cpu().numpy(), tabs.D, dev)
         self.pool, self.pool_T = tabs.symmetric()
         self.pool_grad, self.pool_Gd = tabs.symmetric()
         self.layer = [tabs.symmetric(), tabs.symmetric()]
         self.sumsq = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=dev)
+        # Neighbour rows: read in place from their owners (small tables: latency matters, the rows are few), or
+        # all-gathered into a local copy first (large power-law graphs: every neighbour row is re-read many times and
+        # only local memory has those re-reads served by the L2; peer reads always cross NVLink).
+        self.gather_first = (lay.world > 1 and total * 4 * tabs.D > (256 << 20)) if gather_first is None \
+            else bool(gather_first) and lay.world > 1
+        self.gathered = torch.empty((lay.world, lay.n_local, tabs.D), dtype=torch.float32, device=dev) \
+            if self.gather_first else None
+        self._local_views = {}
         tabs.peers.host_sync()
+
+    def _local_view(self, X):
+        """wr_shards whose peers' bases point into the gathered local copy (own shard read in place)."""
+        key = X.base[X.rank]
+        v = self._local_views.get(key)
+        if v is None:
+            v = _lib.ShardsStruct()
+            ctypes.memmove(ctypes.addressof(v), ctypes.addressof(X), ctypes.sizeof(v))
+            step = self.gathered[0].numel() * 4
+            for g in range(X.world):
+                if g != X.rank:
+                    v.base[g] = self.gathered.data_ptr() + g * step
+            self._local_views[key] = v
+        return v
 
     def _spmm(self, X, **kw):
         t = self.tabs
+        if self.gather_first:
+            _lib.allgather_shards(X, self.gathered, t.D)
+            X = self._local_view(X)
         _lib.csr_spmm_sharded(self.rowptr, self.col, self.val, t.layout.n_local, t.D, X, plan=self.plan, **kw)
         t.peers.barrier()          # every rank's rows of the output exist before anyone reads them as neighbours
 
