@@ -413,10 +413,84 @@ def run_ours_sharded(a, rank, world, local_rank):
                                              'adam_l2_sweep': float(seg[:, 2].mean()),
                                              'barrier_after_adam': float(seg[:, 3].mean())}},
     }
+    if not a.no_extras:
+        line['extra'] = extras_sharded(peers, dev, hbm_peak, flush)
     if rank == 0:
         emit(line)
     peers.close()
     dist.destroy_process_group()
+
+
+def extras_sharded(peers, dev, hbm_peak, flush):
+    """Secondary multi-GPU measurements: the HBM-bound BPRMF shape (10M x 2M, D=128) with the tables row-sharded, and
+    item-sharded tensor-core evaluation.  Every rank runs them; the numbers are rank 0's device times (max over ranks)."""
+    import torch.distributed as dist
+    from whisprrec_b200 import _lib, sharded as S
+    out = {}
+    world, rank = peers.world, peers.rank
+
+    def timed_max(fn, reps):
+        ms = []
+        for _ in range(reps):
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([float(np.median(ms))], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    try:
+        nU, nI, d, b = 10_000_000, 2_000_000, 128, 65536
+        lay = S.ShardLayout(nU, nI, world, rank)
+        tabs = S.ShardedTables(peers, lay, d)
+        tabs.P.normal_(0, 0.01)
+        peers.host_sync()
+        g = torch.Generator(device=dev); g.manual_seed(100 + rank)
+        u = torch.randint(0, nU, (b,), device=dev, generator=g)
+        p = torch.randint(0, nI, (b,), device=dev, generator=g)
+        n = torch.randint(1, nI, (b,), device=dev, generator=g)
+        step = lambda: S.bprmf_step(tabs, u, p, n, b * world, LR, L2)
+        step()
+        ms = timed_max(step, 5)
+        step_bytes = algorithmic_bytes_adam(lay.n_local, d) + algorithmic_bytes_bpr(b, d)
+        out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {
+            'ms_per_step': ms, 'interactions_per_s': b * world / (ms * 1e-3), 'rows_per_gpu': lay.n_local,
+            'algorithmic_gbs_per_gpu': step_bytes / (ms * 1e-3) / 1e9,
+            'frac_of_hbm_peak': step_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
+            'note': 'total table fixed (24.6 GB of state over all GPUs), batch 65536 per GPU; remote gathers / REDs over '
+                    'NVLink inside the BPR kernel, barrier, local Adam sweep, barrier'}
+        del tabs
+    except Exception as e:  # noqa: BLE001
+        out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {'error': repr(e)}
+    try:
+        _, tensor_peak, _ = peaks()
+        for d in (64, 128):
+            nUs, nIs, Rs = 200_000, 1_000_000, 262_144
+            lay = S.ShardLayout(nUs, nIs, world, rank)
+            tabs = S.ShardedTables(peers, lay, d)
+            g = torch.Generator(device=dev); g.manual_seed(3407 + rank)
+            tabs.P.copy_(torch.randn((lay.n_local, d), device=dev, generator=g) / d ** 0.5)
+            peers.host_sync()
+            g2 = torch.Generator(device=dev); g2.manual_seed(3407)
+            us = torch.randint(0, nUs, (Rs,), device=dev, generator=g2)
+            ps = torch.randint(0, nIs, (Rs,), device=dev, generator=g2)
+            hl = 50 // world + 1
+            hp_ = torch.arange(0, (nUs + 1) * hl, hl, device=dev, dtype=torch.int64)
+            n_loc_items = len(lay.local_items())
+            hi_ = torch.sort(torch.randint(0, n_loc_items, (nUs, hl), device=dev, generator=g2), dim=1).values \
+                .to(torch.int32).reshape(-1).contiguous()
+            fn = lambda: S.sharded_eval(tabs, tabs.T, tabs.item_rows(tabs.P), us, ps, (hp_, hi_), precision=1)
+            fn()
+            ms = timed_max(fn, 3)
+            tf = 2.0 * Rs * nIs * d / (ms * 1e-3) / 1e12
+            out['eval_tcgen05_item_sharded_262144x1M_d%d' % d] = {
+                'users_per_s': Rs / (ms * 1e-3), 'ms': ms, 'job_tflops': tf, 'tflops_per_gpu': tf / world,
+                'frac_of_bf16_peak_per_gpu': tf / world / tensor_peak}
+            del tabs
+    except Exception as e:  # noqa: BLE001
+        out['eval_tcgen05_item_sharded'] = {'error': repr(e)}
+    return out
 
 
 def cpu_problem(corpus):
