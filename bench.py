@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 B, D, LR, L2 = 2048, 64, 1e-3, 1e-6
 CACHE = os.environ.get('WR_CACHE', '/tmp/wr_cache')
-TRAFFIC_PER_LAUNCH = None      # dram bytes of one bprmf_step_kernel launch from `ncu --set full` (profiles/), once captured
+TRAFFIC_PER_LAUNCH = 10067456   # dram__bytes_read.sum + dram__bytes_write.sum of one bprmf_step_kernel launch (ncu --set full, profiles/r01_ncu_full_v2_step_and_eval_raw.csv); the 10 MB of writes leave L2 after the kernel
 WORKLOAD = 'BPRMF emb=64 B=2048 Adam(lr=1e-3,l2=1e-6) on ml-1m-shaped synthetic (6040 users x 3706 items, 668862 train rows)'
 
 
