@@ -196,6 +196,25 @@ int wr_gather_rows(const float *T, const int64_t *idx, int64_t B, int D, int64_t
 int wr_scatter_add_rows(float *G, const int64_t *idx, int64_t B, int D, int64_t n_rows, const float *rows,
                         void *ws, void *stream);
 
+/* ---- negative sampling on the device --------------------------------------------------
+ * wr_neg_sample_mt19937: GeneralModel.Dataset.actions_before_epoch (models/BaseModel.py:167-177) with num_neg = 1,
+ * bit-exact on NumPy's global legacy MT19937 stream: the bulk `randint(1, n_items, size=N)` followed, row by row, by
+ * scalar redraws while the candidate is in the user's train set.
+ *   host_key / pos:   the generator state, `np.random.get_state()[1:3]` (624 words, position 0..624)
+ *   user [N]:         int64 user id of every train row, in dataset order;  train_ptr / train_idx: CSR of the sorted
+ *                     train_clicked_set per user (int64 [n_users + 1] / int32)
+ *   neg_out [N]:      the epoch's negatives (int64)
+ *   host_key_out / host_pos_out: the state to hand back to `np.random.set_state` so the host stream continues exactly
+ *                     where the reference's would
+ * SYNCHRONISES the stream (the state goes back to the host).  Returns WR_E_SIZE if the scratch (sized by
+ * wr_neg_sample_scratch_bytes for ~15 % redraws) was too small for this draw: call again with a larger one.
+ */
+size_t wr_neg_sample_scratch_bytes(int64_t N, int64_t n_items);
+int wr_neg_sample_mt19937(const uint32_t *host_key, int pos, int64_t N, const int64_t *user, int64_t n_users,
+                          int64_t n_items, const int64_t *train_ptr, const int32_t *train_idx, int64_t *neg_out,
+                          uint32_t *host_key_out, int *host_pos_out, void *scratch, size_t scratch_bytes, void *ws,
+                          void *stream);
+
 /* ==== one 8 x B200 box: row-sharded tables over NVLink peer memory =====================
  * One process per GPU.  Every rank owns a slab of device memory (wr_peer_alloc), exports it (wr_peer_export),
  * and maps every other rank's slab (wr_peer_open): after that a kernel on any GPU can load, store and reduce into

@@ -44,6 +44,8 @@ SIGNATURES = {
     'wr_metrics': (_int, [_p, _i64, _c.POINTER(_int), _int, _p, _p, _p]),
     'wr_gather_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
     'wr_scatter_add_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
+    'wr_neg_sample_scratch_bytes': (_sz, [_i64, _i64]),
+    'wr_neg_sample_mt19937': (_int, [_p, _int, _i64, _p, _i64, _i64, _p, _p, _p, _p, _c.POINTER(_int), _p, _sz, _p, _p]),
     # ---- row-sharded tables over NVLink peer memory ----
     'wr_peer_alloc': (_int, [_sz, _c.POINTER(_p)]),
     'wr_peer_free': (_int, [_p]),
@@ -340,6 +342,33 @@ def gather_rows(T, idx, ws, out=None):
 def scatter_add_rows(G, idx, rows, ws):
     check(load().wr_scatter_add_rows(ptr(G, F32), ptr(idx, I64), idx.numel(), G.shape[1], G.shape[0],
                                      ptr(rows, F32), ws.ptr, stream_ptr()))
+
+
+def neg_sample_numpy_stream(user, n_users, n_items, train_ptr, train_idx, ws, scale=1):
+    """One epoch of negatives on the device, consuming NumPy's GLOBAL legacy generator exactly as
+    `np.random.randint` + the reference's redraw loop would (models/BaseModel.py:167-177); the global state is
+    advanced accordingly.  user: int64 [N] device tensor; train_ptr / train_idx: device CSR.  Returns int64 [N]."""
+    import numpy as np
+    lib = load()
+    N = user.numel()
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    if name != 'MT19937':
+        raise WhisprError('the global NumPy generator is not MT19937')
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    key_out = np.empty(624, dtype=np.uint32)
+    pos_out = _int(0)
+    neg = torch.empty(N, dtype=I64, device=user.device)
+    nbytes = lib.wr_neg_sample_scratch_bytes(N, n_items) * scale
+    scratch = torch.empty(nbytes + 16, dtype=torch.uint8, device=user.device)
+    off = (-scratch.data_ptr()) % 16
+    rc = lib.wr_neg_sample_mt19937(key.ctypes.data, int(pos), N, ptr(user, I64), n_users, n_items, ptr(train_ptr, I64),
+                                   ptr(train_idx, I32), ptr(neg, I64), key_out.ctypes.data, ctypes.byref(pos_out),
+                                   scratch.data_ptr() + off, nbytes, ws.ptr, stream_ptr())
+    if rc == -2 and scale < 8:          # WR_E_SIZE: an unusually rejection-heavy draw; nothing was consumed yet
+        return neg_sample_numpy_stream(user, n_users, n_items, train_ptr, train_idx, ws, scale * 2)
+    check(rc)
+    np.random.set_state((name, key_out, pos_out.value, has_gauss, cached))
+    return neg
 
 
 # ------------------------------------------------------------------------------------------------------

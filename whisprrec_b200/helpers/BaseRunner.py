@@ -170,6 +170,11 @@ class BaseRunner(object):
         dataset.actions_before_epoch()                       # BaseRunner.py:184 (must precede the loader draws)
         perm = dataloader_draws(len(dataset), shuffle=True)  # BaseRunner.py:188-193
         dev = model.tables.P.device
+        if getattr(dataset, 'neg_device', None) is not None:
+            # negatives were drawn on the device: only the permutation crosses the bus
+            user, item = dataset._device_cols(dev)[:2]
+            p = torch.from_numpy(perm).to(dev)
+            return torch.stack([user[p], item[p], dataset.neg_device[p]])
         cols = [dataset.data['user_id'], dataset.data['item_id'], dataset.data['neg_items']]
         host = torch.from_numpy(np.stack([np.asarray(c, dtype=np.int64)[perm] for c in cols]))
         return host.to(dev, non_blocking=False)

@@ -271,6 +271,19 @@ class GeneralModel(BaseModel):
                 neg_items = self.data['neg_items'][index]
             return {'user_id': user_id, 'pos_item': target_item, 'neg_items': neg_items}
 
+        def _device_cols(self, dev):
+            """(user, item) of every row and the train CSR as device tensors, uploaded once."""
+            c = getattr(self, '_dev_cols', None)
+            if c is None or c[0].device != dev:
+                ptr, idx = self.corpus.train_csr()
+                if len(idx) == 0:
+                    idx = np.zeros(1, dtype=np.int32)
+                c = self._dev_cols = (torch.from_numpy(np.asarray(self.data['user_id'], dtype=np.int64)).to(dev),
+                                      torch.from_numpy(np.asarray(self.data['item_id'], dtype=np.int64)).to(dev),
+                                      torch.from_numpy(np.ascontiguousarray(ptr, dtype=np.int64)).to(dev),
+                                      torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int32)).to(dev))
+            return c
+
         def actions_before_epoch(self):
             """BaseModel.py:167-177, bit-exact on NumPy's global stream.
 
@@ -280,6 +293,17 @@ class GeneralModel(BaseModel):
             membership test and only those are walked -- in the same order, with the same scalar calls.
             """
             n, num_neg, n_items = len(self), self.model.num_neg, int(self.corpus.n_items)
+            self.neg_device = None
+            t = getattr(self.model, 'tables', None)
+            if t is not None and num_neg == 1 and n_items >= 3 and getattr(self.model, 'device_sampler', True):
+                # the same draws on the device (wr_neg_sample_mt19937): NumPy's global state goes in and comes back
+                # advanced exactly as the host loop below would leave it
+                dev = t.P.device
+                cols = self._device_cols(dev)
+                self.neg_device = _lib.neg_sample_numpy_stream(cols[0], int(self.corpus.n_users), n_items, cols[2],
+                                                               cols[3], t.ws)
+                self.data['neg_items'] = self.neg_device.cpu().numpy()
+                return
             neg = np.random.randint(1, n_items, size=(n, num_neg))
             ptr, idx = self.corpus.train_csr()
             keys = np.repeat(np.arange(len(ptr) - 1, dtype=np.int64), np.diff(ptr)) * n_items + idx   # sorted
