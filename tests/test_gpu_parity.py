@@ -627,8 +627,9 @@ def test_compat_api_full_predict_and_interface():
 def test_ml100k_training_to_convergence_matches_reference_metrics(name, hr10, ndcg10):
     """BaseRunner.train (early stop on dev NDCG@10, checkpoint reload) then test HR@10 / NDCG@10.  Inputs (init,
     negatives, batch order) are bit-identical to the reference's; fp32 summation order is not, and ~100 epochs of Adam
-    amplify that, so the end metrics agree to about 1e-2 absolute (the reference's own README and re-run differ by
-    2.5e-3 in NDCG@10 for BPRMF)."""
+    could amplify that; measured on a B200 the runs stop at the reference's epochs (73 / 114, best 63 / 104) and the
+    test metrics equal the reference's to every printed digit (BPRMF) / four decimals (LightGCN, README.md:41).  The
+    bound below leaves room for the run-to-run order of the gradient REDs."""
     import importlib.util
     import os
     spec = importlib.util.spec_from_file_location(
@@ -637,8 +638,8 @@ def test_ml100k_training_to_convergence_matches_reference_metrics(name, hr10, nd
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     out = mod.train(name)
-    assert abs(out['test']['HR@10'] - hr10) < 1.2e-2, out
-    assert abs(out['test']['NDCG@10'] - ndcg10) < 8e-3, out
+    assert abs(out['test']['HR@10'] - hr10) < 3e-3, out
+    assert abs(out['test']['NDCG@10'] - ndcg10) < 3e-3, out
 
 
 # ---------------------------------------------------------------------------------------------------------
