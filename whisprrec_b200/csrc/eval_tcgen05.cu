@@ -30,6 +30,7 @@ struct TcParams {
     float *scores;              // optional dense [R, n_items] dump of the tensor-core scores (tests)
     int splits, tiles_per_split, n_tiles;
     int k;                      // top-k lists (TOPK instantiation only)
+    int top_trigger;
     int32_t *topk_idx;
     float *topk_val;
 };
@@ -364,6 +365,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         int cnt = 0;
         TopState top;
+        const int top_trigger = p.top_trigger;      // fold the buffers once any lane holds more than this many
         float tau = -INFINITY;
         int bcnt = 0, worst = 0;
         if (TOPK) {
@@ -425,7 +427,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             }
                         }
                     }
-                    if (__any_sync(0xffffffffu, bcnt > TC_TOPBUF - 32)) top_compact(top, p.k, bcnt, tau, worst);
+                    if (__any_sync(0xffffffffu, bcnt > top_trigger)) top_compact(top, p.k, bcnt, tau, worst);
                 }
                 if (m == 0) {
                     // fast path, 2 instructions per score.  VARIANT 0: FSETP + predicated integer add (both ALU pipe);
@@ -631,7 +633,8 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
     if (rc) return rc;
 
     TcParams p{user, pos, R, n_users, n_items, hist_ptr, hist_idx, target_in ? target_in : target, row_ok, rank,
-               scores_out, 1, 0, 0, k, topk_idx, topk_val};
+               scores_out, 1, 0, 0, k, k <= 16 ? 4 : 16, topk_idx, topk_val};    // small k: keep tau fresh
+    if (const char *e = getenv("WR_TC_TOP_TRIGGER")) p.top_trigger = atoi(e);     // tuning knob, <= TC_TOPBUF - 32
     p.n_tiles = (int)((n_items + TC_BN - 1) / TC_BN);
     const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
     if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
