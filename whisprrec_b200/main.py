@@ -160,6 +160,11 @@ def run(args, model_class, reader_class, runner_class, reader_name):
     logging.info(os.linesep + 'Test After Training: ' + eval_res)
     model.actions_after_train()
     logging.info(os.linesep + '-' * 45 + ' END: ' + utils.get_time() + ' ' + '-' * 45)
+    if peers is not None:
+        import torch.distributed as dist
+        model.unshard()                          # leave the full tables behind for whoever holds the model object
+        peers.host_sync()
+        dist.destroy_process_group()
     return model, runner, data_dict
 
 
