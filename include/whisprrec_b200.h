@@ -269,6 +269,22 @@ int wr_bpr_fwd_bwd_sharded(const wr_shards *host_T, const wr_shards *host_Gd, co
                            const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D, float gamma,
                            float grad_scale, float *loss_out, void *ws, void *stream);
 
+/* wr_bpr_fwd_bwd_sharded_staged + wr_inbox_scatter: the same for LARGE batches.  16-byte reductions over NVLink do not
+ * scale with the number of GPUs (each is its own fabric transaction; measured: 65,536 rows per GPU on 8 GPUs spend
+ * 4.5 ms in them), so remote gradient rows are written -- plain coalesced stores -- into the owner's inbox instead, slot
+ * 3 b + which of the sender's region (no counters, no atomics), with the owner-local row index + 1 beside them; local
+ * rows are still reduced in place.  After the barrier every owner folds its inbox into its gradient shard
+ * (wr_inbox_scatter, which also clears the slots).  host_inbox_rows[g] / host_inbox_idx[g]: rank g's
+ * [world][cap][D] fp32 / [world][cap] int32 (zero-initialised), cap >= 3 x the largest per-rank batch.
+ */
+int wr_bpr_fwd_bwd_sharded_staged(const wr_shards *host_T, const wr_shards *host_Gd,
+                                  float *const host_inbox_rows[WR_MAX_WORLD], int32_t *const host_inbox_idx[WR_MAX_WORLD],
+                                  int64_t cap, const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B,
+                                  int64_t B_global, int D, float gamma, float grad_scale, float *loss_out, void *ws,
+                                  void *stream);
+int wr_inbox_scatter(float *G, const float *inbox_rows, int32_t *inbox_idx, int world, int64_t cap, int D,
+                     void *stream);
+
 /* wr_bprmf_step_sharded: wr_bprmf_step on row-sharded tables -- ONE cooperative launch per rank and step, with the
  * two cross-GPU meeting points inside the kernel: (1) the grid barrier between the BPR phase and the Adam phase is
  * extended across the GPUs by CTA 0 (every rank's remote gradient REDs have landed, the loss shares are exchanged),

@@ -165,6 +165,30 @@ def run_gpu():
             peers.barrier()
         assert float(tabs.G.abs().max()) == 0.0 and tabs.ws.status() == 0
 
+        # ---------------- the multi-launch form with the staged (inbox) gradient scatter: large batches ----------------
+        if D == 128:
+            Bs = 16384
+            tabs3 = S.ShardedTables(peers, lay, D)
+            tabs3.load_full(d(U), d(I))
+            tabs3.single_launch = False                     # what shards too large for the cooperative step take
+            Pf3 = d(np.concatenate([U, I]))
+            Mf3, Vf3, Gf3 = torch.zeros_like(Pf3), torch.zeros_like(Pf3), torch.zeros_like(Pf3)
+            for step in range(1, 4):
+                sel = rng.randint(0, len(pairs), Bs)
+                user, pos, neg = pairs[sel, 0].astype(np.int64), pairs[sel, 1].astype(np.int64), rng.randint(1, nI, Bs).astype(np.int64)
+                lo, hi = lay.batch_slice(Bs)
+                loss = S.bprmf_step(tabs3, d(user[lo:hi]), d(pos[lo:hi]), d(neg[lo:hi]), Bs, 1e-3, 1e-6)
+                loss_v = float(loss[0])
+                _lib.bpr_fwd_bwd(Pf3[:nU], Pf3[nU:], d(user), d(pos), d(neg), Gf3[:nU], Gf3[nU:], lossf, ws)
+                _lib.adam_l2_sweep(Pf3, Mf3, Vf3, Gf3, step, 1e-3, 1e-6)
+                assert abs(loss_v - float(lossf[0])) <= 2e-6 * abs(float(lossf[0])), (loss_v, float(lossf[0]))
+                gu, gi = tabs3.gather_full()
+                assert_close(host(gu), host(Pf3[:nU]), f'staged scatter U step {step}', rtol=1e-5, atol_scale=2e-6)
+                assert_close(host(gi), host(Pf3[nU:]), f'staged scatter I step {step}', rtol=1e-5, atol_scale=2e-6)
+                peers.barrier()
+            assert getattr(tabs3, '_inbox', None) is not None and int(tabs3._inbox['idx'].abs().max()) == 0
+            assert float(tabs3.G.abs().max()) == 0.0 and tabs3.ws.status() == 0
+
         # ---------------- evaluation: items sharded, ranks / top-k equal the single-GPU kernel ----------------
         half = len(pairs) // 2
         hp, hi_ = O.history_csr(nU, pairs[:half], pairs[:1])

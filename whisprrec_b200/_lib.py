@@ -54,6 +54,8 @@ SIGNATURES = {
     'wr_peer_close': (_int, [_p]),
     'wr_peer_barrier': (_int, [_p, _int, _int, _c.c_uint32, _p, _p, _int, _p, _p]),
     'wr_bpr_fwd_bwd_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_bpr_fwd_bwd_sharded_staged': (_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_inbox_scatter': (_int, [_p, _p, _p, _int, _i64, _int, _p]),
     'wr_bprmf_step_sharded_supported': (_int, [_i64, _int]),
     'wr_bprmf_step_sharded': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _f64, _f64, _f32, _f32,
                                      _f32, _c.c_uint32, _p, _p, _p, _p, _p]),
@@ -451,6 +453,23 @@ def bpr_fwd_bwd_sharded(T, Gd, user, pos, neg, B_global, D, loss_out, ws, gamma=
     check(load().wr_bpr_fwd_bwd_sharded(ctypes.addressof(T), ctypes.addressof(Gd), ptr(user, I64), ptr(pos, I64),
                                         ptr(neg, I64), user.numel(), B_global, D, gamma, grad_scale,
                                         ptr(loss_out, F32), ws.ptr, stream_ptr()))
+
+
+def bpr_fwd_bwd_sharded_staged(T, Gd, inbox_row_ptrs, inbox_idx_ptrs, cap, user, pos, neg, B_global, D, loss_out, ws,
+                               gamma=1e-10, grad_scale=1.0):
+    world = T.world
+    FA = _p * MAX_WORLD
+    ra = FA(*(list(inbox_row_ptrs) + [None] * (MAX_WORLD - world)))
+    ia = FA(*(list(inbox_idx_ptrs) + [None] * (MAX_WORLD - world)))
+    check(load().wr_bpr_fwd_bwd_sharded_staged(ctypes.addressof(T), ctypes.addressof(Gd), ctypes.addressof(ra),
+                                               ctypes.addressof(ia), cap, ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
+                                               user.numel(), B_global, D, gamma, grad_scale, ptr(loss_out, F32), ws.ptr,
+                                               stream_ptr()))
+
+
+def inbox_scatter(G, inbox_rows, inbox_idx, world, cap):
+    check(load().wr_inbox_scatter(ptr(G, F32), ptr(inbox_rows, F32), ptr(inbox_idx, I32), world, cap, G.shape[1],
+                                  stream_ptr()))
 
 
 def bprmf_step_sharded_supported(n_local_rows, D):

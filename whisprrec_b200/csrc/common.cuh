@@ -119,6 +119,13 @@ struct LocalTabs {
     __device__ __forceinline__ const float *irow(int64_t i, int D) const { return I + i * D; }
     __device__ __forceinline__ float *gurow(int64_t u, int D) const { return gU + u * D; }
     __device__ __forceinline__ float *girow(int64_t i, int D) const { return gI + i * D; }
+    // gradient contribution `v` to floats [off, off+4) of a row; (b, which) name the batch row and its role
+    __device__ __forceinline__ void add_user(int64_t u, int D, int off, float4 v, int64_t, int) const {
+        red_add_v4(gU + u * D + off, v);
+    }
+    __device__ __forceinline__ void add_item(int64_t i, int D, int off, float4 v, int64_t, int) const {
+        red_add_v4(gI + i * D + off, v);
+    }
 };
 
 // user u -> rank u % world, local row u / world; item i -> rank i % world, local row rows_u_local + i / world.
@@ -141,6 +148,45 @@ struct ShardTabs {
     __device__ __forceinline__ const float *irow(int64_t i, int D) const { return shard_item_row(t, i, D); }
     __device__ __forceinline__ float *gurow(int64_t u, int D) const { return shard_user_row(g, u, D); }
     __device__ __forceinline__ float *girow(int64_t i, int D) const { return shard_item_row(g, i, D); }
+    __device__ __forceinline__ void add_user(int64_t u, int D, int off, float4 v, int64_t, int) const {
+        red_add_v4(shard_user_row(g, u, D) + off, v);       // remote rows: a reduction over NVLink per 16 bytes
+    }
+    __device__ __forceinline__ void add_item(int64_t i, int D, int off, float4 v, int64_t, int) const {
+        red_add_v4(shard_item_row(g, i, D) + off, v);
+    }
+};
+
+// Large batches: 16-byte reductions over NVLink do not scale (every one is its own fabric transaction).  Remote
+// gradient rows are instead WRITTEN (plain coalesced stores) into the owner's inbox -- slot 3 b + which of the
+// sender's region, no counters, no atomics -- together with the owner-local row index (+1; 0 = empty), and the owner
+// reduces its inbox into its gradient shard locally after the barrier (inbox_scatter_kernel).
+struct StageTabs {
+    wr_shards t, g;
+    float *inbox_rows[WR_MAX_WORLD];     // rank o's [world][cap][D]
+    int32_t *inbox_idx[WR_MAX_WORLD];    // rank o's [world][cap]
+    int64_t cap;                         // slots per sender (>= 3 x the largest per-rank batch)
+    __device__ __forceinline__ const float *urow(int64_t u, int D) const { return shard_user_row(t, u, D); }
+    __device__ __forceinline__ const float *irow(int64_t i, int D) const { return shard_item_row(t, i, D); }
+    __device__ __forceinline__ float *gurow(int64_t u, int D) const { return shard_user_row(g, u, D); }
+    __device__ __forceinline__ float *girow(int64_t i, int D) const { return shard_item_row(g, i, D); }
+    __device__ __forceinline__ void put(uint32_t owner, int64_t local_row, int D, int off, float4 v, int64_t b,
+                                        int which) const {
+        if ((int)owner == g.rank) {
+            red_add_v4(g.base[owner] + local_row * D + off, v);
+            return;
+        }
+        const int64_t slot = (int64_t)g.rank * cap + 3 * b + which;
+        *reinterpret_cast<float4 *>(inbox_rows[owner] + slot * D + off) = v;
+        if (off == 0) inbox_idx[owner][slot] = (int32_t)local_row + 1;
+    }
+    __device__ __forceinline__ void add_user(int64_t u, int D, int off, float4 v, int64_t b, int which) const {
+        const uint32_t q = (uint32_t)u / (uint32_t)g.world, r = (uint32_t)u - q * (uint32_t)g.world;
+        put(r, (int64_t)q, D, off, v, b, which);
+    }
+    __device__ __forceinline__ void add_item(int64_t i, int D, int off, float4 v, int64_t b, int which) const {
+        const uint32_t q = (uint32_t)i / (uint32_t)g.world, r = (uint32_t)i - q * (uint32_t)g.world;
+        put(r, g.rows_u_local + (int64_t)q, D, off, v, b, which);
+    }
 };
 
 }  // namespace wr

@@ -95,13 +95,12 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParamsT<TABS> p) {
             float l, c;
             bpr_pointwise(sp, sn, p.gamma, p.coef, l, c);
             if (sub == 0) local += l;
-            float *gu = p.tabs.gurow(u, D), *gp = p.tabs.girow(i, D), *gn = p.tabs.girow(j, D);
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
                 const int off = 4 * (sub + v * LPR);
-                red_add_v4(gu + off, scale4(sub4(pe[v], ne[v]), c));
-                red_add_v4(gp + off, scale4(ue[v], c));
-                red_add_v4(gn + off, scale4(ue[v], -c));
+                p.tabs.add_user(u, D, off, scale4(sub4(pe[v], ne[v]), c), b, 0);
+                p.tabs.add_item(i, D, off, scale4(ue[v], c), b, 1);
+                p.tabs.add_item(j, D, off, scale4(ue[v], -c), b, 2);
             }
         }
     }
@@ -678,6 +677,69 @@ extern "C" int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_
     embloss_sumsq_kernel<LocalTabs><<<grid, 256, 0, st>>>(p, D);
     WR_CHECK_LAUNCH();
     embloss_scatter_kernel<LocalTabs><<<grid, 256, 0, st>>>(p, D);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+// Reduce this rank's inbox into its gradient shard: for every sender s and slot j, idx = inbox_idx[s][j] (0 = empty),
+// G[idx - 1] += inbox_rows[s][j]; the slot is cleared for the next step.  One warp per slot, lanes over the row.
+__global__ void __launch_bounds__(256) inbox_scatter_kernel(float *G, const float *__restrict__ rows, int32_t *idx,
+                                                             int64_t n_slots, int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int D4 = D >> 2;
+    // lanes first look at 32 slots at once (most are empty: only 1/world of the senders' rows live here)
+    for (int64_t base = warp * 32; base < n_slots; base += nwarps * 32) {
+        const int64_t j = base + lane;
+        const int32_t mine = j < n_slots ? idx[j] : 0;
+        if (mine != 0) idx[j] = 0;
+        uint32_t live = __ballot_sync(0xffffffffu, mine != 0);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            const int64_t row = (int64_t)__shfl_sync(0xffffffffu, mine, src) - 1;
+            const float *r = rows + (base + src) * D;
+            for (int v = lane; v < D4; v += 32) red_add_v4(G + row * D + 4 * v, ldg4(r + 4 * v));
+        }
+    }
+}
+
+extern "C" int wr_bpr_fwd_bwd_sharded_staged(const wr_shards *host_T, const wr_shards *host_Gd,
+                                             float *const host_inbox_rows[WR_MAX_WORLD],
+                                             int32_t *const host_inbox_idx[WR_MAX_WORLD], int64_t cap,
+                                             const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B,
+                                             int64_t B_global, int D, float gamma, float grad_scale, float *loss_out,
+                                             void *ws, void *stream) {
+    if (!host_T || !host_Gd || !host_inbox_rows || !host_inbox_idx || !user || !pos || !neg || !loss_out || !ws)
+        return WR_E_NULL;
+    int rc = wr_check_shards(host_T);
+    if (rc) return rc;
+    rc = wr_check_shards(host_Gd);
+    if (rc) return rc;
+    if (B <= 0 || B_global < B || cap < 3 * B) return WR_E_SIZE;
+    if (!(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return WR_E_DIM;
+    BprParamsT<StageTabs> p{{*host_T, *host_Gd, {}, {}, cap}, user, pos, neg, B, host_T->n_users, host_T->n_items,
+                            gamma, grad_scale / (float)B_global, (float)B_global, loss_out, 0, (WrWorkspace *)ws};
+    for (int g = 0; g < host_T->world; ++g) {
+        if (!host_inbox_rows[g] || !host_inbox_idx[g]) return WR_E_NULL;
+        if (!wr_aligned16(host_inbox_rows[g])) return WR_E_ALIGN;
+        p.tabs.inbox_rows[g] = host_inbox_rows[g];
+        p.tabs.inbox_idx[g] = host_inbox_idx[g];
+    }
+    return launch_bpr(p, D, (cudaStream_t)stream);
+}
+
+extern "C" int wr_inbox_scatter(float *G, const float *inbox_rows, int32_t *inbox_idx, int world, int64_t cap, int D,
+                                void *stream) {
+    if (!G || !inbox_rows || !inbox_idx) return WR_E_NULL;
+    if (world < 1 || world > WR_MAX_WORLD || cap <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(G) || !wr_aligned16(inbox_rows)) return WR_E_ALIGN;
+    const int64_t n_slots = (int64_t)world * cap;
+    int64_t g = (n_slots + 255) / 256;
+    if (g > 16 * kSMs) g = 16 * kSMs;
+    inbox_scatter_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(G, inbox_rows, inbox_idx, n_slots, D);
     WR_CHECK_LAUNCH();
     return WR_OK;
 }

@@ -207,6 +207,18 @@ class ShardedTables(object):
         self.single_launch = _lib.bprmf_step_sharded_supported(layout.n_local, self.D)
         self._sync_epoch = 0           # last epoch the single-launch step has used on this table set
 
+    def inbox(self, B_global):
+        """Symmetric gradient inbox for the staged scatter: per sender 3 x (largest per-rank batch) row slots."""
+        lay = self.layout
+        cap = 3 * ((int(B_global) + lay.world - 1) // lay.world)
+        box = getattr(self, '_inbox', None)
+        if box is None or box['cap'] < cap:
+            rows, row_ptrs = self.peers.alloc((lay.world, cap, self.D))
+            idx, idx_ptrs = self.peers.alloc((lay.world, cap), dtype=torch.int32)
+            box = self._inbox = {'cap': cap, 'rows': rows, 'idx': idx, 'row_ptrs': row_ptrs, 'idx_ptrs': idx_ptrs}
+            self.peers.host_sync()
+        return box
+
     def symmetric(self):
         """A zeroed [n_local, D] fp32 table on every rank -> (local tensor, wr_shards describing all of them)."""
         lay = self.layout
@@ -259,8 +271,18 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
                                 lr, l2, tabs.step_flag_ptrs, tabs.step_slot_ptrs, tabs.loss, tabs.ws,
                                 epoch=tabs._sync_epoch)
         return tabs.loss
-    _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
+    B = user.numel()
+    staged = tabs.layout.world > 1 and B >= 8192 and tabs.D in (16, 32, 64, 128, 256)
+    if staged:
+        # large batches: remote gradient rows are written into the owners' inboxes and reduced there after the barrier
+        inbox = tabs.inbox(B_global)
+        _lib.bpr_fwd_bwd_sharded_staged(tabs.T, tabs.Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'], user, pos,
+                                        neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
+    else:
+        _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
     loss = tabs.peers.barrier(tabs.loss_part[:1])
+    if staged:
+        _lib.inbox_scatter(tabs.G, inbox['rows'], inbox['idx'], tabs.layout.world, inbox['cap'])
     tabs.adam(lr, l2)
     tabs.peers.barrier()
     return loss
