@@ -458,8 +458,9 @@ def extras_sharded(peers, dev, hbm_peak, flush):
             'ms_per_step': ms, 'interactions_per_s': b * world / (ms * 1e-3), 'rows_per_gpu': lay.n_local,
             'algorithmic_gbs_per_gpu': step_bytes / (ms * 1e-3) / 1e9,
             'frac_of_hbm_peak': step_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
-            'note': 'total table fixed (24.6 GB of state over all GPUs), batch 65536 per GPU; remote gathers / REDs over '
-                    'NVLink inside the BPR kernel, barrier, local Adam sweep, barrier'}
+            'note': 'total table fixed (24.6 GB of state over all GPUs), batch 65536 per GPU; remote gathers over NVLink and '
+                    'remote gradient rows written into the owners\' inboxes inside the BPR kernel, barrier, local inbox '
+                    'reduction, local Adam sweep, barrier'}
         del tabs
     except Exception as e:  # noqa: BLE001
         out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {'error': repr(e)}
