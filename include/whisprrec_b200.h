@@ -39,6 +39,9 @@ extern "C" {
 
 /* bits of the device-side status word (wr_status) */
 #define WR_STATUS_INDEX_OUT_OF_RANGE 1u /* an id outside its table: the row was skipped (torch raises IndexError) */
+#define WR_STATUS_PEER_TIMEOUT 2u       /* a cross-GPU wait gave up after WR_PEER_TIMEOUT_NS: a peer never arrived
+                                           (crashed or out of step); results of that step are invalid */
+#define WR_PEER_TIMEOUT_NS 20000000000ull
 
 int wr_version(void);
 const char *wr_error_string(int code);
@@ -253,11 +256,13 @@ int wr_peer_close(void *dev_ptr);
  * rank order (deterministic, identical on every rank).  host_slots[g]: rank g's array of 2 * WR_MAX_WORLD *
  * WR_PEER_VALUES floats (double-buffered by epoch parity).
  * The ranks MUST run on different GPUs (a spin-wait between processes sharing one GPU can deadlock the device).
+ * Every cross-GPU wait (here and inside wr_bprmf_step_sharded) gives up after WR_PEER_TIMEOUT_NS and raises
+ * WR_STATUS_PEER_TIMEOUT in the workspace status word instead of hanging the GPU when a peer has died.
  */
 #define WR_PEER_VALUES 4
 int wr_peer_barrier(uint32_t *const host_flags[WR_MAX_WORLD], int world, int rank, uint32_t epoch,
                     float *const host_slots[WR_MAX_WORLD], const float *values_in, int n_values, float *sums_out,
-                    void *stream);
+                    void *ws /* nullable: receives WR_STATUS_PEER_TIMEOUT */, void *stream);
 
 /* wr_bpr_fwd_bwd_sharded: wr_bpr_fwd_bwd on this rank's slice of the global batch against sharded tables.
  * T: the embedding shards read (P for BPRMF, the pooled table for LightGCN); Gd: the gradient shards reduced into

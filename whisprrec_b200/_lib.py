@@ -52,7 +52,7 @@ SIGNATURES = {
     'wr_peer_export': (_int, [_p, _c.c_char_p]),
     'wr_peer_open': (_int, [_c.c_char_p, _c.POINTER(_p)]),
     'wr_peer_close': (_int, [_p]),
-    'wr_peer_barrier': (_int, [_p, _int, _int, _c.c_uint32, _p, _p, _int, _p, _p]),
+    'wr_peer_barrier': (_int, [_p, _int, _int, _c.c_uint32, _p, _p, _int, _p, _p, _p]),
     'wr_bpr_fwd_bwd_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
     'wr_bpr_fwd_bwd_sharded_staged': (_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
     'wr_inbox_scatter': (_int, [_p, _p, _p, _int, _i64, _int, _p]),
@@ -146,6 +146,8 @@ class Workspace:
 
     def raise_on_status(self):
         st = self.status()
+        if st & 2:
+            raise WhisprError('a cross-GPU wait timed out: a peer rank died or fell out of step')
         if st & 1:
             raise IndexError('index out of range in self')      # what nn.Embedding raises in the reference
 
@@ -439,14 +441,14 @@ class PeerBlock:
                 self.ptr = None
 
 
-def peer_barrier(flag_ptrs, slot_ptrs, world, rank, epoch, values_in=None, sums_out=None):
+def peer_barrier(flag_ptrs, slot_ptrs, world, rank, epoch, values_in=None, sums_out=None, ws=None):
     """flag_ptrs / slot_ptrs: lists of `world` raw device pointers (every rank's flag / slot array as mapped here)."""
     FA = _p * MAX_WORLD
     fa = FA(*(list(flag_ptrs) + [None] * (MAX_WORLD - world)))
     sa = FA(*(list(slot_ptrs) + [None] * (MAX_WORLD - world)))
     n = 0 if values_in is None else values_in.numel()
     check(load().wr_peer_barrier(ctypes.addressof(fa), world, rank, epoch, ctypes.addressof(sa), ptr(values_in, F32), n,
-                                 ptr(sums_out, F32), stream_ptr()))
+                                 ptr(sums_out, F32), None if ws is None else ws.ptr, stream_ptr()))
 
 
 def bpr_fwd_bwd_sharded(T, Gd, user, pos, neg, B_global, D, loss_out, ws, gamma=1e-10, grad_scale=1.0):

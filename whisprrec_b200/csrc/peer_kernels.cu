@@ -33,7 +33,7 @@ __device__ __forceinline__ float ld_relaxed_sys_f32(const float *p) {
 // rank's flag array (release at system scope: the stream's earlier kernels have completed, so their peer writes are
 // ordered before it), then wait until every rank's arrival for this epoch is visible here.
 __global__ void peer_barrier_kernel(PeerPtrs pp, int world, int rank, uint32_t epoch, const float *values_in,
-                                    int n_values, float *sums_out) {
+                                    int n_values, float *sums_out, uint32_t *status) {
     const int g = threadIdx.x;
     const int half = (int)(epoch & 1u) * WR_MAX_WORLD * WR_PEER_VALUES;
     if (g < world) {
@@ -42,7 +42,13 @@ __global__ void peer_barrier_kernel(PeerPtrs pp, int world, int rank, uint32_t e
         __threadfence_system();
         st_release_sys_u32(pp.flags[g] + rank, epoch);
         // arrivals are monotonic: a rank that is already one epoch ahead has passed this one
-        while ((int32_t)(ld_acquire_sys_u32(pp.flags[rank] + g) - epoch) < 0) {}
+        const uint64_t t0 = global_timer_ns();
+        while ((int32_t)(ld_acquire_sys_u32(pp.flags[rank] + g) - epoch) < 0) {
+            if (global_timer_ns() - t0 > WR_PEER_TIMEOUT_NS) {      // the peer is gone: do not hang the GPU
+                if (status) atomicOr(status, WR_STATUS_PEER_TIMEOUT);
+                break;
+            }
+        }
     }
     __syncthreads();
     if (g < n_values) {
@@ -197,7 +203,7 @@ extern "C" int wr_peer_close(void *dev_ptr) { return dev_ptr ? (int)cudaIpcClose
 
 extern "C" int wr_peer_barrier(uint32_t *const host_flags[WR_MAX_WORLD], int world, int rank, uint32_t epoch,
                                float *const host_slots[WR_MAX_WORLD], const float *values_in, int n_values,
-                               float *sums_out, void *stream) {
+                               float *sums_out, void *ws, void *stream) {
     if (!host_flags) return WR_E_NULL;
     if (world < 1 || world > WR_MAX_WORLD || rank < 0 || rank >= world || epoch == 0) return WR_E_SIZE;
     if (n_values < 0 || n_values > WR_PEER_VALUES) return WR_E_SIZE;
@@ -208,7 +214,8 @@ extern "C" int wr_peer_barrier(uint32_t *const host_flags[WR_MAX_WORLD], int wor
         pp.flags[g] = host_flags[g];
         pp.slots[g] = n_values > 0 ? host_slots[g] : nullptr;
     }
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, values_in, n_values, sums_out);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pp, world, rank, epoch, values_in, n_values, sums_out,
+                                                            reinterpret_cast<uint32_t *>(ws));
     WR_CHECK_LAUNCH();
     return WR_OK;
 }

@@ -423,8 +423,15 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
     }
     if (sy.world > 1) {
         // remote rows may be gathered only once their owners have finished the previous step's Adam
-        if (threadIdx.x < sy.world)
-            while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + WR_MAX_WORLD + threadIdx.x) - (sy.epoch - 1u)) < 0) {}
+        if (threadIdx.x < sy.world) {
+            const uint64_t t0 = global_timer_ns();
+            while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + WR_MAX_WORLD + threadIdx.x) - (sy.epoch - 1u)) < 0) {
+                if (global_timer_ns() - t0 > WR_PEER_TIMEOUT_NS) {
+                    atomicOr(&p.ws->status, WR_STATUS_PEER_TIMEOUT);
+                    break;
+                }
+            }
+        }
         __syncthreads();
     }
     // ---- phase 1: BPR forward + backward; consecutive interaction groups go to different CTAs ----
@@ -506,7 +513,13 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
                 asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(sy.slots[g] + half + sy.rank), "f"(loss_sum) : "memory");
                 __threadfence_system();
                 st_release_sys(sy.flags[g] + sy.rank, sy.epoch);
-                while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + g) - sy.epoch) < 0) {}
+                const uint64_t t0 = global_timer_ns();
+                while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + g) - sy.epoch) < 0) {
+                    if (global_timer_ns() - t0 > WR_PEER_TIMEOUT_NS) {      // the peer is gone: do not hang the GPU
+                        atomicOr(&p.ws->status, WR_STATUS_PEER_TIMEOUT);
+                        break;
+                    }
+                }
             }
             __syncthreads();
             if (threadIdx.x == 0) {

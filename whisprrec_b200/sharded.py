@@ -142,6 +142,7 @@ class PeerGroup(object):
         self._sig, self._sig_ptrs = self.alloc_bytes((sig_bytes + 255) // 256 * 256)
         self.flag_ptrs = list(self._sig_ptrs)
         self.slot_ptrs = [p + 4 * _lib.MAX_WORLD for p in self._sig_ptrs]
+        self.ws = _lib.Workspace(self.device)      # receives WR_STATUS_PEER_TIMEOUT if a peer never arrives
         self._values = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=self.device)
         self.sums = torch.zeros(_lib.PEER_VALUES, dtype=torch.float32, device=self.device)
         self.host_sync()
@@ -173,14 +174,16 @@ class PeerGroup(object):
         of the result, valid until the next barrier with values)."""
         self.epoch += 1
         if values is None:
-            _lib.peer_barrier(self.flag_ptrs, self.slot_ptrs, self.world, self.rank, self.epoch)
+            _lib.peer_barrier(self.flag_ptrs, self.slot_ptrs, self.world, self.rank, self.epoch, ws=self.ws)
             return None
         n = values.numel()
-        _lib.peer_barrier(self.flag_ptrs, self.slot_ptrs, self.world, self.rank, self.epoch, values, self.sums[:n])
+        _lib.peer_barrier(self.flag_ptrs, self.slot_ptrs, self.world, self.rank, self.epoch, values, self.sums[:n],
+                          ws=self.ws)
         return self.sums[:n]
 
     def close(self):
         self.host_sync()
+        self.ws.raise_on_status()
         for b in self._blocks:
             b.close()
         self._blocks = []
