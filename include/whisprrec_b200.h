@@ -96,6 +96,14 @@ int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, c
                   double beta1, double beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
                   float *loss_out, void *ws, void *stream);
 
+/* wr_bprmf_epoch: the step loop of BaseRunner.fit (BaseRunner.py:194-200) in one call: batch s is columns
+ * [s * batch, min(N, (s + 1) * batch)) of ids[3][N] (DEVICE, rows user / pos / neg), Adam's t runs from adam_t0 + 1,
+ * losses[s] (DEVICE, ceil(N / batch) floats) receives the loss of step s.  Launches only; nothing is synchronised.
+ */
+int wr_bprmf_epoch(float *P, float *M, float *V, float *G, const int64_t *ids, int64_t N, int64_t batch, int D,
+                   int64_t n_users, int64_t n_items, float gamma, double lr, float l2, double beta1, double beta2,
+                   float eps, int64_t adam_t0, float *losses, void *ws, void *stream);
+
 /* wr_bprmf_step_host: the same iteration fed from the HOST, i.e. utils.batch_to_gpu (utils/utils.py:33-37) +
  * the step + `loss.detach().cpu()` (BaseRunner.py:200).  host_ids: pinned [3, B] int64 (user, pos, neg rows);
  * dev_ids: device staging of the same shape; host_loss: pinned float that receives the batch loss.

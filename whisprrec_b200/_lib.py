@@ -30,6 +30,8 @@ SIGNATURES = {
     'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f64, _f64, _f32, _f32, _f32, _p, _p]),
     'wr_bprmf_step': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32, _f32,
                              _f32, _p, _p, _p, _p]),
+    'wr_bprmf_epoch': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _f32, _f64, _f32, _f64, _f64, _f32, _i64,
+                              _p, _p, _p]),
     'wr_bprmf_step_host': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32,
                                   _f32, _f32, _p, _p, _p, _int]),
     'wr_bprmf_ctx_create': (_int, [_p, _p, _p, _p, _i64, _i64, _int, _f32, _f64, _f32, _f64, _f64, _f32, _p, _p,
@@ -192,6 +194,18 @@ def bprmf_step(P, M, V, G, user, pos, neg, n_users, step, lr, l2, loss_out, ws, 
                                ptr(neg, I64), user.numel(), P.shape[1], n_users, P.shape[0] - n_users, gamma, l2,
                                beta1, beta2, eps, ss, bc2s, ptr(dev_scalars, F32), ptr(loss_out, F32), ws.ptr,
                                stream_ptr()))
+
+
+def bprmf_epoch(P, M, V, G, ids, batch, n_users, adam_t0, lr, l2, losses, ws, beta1=0.9, beta2=0.999, eps=1e-8,
+                gamma=1e-10):
+    """Every step of an epoch from one call; ids: contiguous int64 [3, N] device tensor in batch order."""
+    N = ids.shape[1]
+    if ids.dim() != 2 or ids.shape[0] != 3 or losses.numel() < (N + batch - 1) // batch:
+        raise WhisprError('ids must be [3, N] and losses hold one float per step')
+    check(load().wr_bprmf_epoch(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), ptr(ids, I64), N, batch, P.shape[1],
+                                n_users, P.shape[0] - n_users, gamma, lr, l2, beta1, beta2, eps, adam_t0,
+                                ptr(losses, F32), ws.ptr, stream_ptr()))
+    return (N + batch - 1) // batch
 
 
 def bprmf_step_host(host_ids, dev_ids, host_loss, P, M, V, G, n_users, step, lr, l2, loss_out, ws, beta1=0.9,

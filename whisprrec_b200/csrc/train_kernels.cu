@@ -953,6 +953,27 @@ extern "C" int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, flo
     return (int)e;
 }
 
+// A whole epoch of BPRMF steps launched from one call (BaseRunner.fit's loop, BaseRunner.py:194-200): batches are
+// consecutive column slices of ids[3][N] (device), the last one ragged; losses[s] receives the loss of step s.
+extern "C" int wr_bprmf_epoch(float *P, float *M, float *V, float *G, const int64_t *ids, int64_t N, int64_t batch,
+                              int D, int64_t n_users, int64_t n_items, float gamma, double lr, float l2, double beta1,
+                              double beta2, float eps, int64_t adam_t0, float *losses, void *ws, void *stream) {
+    if (!ids || !losses) return WR_E_NULL;
+    if (N <= 0 || batch <= 0 || adam_t0 < 0) return WR_E_SIZE;
+    int64_t s = 0;
+    for (int64_t lo = 0; lo < N; lo += batch, ++s) {
+        const int64_t B = N - lo < batch ? N - lo : batch;
+        const double t = (double)(adam_t0 + s + 1);
+        // torch/optim/adam.py evaluates these in Python floats (C doubles, libm pow): the same calls here
+        const float step_size = (float)(lr / (1.0 - pow(beta1, t)));
+        const float bc2_sqrt = (float)pow(1.0 - pow(beta2, t), 0.5);
+        const int rc = wr_bprmf_step(P, M, V, G, ids + lo, ids + N + lo, ids + 2 * N + lo, B, D, n_users, n_items, gamma,
+                                     l2, beta1, beta2, eps, step_size, bc2_sqrt, nullptr, losses + s, ws, stream);
+        if (rc) return rc;
+    }
+    return WR_OK;
+}
+
 // ---- host-fed step with no copy engine and no stream synchronisation in the loop ----------------------------------
 struct wr_bprmf_ctx {
     float *P, *M, *V, *G;

@@ -197,6 +197,9 @@ class BaseRunner(object):
         fused_step = hasattr(model, 'train_step')
         if model.sharded is not None:
             return self._fit_sharded(model, batches, starts, losses, t0, t1)
+        if hasattr(model, 'train_epoch'):
+            model.train_epoch(batches.contiguous(), self.batch_size, losses)      # the whole step loop in one C call
+            starts = []
         for s, lo in enumerate(starts):
             hi = min(n, lo + self.batch_size)
             batch = {'user_id': batches[0, lo:hi], 'pos_item': batches[1, lo:hi], 'neg_items': batches[2, lo:hi],
@@ -210,7 +213,7 @@ class BaseRunner(object):
             model.optimizer.step()
         loss_host = losses.cpu().numpy()                    # one sync per epoch
         model.tables.ws.raise_on_status()
-        self.last_epoch_stats = {'host_prep_s': t1 - t0, 'device_s': time() - t1, 'steps': len(starts), 'rows': n}
+        self.last_epoch_stats = {'host_prep_s': t1 - t0, 'device_s': time() - t1, 'steps': len(loss_host), 'rows': n}
         return np.mean(loss_host).item()
 
     def _fit_sharded(self, model, batches, starts, losses, t0, t1):

@@ -65,6 +65,16 @@ class BPRMF(GeneralModel):
                         beta2=opt.betas[1], eps=opt.eps)
         return out[0].detach().as_subclass(_base.FusedLoss)
 
+    def train_epoch(self, ids, batch_size, losses):
+        """All steps of an epoch (BaseRunner.py:194-200 for every batch) from one C call; `ids` is the epoch's int64
+        [3, N] device tensor in batch order, `losses` a device float per step."""
+        t = self.fuse()
+        opt = self.optimizer
+        steps = _lib.bprmf_epoch(t.P, t.M, t.V, t.G, ids, batch_size, t.n_users, opt.step_count, opt.lr,
+                                 opt.weight_decay, losses, t.ws, beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps)
+        opt.step_count += steps
+        return steps
+
     def train_step_host(self, host_ids, wait=1):
         """The same iteration fed from the host: `host_ids` is a pinned int64 [3, B] tensor holding the batch's
         user / positive / negative ids (what collate_batch produces, BaseModel.py:96-127).  Covers
