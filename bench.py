@@ -3,19 +3,23 @@
 
     python bench.py --gpus 1 --steps 200 --warmup 10          # this repository's sm_100a path
     python bench.py --impl reference --steps 20 --warmup 3    # the reference's CPU path (oracle port) on host cores
-    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, NCCL
+    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, tables row-sharded over NVLink
 
 Workload (config.workload): BPRMF, embedding 64, batch 2048, Adam lr=1e-3 l2=1e-6 on the ml-1m-SHAPED synthetic
 corpus (6,040 users x 3,706 items, 836k interactions after the reader's rating filter, 668,862 train rows):
 `ml-1m.inter` is missing from the reference checkout and there is no network.
-A step = one mini-batch through the whole training path: gather + BPR loss + backward scatter (wr_bpr_fwd_bwd)
-and the dense Adam+L2 sweep over every table row (wr_adam_l2_sweep).
+A step = one mini-batch through the whole training path (gather + BPR loss + backward scatter + dense Adam/L2 sweep
+over every table row): ONE cooperative launch, wr_bprmf_step (wr_bprmf_step_sharded per rank for N > 1, with 2048
+rows per GPU and the cross-GPU synchronisation inside the kernel).
 
 value    : interactions/s with the epoch's batches already resident in HBM, device-timed (CUDA events around every
-           step, L2 flushed between steps by writing a 512 MB buffer, outside the events).
-e2e      : the same through the reference-facing API (model.predict / optimizer.step) with HOST batches: per
-           step a pinned H2D copy of the three id vectors and a D2H read of the loss, host-timed, same L2 flush.
-roofline : the Adam sweep (the dominant kernel: 32 B per parameter per step) against the measured HBM copy peak.
+           step, L2 flushed between steps by writing a 512 MB buffer, outside the events), max over ranks.
+e2e      : the same through the reference-facing API with HOST batches -- model.train_step_host -> wr_bprmf_ctx_step:
+           the kernel reads the step's ids from pinned (mapped) host memory and delivers the loss to mapped host memory;
+           the call returns when the whole step is complete.  Host-timed, same L2 flush.
+roofline : the step kernel's algorithmic bytes (24 B D + 24 B + 32 D (U + I)) over its event-timed
+           duration against the measured HBM copy peak; `traffic` = its DRAM bytes from ncu.
+extra    : epoch-level fit, eval (fp32 / tcgen05), LightGCN step, the HBM-bound 10M x 2M shape; multi-GPU extras.
 """
 import argparse
 import json
