@@ -151,6 +151,29 @@ def test_bprmf_host_fed_step_matches_device_step(ws):
     assert models[0].tables.ws.status() == 0
 
 
+def test_bprmf_epoch_call_equals_the_step_loop(ws):
+    """wr_bprmf_epoch (every step of an epoch from one call, ragged last batch, Adam's t continuing from adam_t0)
+    against the same steps issued one by one."""
+    rng = np.random.RandomState(5)
+    nU, nI, D, N, B = 500, 700, 64, 5000, 2048
+    P0 = (rng.randn(nU + nI, D) * 0.1).astype(np.float32)
+    ids = dv(np.stack([rng.randint(0, nU, N), rng.randint(0, nI, N), rng.randint(1, nI, N)]).astype(np.int64))
+    Pa, Pb = dv(P0), dv(P0)
+    Ma, Va, Ga = (torch.zeros_like(Pa) for _ in range(3))
+    Mb, Vb, Gb = (torch.zeros_like(Pb) for _ in range(3))
+    steps = (N + B - 1) // B
+    la, lb = torch.zeros(steps, device=DEV), torch.zeros(steps, device=DEV)
+    assert _lib.bprmf_epoch(Pa, Ma, Va, Ga, ids, B, nU, 7, 1e-3, 1e-6, la, ws) == steps
+    for s in range(steps):
+        lo, hi = s * B, min(N, (s + 1) * B)
+        _lib.bprmf_step(Pb, Mb, Vb, Gb, ids[0, lo:hi], ids[1, lo:hi], ids[2, lo:hi], nU, 7 + s + 1, 1e-3, 1e-6,
+                        lb[s:s + 1], ws)
+    assert_close(host(la), host(lb), 'losses', rtol=2e-6)
+    assert_close(host(Pa), host(Pb), 'P', rtol=1e-5, atol_scale=2e-6)
+    assert_close(host(Va), host(Vb), 'V')
+    assert ws.status() == 0
+
+
 @pytest.mark.parametrize('D', [16, 32, 64, 128, 256, 48, 8])
 @pytest.mark.parametrize('B', [1, 31, 480, 2048])
 def test_bpr_fwd_bwd_vs_oracle(D, B, ws):

@@ -55,6 +55,24 @@ def test_argument_errors_need_no_gpu():
     assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 64, 16, 16, 0, 7, None, None, 16, 16, None, None, 16, None) == -6
     assert lib.wr_eval_rank_topk(16, 16, 16, 16, 4, 4, 4, 32, 16, 16, 0, 1, None, None, 16, 16, None, 1024, 16, None) == -3   # tensor-core path: D in {64,128}
     assert lib.wr_eval_scratch_bytes(1000, 5000, 64, 0) == 0 and lib.wr_eval_scratch_bytes(1000, 5000, 64, 1) >= (1000 + 5000) * 128
+    # the entry points added for the sampler, the epoch loop and the multi-GPU path check their arguments first too
+    assert lib.wr_neg_sample_scratch_bytes(0, 100) == 0 and lib.wr_neg_sample_scratch_bytes(1000, 2) == 0
+    small, big = lib.wr_neg_sample_scratch_bytes(10_000, 3706), lib.wr_neg_sample_scratch_bytes(1_000_000, 3706)
+    assert 0 < small < big and big > 1_000_000 * 12
+    assert lib.wr_neg_sample_mt19937(None, 0, 10, 16, 4, 100, 16, 16, 16, None, None, 16, 1 << 20, 16, None) == -1
+    assert lib.wr_bprmf_epoch(16, 16, 16, 16, None, 100, 10, 8, 4, 4, 1e-10, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, 16, 16, None) == -1
+    assert lib.wr_bprmf_epoch(16, 16, 16, 16, 16, 100, 0, 8, 4, 4, 1e-10, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, 16, 16, None) == -2
+    assert lib.wr_allgather_shards(None, 16, 64, None) == -1
+    assert lib.wr_inbox_scatter(None, 16, 16, 2, 100, 64, None) == -1
+    assert lib.wr_inbox_scatter(16, 16, 16, 9, 100, 64, None) == -2          # more ranks than one box holds
+    assert lib.wr_topk_merge(16, 16, 2, 10, 33, 16, 16, None) == -4
+    assert lib.wr_peer_barrier(None, 2, 0, 1, None, None, 0, None, None, None) == -1
+    assert lib.wr_bprmf_step_sharded_supported(4873, 64) == 1 and lib.wr_bprmf_step_sharded_supported(6_000_000, 128) == 0
+    shards = _lib.ShardsStruct()
+    shards.world, shards.rank, shards.n_users, shards.n_items, shards.rows_u_local, shards.rows_i_local = 2, 0, 10, 7, 5, 4
+    assert lib.wr_gather_rows_sharded(ctypes.addressof(shards), 0, 16, 4, 64, 16, 16, None) == -1        # bases not mapped
+    shards.rows_u_local = 6
+    assert lib.wr_gather_rows_sharded(ctypes.addressof(shards), 0, 16, 4, 64, 16, 16, None) == -2        # layout mismatch
 
 
 def test_product_refuses_cpu_tensors():
