@@ -84,84 +84,82 @@ class BaseRunner(object):
         gt_rank = np.argwhere(order == 0)[:, 1] + 1
         return BaseRunner.metrics_from_ranks(gt_rank, topk, metrics)
 
+    # runner flags copied onto the instance under the reference's attribute names (BaseRunner.py:94-110)
+    _PLAIN_ATTRS = ('epoch', 'check_epoch', 'test_epoch', 'early_stop', 'batch_size', 'eval_batch_size', 'l2',
+                    'num_workers', 'pin_memory')
+
     def __init__(self, args):
-        self.epoch = args.epoch
-        self.check_epoch = args.check_epoch
-        self.test_epoch = args.test_epoch
-        self.early_stop = args.early_stop
-        self.learning_rate = float(args.lr)
-        self.batch_size = args.batch_size
-        self.eval_batch_size = args.eval_batch_size
-        self.l2 = args.l2
-        self.optimizer_name = args.optimizer
-        self.num_workers = args.num_workers
-        self.pin_memory = args.pin_memory
-        self.topk = [int(x) for x in args.topk.split(',')]
-        self.metrics = [m.strip().upper() for m in args.metric.split(',')]
-        self.main_metric = '{}@{}'.format(self.metrics[0], self.topk[0])
-        self.time = None
+        for name in self._PLAIN_ATTRS:
+            setattr(self, name, getattr(args, name))
+        self.learning_rate, self.optimizer_name = float(args.lr), args.optimizer
+        self.topk = [int(k) for k in args.topk.split(',')]
+        self.metrics = [name.strip().upper() for name in args.metric.split(',')]
+        self.main_metric = '%s@%d' % (self.metrics[0], self.topk[0])      # early stopping watches this one
+        self.time = None                                # [start of train(), last lap]
         self.eval_precision = getattr(args, 'eval_precision', 0)
         self.last_epoch_stats = {}
 
     def _check_time(self, start=False):
-        if self.time is None or start:
-            self.time = [time()] * 2
-            return self.time[0]
-        previous = self.time[1]
-        self.time[1] = time()
-        return self.time[1] - previous
+        """Lap timer of BaseRunner.py:112-118: seconds since the previous call (the start time on a (re)start)."""
+        now = time()
+        if start or self.time is None:
+            self.time = [now, now]
+            return now
+        lap, self.time[1] = now - self.time[1], now
+        return lap
 
     def _build_optimizer(self, model):
         logging.info('Optimizer: ' + self.optimizer_name)
         return model.build_optimizer(self.optimizer_name, self.learning_rate, self.l2)
 
-    def train(self, data_dict):
-        """BaseRunner.py:126-178."""
+    def _run_epoch(self, number, data_dict, history):
+        """One pass of the reference's epoch body (BaseRunner.py:133-166): fit, dev (and optionally test) evaluation,
+        checkpoint on a new best, one log line in the reference's format.  Returns True when training should stop."""
         model = data_dict['train'].model
-        main_metric_results, dev_results = list(), list()
+        self._check_time()
+        gc.collect()
+        torch.cuda.empty_cache()
+        loss = self.fit(data_dict['train'], epoch=number)
+        fit_seconds = self._check_time()
+        if model.check_list and self.check_epoch > 0 and (number - 1) % self.check_epoch == 0:
+            utils.check(model.check_list)
+        dev = self.evaluate(data_dict['dev'], self.topk[:1], self.metrics)
+        history.append(dev)
+        line = 'Epoch {:<5} loss={:<.4f} [{:<3.1f} s]    dev=({})'.format(number, loss, fit_seconds,
+                                                                        utils.format_metric(dev))
+        if self.test_epoch > 0 and (number - 1) % self.test_epoch == 0:
+            test = self.evaluate(data_dict['test'], self.topk[:1], self.metrics)
+            line += ' test=({})'.format(utils.format_metric(test))
+        line += ' [{:<.1f} s]'.format(self._check_time())
+        watched = [h[self.main_metric] for h in history]
+        if watched[-1] == max(watched) or getattr(model, 'stage', None) == 1:
+            model.save_model()
+            line += ' *'
+        logging.info(line)
+        if self.early_stop > 0 and self.eval_termination(watched):
+            logging.info('Early stop at %d based on dev result.' % number)
+            return True
+        return False
+
+    def train(self, data_dict):
+        """BaseRunner.py:126-178: epochs until the budget or the early-stop rule ends them, then reload the best."""
+        model = data_dict['train'].model
+        history = []                                    # dev results, one dict per finished epoch
         self._check_time(start=True)
         try:
-            for epoch in range(self.epoch):
-                self._check_time()
-                gc.collect()
-                torch.cuda.empty_cache()
-                loss = self.fit(data_dict['train'], epoch=epoch + 1)
-                training_time = self._check_time()
-
-                if len(model.check_list) > 0 and self.check_epoch > 0 and epoch % self.check_epoch == 0:
-                    utils.check(model.check_list)
-
-                dev_result = self.evaluate(data_dict['dev'], self.topk[:1], self.metrics)
-                dev_results.append(dev_result)
-                main_metric_results.append(dev_result[self.main_metric])
-                logging_str = 'Epoch {:<5} loss={:<.4f} [{:<3.1f} s]    dev=({})'.format(
-                    epoch + 1, loss, training_time, utils.format_metric(dev_result))
-
-                if self.test_epoch > 0 and epoch % self.test_epoch == 0:
-                    test_result = self.evaluate(data_dict['test'], self.topk[:1], self.metrics)
-                    logging_str += ' test=({})'.format(utils.format_metric(test_result))
-                testing_time = self._check_time()
-                logging_str += ' [{:<.1f} s]'.format(testing_time)
-
-                if max(main_metric_results) == main_metric_results[-1] or \
-                        (hasattr(model, 'stage') and model.stage == 1):
-                    model.save_model()
-                    logging_str += ' *'
-                logging.info(logging_str)
-
-                if self.early_stop > 0 and self.eval_termination(main_metric_results):
-                    logging.info('Early stop at %d based on dev result.' % (epoch + 1))
+            for number in range(1, self.epoch + 1):
+                if self._run_epoch(number, data_dict, history):
                     break
         except KeyboardInterrupt:
             logging.info('Early stop manually')
-            exit_here = input('Exit completely without evaluation? (y/n) (default n):')
-            if exit_here.lower().startswith('y'):
+            answer = input('Exit completely without evaluation? (y/n) (default n):')
+            if answer.lower().startswith('y'):
                 logging.info(os.linesep + '-' * 45 + ' END: ' + utils.get_time() + ' ' + '-' * 45)
                 exit(1)
-
-        best_epoch = main_metric_results.index(max(main_metric_results))
+        watched = [h[self.main_metric] for h in history]
+        best = watched.index(max(watched))
         logging.info(os.linesep + 'Best Iter(dev)={:>5}\t dev=({}) [{:<.1f} s] '.format(
-            best_epoch + 1, utils.format_metric(dev_results[best_epoch]), self.time[1] - self.time[0]))
+            best + 1, utils.format_metric(history[best]), self.time[1] - self.time[0]))
         model.load_model()
 
     def epoch_batches(self, dataset):
@@ -237,11 +235,12 @@ class BaseRunner(object):
         return np.mean(loss_host).item()
 
     def eval_termination(self, criterion):
-        if len(criterion) > self.early_stop and utils.non_increasing(criterion[-self.early_stop:]):
-            return True
-        elif len(criterion) - criterion.index(max(criterion)) > self.early_stop:
-            return True
-        return False
+        """BaseRunner.py:203-208: stop after `early_stop` epochs that never improved on their predecessor, or once the
+        best epoch lies more than `early_stop` epochs back."""
+        patience = self.early_stop
+        stalled = len(criterion) > patience and utils.non_increasing(criterion[-patience:])
+        epochs_since_best = len(criterion) - criterion.index(max(criterion))
+        return bool(stalled or epochs_since_best > patience)
 
     def _eval_inputs(self, dataset):
         """Device copies of the eval rows and the history CSR, cached on the dataset / model."""

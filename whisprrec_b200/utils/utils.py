@@ -9,14 +9,15 @@ import torch
 
 
 def init_seed(seed):
-    """utils.py:13-20: python, numpy (legacy global RandomState) and torch generators."""
-    random.seed(seed)
-    np.random.seed(seed)
-    torch.manual_seed(seed)
+    """utils.py:13-20: python, numpy (legacy global RandomState) and torch generators, in the reference's order (the
+    negative sampler and the DataLoader replay depend on exactly these two global streams)."""
+    seeders = [random.seed, np.random.seed, torch.manual_seed]
     if torch.cuda.is_available():
-        torch.cuda.manual_seed_all(seed)
-    torch.backends.cudnn.benchmark = False
-    torch.backends.cudnn.deterministic = True
+        seeders.append(torch.cuda.manual_seed_all)
+    for seed_fn in seeders:
+        seed_fn(seed)
+    cudnn = torch.backends.cudnn
+    cudnn.benchmark, cudnn.deterministic = False, True
 
 
 def df_to_dict(df):
@@ -25,10 +26,8 @@ def df_to_dict(df):
 
 
 def batch_to_gpu(batch, device):
-    """utils.py:33-37."""
-    for key, value in batch.items():
-        if type(value) is torch.Tensor:
-            batch[key] = value.to(device)
+    """utils.py:33-37: every tensor of the feed dict moves to `device`, in place; other entries stay."""
+    batch.update({k: v.to(device) for k, v in batch.items() if type(v) is torch.Tensor})
     return batch
 
 
