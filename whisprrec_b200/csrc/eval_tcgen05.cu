@@ -9,6 +9,8 @@
 //   warps 4-19  epilogue: tcgen05.ld 32 columns at a time, history mask from the sorted per-user CSR (one cursor
 //               per row, the tiles arrive in item order), count of items beating the target -- while the MMA of
 //               the next tile fills the other accumulator.  The score matrix never leaves TMEM.
+//   warps 20-23 (top-k launches only) drain the per-row candidate rings the epilogue warps push into, keep each
+//               row's k best and publish its threshold.
 // Operands are rounded to bf16 once per evaluation (pack kernels below); the target score is the fp32 FMA chain
 // over the same bf16-rounded operands.  Parity with the fp32 path is therefore "looser": see tests.
 #include <cuda.h>
@@ -252,8 +254,49 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     return d;
 }
 
-template <int D, int VARIANT, bool TOPK>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Top-k mode 2: the epilogue warps only FILTER -- a score that reaches the row's current k-th best is pushed into the
+// row's ring in shared memory -- and four extra warps (one thread per row) drain the rings into per-row k-best
+// lists and publish the new threshold.  The epilogue never sorts, never compacts and never waits for another
+// epilogue warp's bookkeeping, and the threshold is per ROW (all 256 columns of a tile), not per 64-column stripe.
+constexpr int TC_RING = 16;                             // ring entries per row
+constexpr int TC_DRAIN_WARPS = 4;
+constexpr int TC_THREADS_DRAIN = TC_THREADS + TC_DRAIN_WARPS * 32;
+constexpr int TC_SMEM_DRAIN = TC_BM * TC_RING * 8 + TC_BM * 12 + 64;      // rings, head / tail / tau per row, counters
+
+__device__ __forceinline__ uint32_t lds_vol_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_vol_u32(uint32_t a, uint32_t v) {
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+struct TopRings {
+    float *v;                 // [TC_BM][TC_RING]
+    int32_t *id;              // [TC_BM][TC_RING]   -1 = empty
+    uint32_t *head, *tail;    // [TC_BM] monotonically increasing slot counters
+    float *tau;               // [TC_BM] value of the row's k-th best so far (-inf until the list is full)
+    int *epi_done;            // epilogue warps that have finished
+};
+__device__ __forceinline__ void ring_push(const TopRings &rg, int row, float x, int32_t id) {
+    const uint32_t slot = atomicAdd(rg.head + row, 1u);
+    const int o = row * TC_RING + (int)(slot & (TC_RING - 1));
+    // The payload is written inside the iteration that finds room: a lane with room must never wait for the lanes
+    // of its warp whose rings are full (their drainers may be waiting for THIS lane's payload).
+    bool pending = true;
+    while (pending) {
+        if ((int32_t)(slot - *reinterpret_cast<volatile uint32_t *>(rg.tail + row)) < TC_RING) {
+            *reinterpret_cast<volatile float *>(rg.v + o) = x;
+            __threadfence_block();
+            *reinterpret_cast<volatile int32_t *>(rg.id + o) = id;
+            pending = false;
+        }
+    }
+}
+
+template <int D, int VARIANT, int TOPK>
+__global__ void __launch_bounds__(TOPK == 2 ? TC_THREADS_DRAIN : TC_THREADS, 1)
 eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     using C = TcCfg<D>;
     extern __shared__ uint8_t smem_raw[];
@@ -265,6 +308,13 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
     int *cnt_s = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [4][128]
+    TopRings rg;
+    rg.v = reinterpret_cast<float *>(cnt_s + 4 * TC_BM);
+    rg.id = reinterpret_cast<int32_t *>(rg.v + TC_BM * TC_RING);
+    rg.head = reinterpret_cast<uint32_t *>(rg.id + TC_BM * TC_RING);
+    rg.tail = rg.head + TC_BM;
+    rg.tau = reinterpret_cast<float *>(rg.tail + TC_BM);
+    rg.epi_done = reinterpret_cast<int *>(rg.tau + TC_BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
@@ -288,6 +338,14 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (TOPK == 2 && threadIdx.x >= TC_THREADS) {
+        const int r = threadIdx.x - TC_THREADS;
+        for (int i = 0; i < TC_RING; ++i) rg.id[r * TC_RING + i] = -1;
+        rg.head[r] = 0;
+        rg.tail[r] = 0;
+        rg.tau[r] = -INFINITY;
+        if (r == 0) *rg.epi_done = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -336,7 +394,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 umma_commit(&tm_full[acc]);                  // accumulator ready for the epilogue
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
         // ---------------- epilogue: 16 warps, TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 ----------------
         const int quarter = warp & 3, grp = (warp - 4) >> 2;
         const int rl = quarter * 32 + lane;
@@ -368,7 +426,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int top_trigger = p.top_trigger;      // fold the buffers once any lane holds more than this many
         float tau = -INFINITY;
         int bcnt = 0, worst = 0;
-        if (TOPK) {
+        if (TOPK == 1) {
             for (int i = 0; i < p.k; ++i) {
                 top.lv[i] = -INFINITY;
                 top.li[i] = INT32_MAX - i;      // empty slots: worse than anything, distinct, evicted first
@@ -401,7 +459,31 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (pj < 32u) m |= 1u << pj;
                 }
                 tmem_ld_wait();
-                if (TOPK) {
+                if (TOPK == 2) {
+                    if (m_top != 0) {       // history / table-end columns can never be candidates (the compiler turns
+#pragma unroll                              // this into 32 selects: cheaper than a divergent branch per chunk)
+                        for (int i = 0; i < 32; ++i)
+                            if ((m_top >> i) & 1u) v[i] = 0xff800000u;      // -inf; these columns are in m as well
+                    }
+                    // the row's threshold as the drain warps last published it (stale = lower = still correct).
+                    // ">=" lets ties through: the drainer decides them by item id
+                    const float tau_row = *reinterpret_cast<volatile float *>(rg.tau + rl);
+#pragma unroll
+                    for (int g8 = 0; g8 < 32; g8 += 8) {
+                        float mx = fmax3(__uint_as_float(v[g8]), __uint_as_float(v[g8 + 1]), __uint_as_float(v[g8 + 2]));
+                        mx = fmax3(mx, __uint_as_float(v[g8 + 3]), __uint_as_float(v[g8 + 4]));
+                        mx = fmax3(mx, __uint_as_float(v[g8 + 5]), __uint_as_float(v[g8 + 6]));
+                        mx = fmaxf(mx, __uint_as_float(v[g8 + 7]));
+                        if (mx >= tau_row && mx > -INFINITY) {
+#pragma unroll
+                            for (int i = g8; i < g8 + 8; ++i) {
+                                const float x = __uint_as_float(v[i]);
+                                if (x >= tau_row && x > -INFINITY) ring_push(rg, rl, x, j0 + i);
+                            }
+                        }
+                    }
+                }
+                if (TOPK == 1) {
                     if (m_top != 0) {       // rare: history / table-end columns can never be candidates
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
@@ -490,11 +572,18 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // the four stripe lists of a row meet in the (now idle) B-stage shared memory: [row][stripe][k]
         float *lv = reinterpret_cast<float *>(sB);
         int32_t *li = reinterpret_cast<int32_t *>(sB + TC_BM * 4 * TC_KMAX * 4);
-        if (TOPK) {
+        if (TOPK == 1) {
             top_compact(top, p.k, bcnt, tau, worst);
             for (int i = 0; i < p.k; ++i) {
                 lv[(rl * 4 + grp) * TC_KMAX + i] = top.lv[i];
                 li[(rl * 4 + grp) * TC_KMAX + i] = top.li[i];
+            }
+        }
+        if (TOPK == 2) {                    // every push of this warp is visible before the drain warps see "done"
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(rg.epi_done, 1);
             }
         }
         cnt_s[grp * TC_BM + rl] = cnt;
@@ -503,7 +592,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int total = cnt_s[rl] + cnt_s[TC_BM + rl] + cnt_s[2 * TC_BM + rl] + cnt_s[3 * TC_BM + rl];
             if (p.splits == 1) p.rank[r] = 1 + total;
             else atomicAdd(&p.rank[r], total);
-            if (TOPK) {
+            if (TOPK == 1) {
                 // the row's 4k candidates (unsorted) -> its k best in order: k selection passes, taken slots marked
                 const int n = 4 * TC_KMAX;
                 for (int s = 0; s < p.k; ++s) {
@@ -525,6 +614,72 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     p.topk_val[r * p.k + s] = best >= 0 ? bv : -INFINITY;
                     p.topk_idx[r * p.k + s] = best >= 0 ? bi : -1;
                 }
+            }
+        }
+    }
+    if (TOPK == 2 && warp >= 4 + TC_EPI_WARPS) {
+        // ---------------- drain warps: thread r owns row r's ring and its k-best list ----------------
+        const int r = threadIdx.x - TC_THREADS;
+        const int k = p.k;
+        float lv[TC_KMAX];
+        int32_t li[TC_KMAX];
+        for (int i = 0; i < k; ++i) {
+            lv[i] = -INFINITY;
+            li[i] = INT32_MAX - i;                      // empty slots: worse than anything, distinct
+        }
+        float w = -INFINITY;                            // the worst kept entry: value, id, position
+        int32_t wid = INT32_MAX;
+        int wp = 0;
+        uint32_t tail = 0;
+        volatile uint32_t *vhead = rg.head + r;
+        volatile int32_t *vid = rg.id + r * TC_RING;
+        volatile float *vv = rg.v + r * TC_RING;
+        while (true) {
+            const bool finishing = *reinterpret_cast<volatile int *>(rg.epi_done) == TC_EPI_WARPS;
+            const uint32_t head = *vhead;               // read AFTER the completion count: if that was final, so is this
+            if (tail == head) {
+                if (finishing) break;
+                __nanosleep(100);
+                continue;
+            }
+            while (tail != head) {
+                const int o = (int)(tail & (TC_RING - 1));
+                int32_t id;
+                while ((id = vid[o]) == -1) {}          // slot claimed, payload still on its way
+                __threadfence_block();
+                const float x = vv[o];
+                vid[o] = -1;
+                __threadfence_block();
+                ++tail;
+                *reinterpret_cast<volatile uint32_t *>(rg.tail + r) = tail;
+                if (top_worse(w, wid, x, id)) {         // beats the worst kept entry (ties: the lower id wins)
+                    lv[wp] = x;
+                    li[wp] = id;
+                    w = lv[0];
+                    wid = li[0];
+                    wp = 0;
+                    for (int j = 1; j < k; ++j) {
+                        if (top_worse(lv[j], li[j], w, wid)) {
+                            w = lv[j];
+                            wid = li[j];
+                            wp = j;
+                        }
+                    }
+                    *reinterpret_cast<volatile float *>(rg.tau + r) = w;
+                }
+            }
+        }
+        const int64_t row = row0 + r;
+        if (row < p.R) {
+            for (int s = 0; s < k; ++s) {               // k selection passes: best first
+                int best = -1;
+                for (int j = 0; j < k; ++j) {
+                    if (li[j] < 0 || li[j] >= INT32_MAX - TC_KMAX) continue;        // taken / empty
+                    if (best < 0 || top_worse(lv[best], li[best], lv[j], li[j])) best = j;
+                }
+                p.topk_val[row * k + s] = best >= 0 ? lv[best] : -INFINITY;
+                p.topk_idx[row * k + s] = best >= 0 ? li[best] : -1;
+                if (best >= 0) li[best] = -1;
             }
         }
     }
@@ -565,14 +720,15 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int D, int VARIANT, bool TOPK>
+template <int D, int VARIANT, int TOPK>
 static int launch_tc_v(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
-    constexpr int smem = TcCfg<D>::SMEM;
+    constexpr int smem = TcCfg<D>::SMEM + (TOPK == 2 ? TC_SMEM_DRAIN : 0);
+    constexpr int threads = TOPK == 2 ? TC_THREADS_DRAIN : TC_THREADS;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D, VARIANT, TOPK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    eval_tc_rank_kernel<D, VARIANT, TOPK><<<dim3(row_tiles, p.splits), TC_THREADS, smem, st>>>(ma, mb, p);
+    eval_tc_rank_kernel<D, VARIANT, TOPK><<<dim3(row_tiles, p.splits), threads, smem, st>>>(ma, mb, p);
     return (int)cudaGetLastError();
 }
 
@@ -583,12 +739,19 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, 
         const char *e = getenv("WR_TC_VARIANT");        // tuning knob for the epilogue's counting form
         variant = e ? atoi(e) : 1;
     }
-    if (p.topk_idx) return launch_tc_v<D, 1, true>(ma, mb, p, row_tiles, st);
+    if (p.topk_idx) {
+        static int mode = -1;
+        if (mode < 0) {
+            const char *e = getenv("WR_TC_TOPK_MODE");      // 1: per-thread lists in the epilogue; 2: drain warps
+            mode = e ? atoi(e) : 2;
+        }
+        return mode == 1 ? launch_tc_v<D, 1, 1>(ma, mb, p, row_tiles, st) : launch_tc_v<D, 1, 2>(ma, mb, p, row_tiles, st);
+    }
     switch (variant) {
-        case 1: return launch_tc_v<D, 1, false>(ma, mb, p, row_tiles, st);
-        case 2: return launch_tc_v<D, 2, false>(ma, mb, p, row_tiles, st);
-        case 3: return launch_tc_v<D, 3, false>(ma, mb, p, row_tiles, st);
-        default: return launch_tc_v<D, 0, false>(ma, mb, p, row_tiles, st);
+        case 1: return launch_tc_v<D, 1, 0>(ma, mb, p, row_tiles, st);
+        case 2: return launch_tc_v<D, 2, 0>(ma, mb, p, row_tiles, st);
+        case 3: return launch_tc_v<D, 3, 0>(ma, mb, p, row_tiles, st);
+        default: return launch_tc_v<D, 0, 0>(ma, mb, p, row_tiles, st);
     }
 }
 
