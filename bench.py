@@ -621,6 +621,31 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
                             'note': 'sampling + shuffle + upload + all steps + loss read-back; tables L2-resident'}
     except Exception as e:  # noqa: BLE001
         out['epoch_fit'] = {'error': repr(e)}
+    try:    # ml-100k (the reference's own CPU-runnable case, BASELINE.json configs[0]): whole epochs and the dev evaluation
+        from tests.helpers import ml100k_corpus
+        c100 = ml100k_corpus()
+        res = {}
+        for name, over in (('BPRMF', {}), ('LightGCN', {'gcn_layers': 2})):
+            m100, r100, d100 = make_model(c100, dev, name, **over)
+            r100.fit(d100['train'])
+            ep = []
+            for _ in range(3):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                r100.fit(d100['train'])
+                torch.cuda.synchronize(); ep.append(time.perf_counter() - t0)
+            ev = []
+            for _ in range(3):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                r100.evaluate(d100['dev'], [10], ['NDCG', 'HR'])
+                torch.cuda.synchronize(); ev.append(time.perf_counter() - t0)
+            n_tr, n_dev = len(d100['train']), len(d100['dev'])
+            res[name] = {'epoch_s': float(np.median(ep)), 'train_interactions_per_s': n_tr / float(np.median(ep)),
+                         'dev_eval_s': float(np.median(ev)), 'eval_rows_per_s': n_dev / float(np.median(ev))}
+        res['reference_cpu'] = {'note': 'unmodified reference on an 8-core host (BASELINE.md section 2): BPRMF epoch 1.4 s '
+                                        '(47k interactions/s), LightGCN 1.7 s (39k/s), dev eval 1.3 s (6.3k rows/s)'}
+        out['ml100k'] = res
+    except Exception as e:  # noqa: BLE001
+        out['ml100k'] = {'error': repr(e)}
     try:    # the two-launch form of the same step (what large tables use): fwd+bwd kernel, then the Adam sweep
         t = model.tables
         batches = runner.epoch_batches(data['train'])
