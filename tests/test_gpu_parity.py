@@ -151,6 +151,30 @@ def test_bprmf_host_fed_step_matches_device_step(ws):
     assert models[0].tables.ws.status() == 0
 
 
+def test_host_fed_context_on_tables_too_large_for_the_single_launch(ws):
+    """wr_bprmf_ctx_step beyond the single-launch size (> 8 Mi elements): the two kernels read the ids straight from
+    the mapped pinned buffer and the loss comes back by copy; same numbers as the device-fed step."""
+    rng = np.random.RandomState(9)
+    nU, nI, D, B = 40000, 30000, 128, 4096            # 8.96 M elements
+    P0 = (rng.randn(nU + nI, D) * 0.05).astype(np.float32)
+    Pa, Pb = dv(P0), dv(P0)
+    Ma, Va, Ga = (torch.zeros_like(Pa) for _ in range(3))
+    Mb, Vb, Gb = (torch.zeros_like(Pb) for _ in range(3))
+    ctx = _lib.BprmfContext(Pa, Ma, Va, Ga, nU, 1e-3, 1e-6, ws)
+    lb = torch.zeros(1, device=DEV)
+    for step in range(1, 4):
+        ids = np.stack([rng.randint(0, nU, B), rng.randint(0, nI, B), rng.randint(1, nI, B)]).astype(np.int64)
+        pinned = torch.from_numpy(ids).pin_memory()
+        loss_a = ctx.step(pinned.data_ptr(), B, step)
+        d = dv(ids)
+        _lib.bprmf_step(Pb, Mb, Vb, Gb, d[0], d[1], d[2], nU, step, 1e-3, 1e-6, lb, ws)
+        assert loss_a == pytest.approx(float(lb[0]), rel=2e-6)
+        assert_close(host(Pa[:256]), host(Pb[:256]), f'P step {step}', rtol=1e-5, atol_scale=2e-6)
+    assert float((Pa - Pb).abs().max()) <= 2e-6 * float(Pb.abs().max()) + 1e-9
+    ctx.close()
+    assert ws.status() == 0
+
+
 def test_bprmf_epoch_call_equals_the_step_loop(ws):
     """wr_bprmf_epoch (every step of an epoch from one call, ragged last batch, Adam's t continuing from adam_t0)
     against the same steps issued one by one."""
