@@ -13,6 +13,7 @@ Same flags, same epoch loop, same early stopping, same log lines.  Differences a
 import gc
 import logging
 import os
+import threading
 from time import time
 
 import numpy as np
@@ -165,9 +166,25 @@ class BaseRunner(object):
     def epoch_batches(self, dataset):
         """The epoch's (user, pos, neg) in the reference's batch order, as int64 device tensors."""
         model = dataset.model
-        dataset.actions_before_epoch()                       # BaseRunner.py:184 (must precede the loader draws)
-        perm = dataloader_draws(len(dataset), shuffle=True)  # BaseRunner.py:188-193
         dev = model.tables.P.device
+        # BaseRunner.py:184 then :188-193.  The sampler consumes NumPy's global generator, the loader draws torch's:
+        # two independent streams, so the device sampler (a C call that waits for the GPU) runs beside the CPU randperm.
+        failure = []
+
+        def sample():
+            try:
+                torch.cuda.set_device(dev)                   # the CUDA current device is per thread
+                dataset.actions_before_epoch()
+            except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
+                failure.append(e)
+        worker = threading.Thread(target=sample)
+        worker.start()
+        try:
+            perm = dataloader_draws(len(dataset), shuffle=True)
+        finally:
+            worker.join()
+        if failure:
+            raise failure[0]
         if getattr(dataset, 'neg_device', None) is not None:
             # negatives were drawn on the device: only the permutation crosses the bus
             user, item = dataset._device_cols(dev)[:2]
