@@ -223,3 +223,23 @@ def test_spmm_plan_slices_tile_the_long_rows_exactly():
         assert beg[sel][0] == rowptr[r] and (beg[sel][1:] == beg[sel][:-1] + ln[sel][:-1]).all()
         assert beg[sel][-1] + ln[sel][-1] == rowptr[r + 1] and ln[sel].max() <= 128 and ln[sel].min() >= 1
     assert _lib.SpmmPlan(rowptr, 64, 'cpu', threshold=10_000).ref() is None      # nothing to split
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
+    contract keys, nothing else there."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                        '--warmup', '3'], capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'train_interactions_per_s' and d['unit'] == 'interactions/s'
+    assert d['higher_is_better'] is True and d['value'] > 0 and d['n_gpus'] == 1
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
