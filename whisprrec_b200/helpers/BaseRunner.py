@@ -177,14 +177,18 @@ class BaseRunner(object):
                 dataset.actions_before_epoch()
             except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
                 failure.append(e)
-        worker = threading.Thread(target=sample)
-        worker.start()
-        try:
+        if len(dataset) >= 200_000:                          # below that a thread hand-over costs more than it hides
+            worker = threading.Thread(target=sample)
+            worker.start()
+            try:
+                perm = dataloader_draws(len(dataset), shuffle=True)
+            finally:
+                worker.join()
+            if failure:
+                raise failure[0]
+        else:
+            dataset.actions_before_epoch()
             perm = dataloader_draws(len(dataset), shuffle=True)
-        finally:
-            worker.join()
-        if failure:
-            raise failure[0]
         if getattr(dataset, 'neg_device', None) is not None:
             # negatives were drawn on the device: only the permutation crosses the bus
             user, item = dataset._device_cols(dev)[:2]
