@@ -287,6 +287,9 @@ class GeneralModel(BaseModel):
         def actions_before_epoch(self):
             """BaseModel.py:167-177, bit-exact on NumPy's global stream.
 
+            Training (`BaseRunner.fit`, which fuses the tables first) always takes the device sampler below; the NumPy
+            loop after it is what a host-side caller without device tables gets (the CPU tests of the data pipeline).
+
             The reference draws all N*num_neg candidates in one bulk call and then walks every row in order,
             redrawing (one scalar `randint` each) while the candidate is in the user's train set.  Only rows
             whose candidate was rejected ever touch the stream again, so they are found with one vectorised
