@@ -189,3 +189,48 @@ def test_ml100k_epoch_trajectory_bprmf():
     res = O.evaluate_method(ranks, [10, 20], ['NDCG', 'HR'])
     for k, v in zip(g['dev_metric_keys'], g['dev_metric_vals']):
         assert res[str(k)] == pytest.approx(float(v), abs=5e-4), k
+
+
+# --------------------------------------------------------------------------------------------------------------
+# SGL: the oracle of the next row, pinned to the reference before any kernel exists
+# --------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize('tag', ['sgl_d16_l2', 'sgl_d32_l3'])
+def test_sgl_oracle_matches_reference(tag):
+    import random
+    from oracle import sgl_oracle as S
+    s = small_case(load('sgl_cases.npz'), tag)
+    lr, l2, reg, L, D, tau, w_ssl, drop = (float(x) for x in s['hp'])
+    L = int(L)
+    nU, nI = s['U0'].shape[0], s['I0'].shape[0]
+    N = nU + nI
+    tr = s['train']
+    # same seeding as utils.init_seed(1234); building the reference model consumes torch's generator only, so python's
+    # `random` is still at its seed when graph_construction() draws the two views
+    random.seed(1234)
+    rows, cols = S.symmetric_edges(nU, nI, tr[:, 0], tr[:, 1])
+    main = S.normalise(rows, cols, N)
+    subs = [S.normalise(*S.edge_dropout(rows, cols, drop), N) for _ in range(2)]
+    graphs = [O.csr_to_torch(*g, N) for g in (main, subs[0], subs[1])]
+    for g, name in zip(graphs, ('graph', 'sub1', 'sub2')):
+        assert (g.to_dense().numpy() == s[name]).all(), name          # views bit for bit (structure and fp32 weights)
+    E0 = torch.from_numpy(np.concatenate([s['U0'], s['I0']]))
+    for g, name in zip(graphs, ('main', 'sub1', 'sub2')):
+        pooled = S.propagate(g, E0, L).numpy()
+        assert_close(pooled[:nU], s[f'pooled_{name}_user'], name + ' users')
+        assert_close(pooled[nU:], s[f'pooled_{name}_item'], name + ' items')
+    U, I = torch.from_numpy(s['U0'].copy()), torch.from_numpy(s['I0'].copy())
+    mom = [torch.zeros_like(U), torch.zeros_like(U), torch.zeros_like(I), torch.zeros_like(I)]
+    for step in range(3):
+        user, pos, neg = s[f's{step}/user'], s[f's{step}/pos'], s[f's{step}/neg']
+        val, gU, gI = S.fwd_bwd(U, I, graphs, user, pos, neg, L, reg, tau, w_ssl)
+        assert_close(val.item(), s[f's{step}/loss'], f'loss step {step}', rtol=2e-6)
+        assert_close(gU.numpy(), s[f's{step}/gU'], f'gU step {step}', rtol=2e-5, atol_scale=2e-6)
+        assert_close(gI.numpy(), s[f's{step}/gI'], f'gI step {step}', rtol=2e-5, atol_scale=2e-6)
+        O.adam_l2_step(U, mom[0], mom[1], gU, step + 1, lr, l2)
+        O.adam_l2_step(I, mom[2], mom[3], gI, step + 1, lr, l2)
+        assert_close(U.numpy(), s[f's{step}/U'], f'U step {step}', rtol=2e-5, atol_scale=2e-6)
+        assert_close(I.numpy(), s[f's{step}/I'], f'I step {step}', rtol=2e-5, atol_scale=2e-6)
+    # the next epoch's views continue python's stream
+    nxt = O.csr_to_torch(*S.normalise(*S.edge_dropout(rows, cols, drop), N), N).to_dense().numpy()
+    assert np.count_nonzero(nxt) == int(s['sub1_epoch2_nnz'])
