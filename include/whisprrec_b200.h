@@ -226,6 +226,11 @@ int wr_neg_sample_mt19937(const uint32_t *host_key, int pos, int64_t N, const in
                           uint32_t *host_key_out, int *host_pos_out, void *scratch, size_t scratch_bytes, void *ws,
                           void *stream);
 
+/* wr_pyrandom_sample: HOST function (no GPU): `random.sample(range(n), k)` of CPython's `random` module on its
+ * Mersenne Twister state (`random.getstate()[1]`: 624 words + position), bit-exact incl. the state afterwards.  SGL's
+ * per-epoch edge dropout (utils/augmentor.py:77-111) is exactly this call on the adjacency's non-zeros. */
+int wr_pyrandom_sample(uint32_t *host_state, int *host_pos, int64_t n, int64_t k, int64_t *host_out);
+
 /* ==== one 8 x B200 box: row-sharded tables over NVLink peer memory =====================
  * One process per GPU.  Every rank owns a slab of device memory (wr_peer_alloc), exports it (wr_peer_export),
  * and maps every other rank's slab (wr_peer_open): after that a kernel on any GPU can load, store and reduce into

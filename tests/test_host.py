@@ -243,3 +243,21 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+@pytest.mark.parametrize('n,k', [(10, 3), (10, 10), (21, 6), (22, 6), (100, 90), (1000, 5), (100000, 7), (200000, 180000),
+                                 (1 << 33, 4), (0, 0)])
+def test_library_replica_of_python_random_sample(n, k):
+    """wr_pyrandom_sample (host code in the library) == random.sample(range(n), k), including the generator state it
+    leaves behind -- both branches of CPython's algorithm (pool shuffle / set of picks) and ranges beyond 32 bits.
+    SGL's per-epoch edge dropout (reference utils/augmentor.py:77-111) is this call."""
+    import random
+    random.seed(3407)
+    random.random()                                    # not at a block boundary
+    want = random.sample(range(n), k)
+    after = random.random()
+    random.seed(3407)
+    random.random()
+    got = _lib.py_random_sample(n, k)
+    assert got.tolist() == want
+    assert random.random() == after

@@ -48,6 +48,7 @@ SIGNATURES = {
     'wr_scatter_add_rows': (_int, [_p, _p, _i64, _int, _i64, _p, _p, _p]),
     'wr_neg_sample_scratch_bytes': (_sz, [_i64, _i64]),
     'wr_neg_sample_mt19937': (_int, [_p, _int, _i64, _p, _i64, _i64, _p, _p, _p, _p, _c.POINTER(_int), _p, _sz, _p, _p]),
+    'wr_pyrandom_sample': (_int, [_p, _c.POINTER(_int), _i64, _i64, _p]),
     # ---- row-sharded tables over NVLink peer memory ----
     'wr_peer_alloc': (_int, [_sz, _c.POINTER(_p)]),
     'wr_peer_free': (_int, [_p]),
@@ -387,6 +388,20 @@ def neg_sample_numpy_stream(user, n_users, n_items, train_ptr, train_idx, ws, sc
     check(rc)
     np.random.set_state((name, key_out, pos_out.value, has_gauss, cached))
     return neg
+
+
+def py_random_sample(n, k):
+    """`random.sample(range(n), k)` on Python's GLOBAL `random` generator, computed by the library (host code, same
+    algorithm, same stream): returns an int64 NumPy array and leaves the generator where Python would."""
+    import random
+    import numpy as np
+    version, internal, gauss = random.getstate()
+    state = np.array(internal[:624], dtype=np.uint32)
+    pos = _int(int(internal[624]))
+    out = np.empty(int(k), dtype=np.int64)
+    check(load().wr_pyrandom_sample(state.ctypes.data, ctypes.byref(pos), int(n), int(k), out.ctypes.data))
+    random.setstate((version, tuple(int(x) for x in state) + (pos.value,), gauss))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
