@@ -261,3 +261,26 @@ def test_library_replica_of_python_random_sample(n, k):
     got = _lib.py_random_sample(n, k)
     assert got.tolist() == want
     assert random.random() == after
+
+
+@pytest.mark.parametrize('tag', ['sgl_d16_l2', 'sgl_d32_l3'])
+def test_sgl_edge_dropout_views_match_reference(tag):
+    """The two augmented views of an epoch, built from our CSR with the library's replica of Python's random stream,
+    equal the reference's sub-graphs bit for bit (tests/golden/sgl_cases.npz)."""
+    import random
+    from tests.helpers import load, small_case
+    from whisprrec_b200.models.general.LightGCN import build_norm_adj_csr
+    from whisprrec_b200.utils.graph_views import edge_dropout_view
+    s = small_case(load('sgl_cases.npz'), tag)
+    nU, nI, drop = s['U0'].shape[0], s['I0'].shape[0], float(s['hp'][7])
+    N = nU + nI
+    tr = np.unique(s['train'].astype(np.int64), axis=0)
+    ptr = np.zeros(nU + 1, dtype=np.int64)
+    np.cumsum(np.bincount(tr[:, 0], minlength=nU), out=ptr[1:])
+    rowptr, col, _ = build_norm_adj_csr(nU, nI, ptr, tr[:, 1].astype(np.int32))
+    random.seed(1234)
+    for name in ('sub1', 'sub2'):
+        vp, vc, vv = edge_dropout_view(rowptr, col, drop)
+        dense = np.zeros((N, N), dtype=np.float32)
+        dense[np.repeat(np.arange(N), np.diff(vp)), vc] = vv
+        assert (dense == s[name]).all(), name
