@@ -284,3 +284,38 @@ def test_sgl_edge_dropout_views_match_reference(tag):
         dense = np.zeros((N, N), dtype=np.float32)
         dense[np.repeat(np.arange(N), np.diff(vp)), vc] = vv
         assert (dense == s[name]).all(), name
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/src/models/general/BPRMF.py'),
+                    reason='needs the reference checkout (authoring container only)')
+def test_checkpoints_interchange_with_the_reference(tmp_path):
+    """a `.pt` written by the reference's BaseModel.save_model loads into ours and the other way
+    round -- same state_dict keys, shapes, dtype (reference models/BaseModel.py:48-59)."""
+    import subprocess
+    import sys
+    corpus = ml100k_corpus()
+    ours = BPRMF(model_args(BPRMF), corpus)
+    ours_path, ref_path = str(tmp_path / 'ours.pt'), str(tmp_path / 'ref.pt')
+    torch.save(ours.state_dict(), ours_path)
+    # the reference runs in its own interpreter: its top-level packages are called `models`, `helpers`, `utils`
+    script = f'''
+import sys, types, numpy as np, torch
+np.float_ = np.float64
+sys.path.insert(0, "/root/reference/src")
+from models.general.BPRMF import BPRMF
+args = types.SimpleNamespace(device=torch.device("cpu"), model_path="", buffer=1, num_neg=1, test_all=1, embedding_size=64)
+corpus = types.SimpleNamespace(n_users={int(corpus.n_users)}, n_items={int(corpus.n_items)})
+m = BPRMF(args, corpus)
+m.load_state_dict(torch.load("{ours_path}"))                      # ours -> reference, strict
+torch.manual_seed(5)
+m = BPRMF(args, corpus)
+m.model_path = "{ref_path}"
+m.save_model()                                                    # reference -> file
+print("REF_SUM", float(m.user_embeddings.weight.double().sum()), float(m.item_embeddings.weight.double().sum()))
+'''
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    u_sum, i_sum = (float(x) for x in r.stdout.split('REF_SUM')[1].split())
+    ours.load_state_dict(torch.load(ref_path))                        # reference -> ours, strict
+    assert float(ours.user_embeddings.weight.double().sum()) == u_sum
+    assert float(ours.item_embeddings.weight.double().sum()) == i_sum
