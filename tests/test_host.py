@@ -319,3 +319,37 @@ print("REF_SUM", float(m.user_embeddings.weight.double().sum()), float(m.item_em
     ours.load_state_dict(torch.load(ref_path))                        # reference -> ours, strict
     assert float(ours.user_embeddings.weight.double().sum()) == u_sum
     assert float(ours.item_embeddings.weight.double().sum()) == i_sum
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_DATA, 'ml-100k', 'ml-100k.inter')),
+                    reason='needs the reference checkout (authoring container only)')
+def test_reference_corpus_cache_loads_as_our_reader(tmp_path):
+    """a `BaseReader.pkl` cached by the reference (main.py:54-63) is picked up by `--regenerate 0`
+    here: it unpickles as this package's reader and yields the same splits and CSR views."""
+    import subprocess
+    import sys
+    from whisprrec_b200 import main as wr_main
+    pkl = str(tmp_path / 'BaseReader.pkl')
+    script = f'''
+import sys, types, pickle, numpy as np
+np.float_ = np.float64
+sys.path.insert(0, "/root/reference/src")
+from helpers.BaseReader import BaseReader
+args = types.SimpleNamespace(sep="\\t", path="{REF_DATA}", dataset="ml-100k", sample="random")
+with open("{pkl}", "wb") as f:
+    pickle.dump(BaseReader(args), f)
+'''
+    r = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    theirs = wr_main.load_corpus(pkl)
+    from whisprrec_b200.helpers.BaseReader import BaseReader
+    assert type(theirs) is BaseReader
+    mine = ml100k_corpus()
+    assert int(theirs.n_users) == int(mine.n_users) and int(theirs.n_items) == int(mine.n_items)
+    for ph in ('train', 'dev', 'test'):
+        assert (theirs.data_df[ph]['user_id'].to_numpy() == mine.data_df[ph]['user_id'].to_numpy()).all()
+        assert (theirs.data_df[ph]['item_id'].to_numpy() == mine.data_df[ph]['item_id'].to_numpy()).all()
+    for a, b in zip(theirs.history_csr(), mine.history_csr()):
+        assert (a == b).all()
+    for a, b in zip(theirs.train_csr(), mine.train_csr()):
+        assert (a == b).all()

@@ -39,6 +39,24 @@ def resolve(kind, name):
     raise NameError("name '{}' is not defined".format(name))
 
 
+class _CorpusUnpickler(pickle.Unpickler):
+    """Corpus caches written by the reference (`../data/<dataset>/BaseReader.pkl`, main.py:54-63) name its top-level
+    packages (`helpers.BaseReader.BaseReader`); they hold the same attributes, so they load as this package's reader."""
+
+    def find_class(self, module, name):
+        if module.split('.')[0] in ('helpers', 'models', 'utils') and not module.startswith(__package__):
+            try:
+                return getattr(importlib.import_module('.' + module, package=__package__), name)
+            except (ImportError, AttributeError):
+                pass
+        return super().find_class(module, name)
+
+
+def load_corpus(path):
+    with open(path, 'rb') as f:
+        return _CorpusUnpickler(f).load()
+
+
 def parse_global_args(parser):
     parser.add_argument('--gpu', type=str, default='0', help='Set CUDA_VISIBLE_DEVICES, default for CPU only')
     parser.add_argument('--verbose', type=int, default=logging.INFO, help='Logging Level, 0, 10, ..., 50')
@@ -132,8 +150,7 @@ def run(args, model_class, reader_class, runner_class, reader_name):
     corpus_path = os.path.join(args.path, args.dataset, reader_name + '.pkl')
     if not args.regenerate and os.path.exists(corpus_path):
         logging.info('Load corpus from {}'.format(corpus_path))
-        with open(corpus_path, 'rb') as f:
-            corpus = pickle.load(f)
+        corpus = load_corpus(corpus_path)
     else:
         corpus = reader_class(args)
         logging.info('Save corpus to {}'.format(corpus_path))
