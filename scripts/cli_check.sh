@@ -14,9 +14,17 @@ p = "$DATA/ml-1m/ml-1m.inter"
 if not os.path.exists(p):
     synthetic.write_inter(synthetic.ml1m_shaped(), p)
 PY
-COMMON="--model_name $MODEL --emb_size 64 --lr 1e-3 --l2 1e-6 --dataset ml-1m --path $DATA/ --epoch $EPOCHS --regenerate 1"
+HP="--lr 1e-3 --l2 1e-6"; [ "$MODEL" = LightGCN ] && HP="--lr 5e-4 --l2 0 --gcn_layers 2"     # what the golden logs were recorded with
+COMMON="--model_name $MODEL --emb_size 64 $HP --dataset ml-1m --path $DATA/ --epoch $EPOCHS --regenerate 1"
 PYTHONPATH=$ROOT python -m whisprrec_b200.main $COMMON --log_file /tmp/wr_cli/one.log --model_path /tmp/wr_cli/one.pt > /tmp/wr_cli/one.out 2>&1
 grep -E "Epoch|Test After" /tmp/wr_cli/one.out | sed 's/\[[0-9. ]*s\]//g' > /tmp/wr_cli/one.txt
+# the unmodified reference's log on the same file, where one was recorded (tests/golden/ml1m_shaped_reference_log*.txt)
+GOLD=$ROOT/tests/golden/ml1m_shaped_reference_log.txt
+[ "$MODEL" = LightGCN ] && GOLD=$ROOT/tests/golden/ml1m_shaped_reference_log_lightgcn.txt
+if [ "$EPOCHS" = 3 ] && [ -f "$GOLD" ]; then
+  if diff -q <(grep -v '^#' "$GOLD" | tr -s ' ' | sed 's/ *$//') <(tr -s ' ' < /tmp/wr_cli/one.txt | sed 's/ *$//') > /dev/null; then
+    echo "cli_check ok: equals the reference's log"; else echo "cli_check: differs from the reference's log"; fi
+fi
 if [ "$NGPU" -gt 1 ]; then
   PYTHONPATH=$ROOT python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29577 \
       -m whisprrec_b200.main $COMMON --log_file /tmp/wr_cli/multi.log --model_path /tmp/wr_cli/multi.pt > /tmp/wr_cli/multi.out 2>&1
