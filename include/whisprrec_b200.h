@@ -86,10 +86,14 @@ int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, fl
                      float eps, float step_size, float bc2_sqrt, const float *dev_scalars, void *stream);
 
 /* wr_bprmf_step: one whole iteration of BaseRunner.fit for BPRMF (BaseRunner.py:196-199: zero_grad, predict,
- * backward, Adam.step) on the fused table P = [U; I] ([n_users + n_items, D], M / V / G alike).  Tables of up to
- * 8 Mi elements take ONE cooperative launch (parameter loads issued first, BPR forward+backward, grid barrier,
- * Adam+L2 with the gradient re-zeroed); larger ones are wr_bpr_fwd_bwd followed by wr_adam_l2_sweep.  Same
- * arithmetic either way.  loss_out[0] is overwritten.
+ * backward, Adam.step) on the fused table P = [U; I] ([n_users + n_items, D], M / V / G alike).  Three forms of the
+ * same arithmetic, chosen by size:
+ *   - the Adam state fits in the SMs' shared memory (48 B per 4 parameters per array, ~29 MB over 148 SMs), the three id
+ *     rows are equally spaced and B <= 128 x SMs: one launch of the resident kernel (csrc/epoch_kernel.cu) -- one CTA
+ *     per SM, P / M / V slices in shared memory, BPR phase, grid barrier, Adam+L2 with the gradient re-zeroed;
+ *   - tables of up to 8 Mi elements: one cooperative launch with the state streamed through L2;
+ *   - larger: wr_bpr_fwd_bwd followed by wr_adam_l2_sweep.
+ * loss_out[0] is overwritten.  dev_scalars != NULL selects the second / third form (graph replay).
  */
 int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
                   const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
@@ -98,11 +102,23 @@ int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, c
 
 /* wr_bprmf_epoch: the step loop of BaseRunner.fit (BaseRunner.py:194-200) in one call: batch s is columns
  * [s * batch, min(N, (s + 1) * batch)) of ids[3][N] (DEVICE, rows user / pos / neg), Adam's t runs from adam_t0 + 1,
- * losses[s] (DEVICE, ceil(N / batch) floats) receives the loss of step s.  Launches only; nothing is synchronised.
+ * losses[s] (DEVICE, ceil(N / batch) floats) receives the loss of step s.  When the tables qualify for the resident
+ * kernel (see wr_bprmf_step) the whole epoch is ONE launch: the Adam moments stay in shared memory from the first step
+ * to the last, the next steps' ids are staged by a helper warp per CTA while the current step runs, two grid barriers
+ * per step; otherwise one wr_bprmf_step per batch.  scratch: 16-byte aligned DEVICE memory of
+ * wr_bprmf_epoch_scratch_bytes(N, batch) bytes (the per-step descriptors: batch slice + Adam scalars of that step,
+ * evaluated in double on the host as torch does); NULL forces the per-step form.  Launches only; nothing is synchronised.
  */
+size_t wr_bprmf_epoch_scratch_bytes(int64_t N, int64_t batch);
+/* Profiling aid: with a DEVICE buffer of 8 x uint64 per step set here (NULL switches it off), every later launch of the
+ * resident kernel records %globaltimer stamps per step: [0] step start, [1] BPR phase done, [2] past grid barrier 1,
+ * [3] Adam phase done, [4] past grid barrier 2 (CTA 0), [5] descriptor seen by the poller, [6] ids staged (CTA 0),
+ * [7] completion word written (streaming).  scripts/prof_resident.py prints the breakdown. */
+int wr_debug_epoch_trace(uint64_t *dev_trace, uint64_t *dev_cta_trace /* nullable: [step][CTA][4], both barriers of every CTA */);
 int wr_bprmf_epoch(float *P, float *M, float *V, float *G, const int64_t *ids, int64_t N, int64_t batch, int D,
                    int64_t n_users, int64_t n_items, float gamma, double lr, float l2, double beta1, double beta2,
-                   float eps, int64_t adam_t0, float *losses, void *ws, void *stream);
+                   float eps, int64_t adam_t0, float *losses, void *scratch, size_t scratch_bytes, void *ws,
+                   void *stream);
 
 /* wr_bprmf_step_host: the same iteration fed from the HOST, i.e. utils.batch_to_gpu (utils/utils.py:33-37) +
  * the step + `loss.detach().cpu()` (BaseRunner.py:200).  host_ids: pinned [3, B] int64 (user, pos, neg rows);
@@ -114,15 +130,23 @@ int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, float *host_lo
                        double beta1, double beta2, float eps, float step_size, float bc2_sqrt, float *loss_out,
                        void *ws, void *stream, int sync);
 
-/* wr_bprmf_ctx_*: the host-fed iteration without a copy engine or a stream synchronisation in the loop.  The context
- * keeps the table pointers and hyper-parameters; wr_bprmf_ctx_step takes the batch ids in MAPPED PINNED host memory
- * ([3, B] int64; e.g. a torch `.pin_memory()` tensor), launches the step kernel on them directly (the H2D transfer is
- * the kernel's own loads over PCIe) and waits on a sequence word the kernel raises in mapped host memory:
- * wait = 1 returns when the whole step is complete (raised by the last CTA to leave); wait = 2 returns as soon as the
- * batch loss is out, which is before the Adam phase, so the host prepares and launches the next step while the update
- * of this one completes (the stream still orders the kernels); wait = 0 does not wait.  adam_t: Adam's step count t
- * (1, 2, ...); step_size / bias correction are evaluated here in double exactly as torch does.  The id buffer may be
- * reused once the call has returned with wait != 0.  Returns WR_E_ALIGN if host_ids is not mapped pinned memory.
+/* wr_bprmf_ctx_*: host-fed training without a launch, a copy-engine hop or a stream synchronisation per step
+ * (utils.batch_to_gpu, utils/utils.py:33-37 + BaseRunner.py:196-200 for a loop whose batches are produced on the host).
+ * The first wr_bprmf_ctx_step launches the RESIDENT kernel (csrc/epoch_kernel.cu, streaming mode) on the context's own
+ * stream; from then on a step is: the host writes a 32-byte descriptor (id buffer, rows, Adam scalars of step adam_t,
+ * evaluated in double exactly as torch does) into a ring in mapped pinned memory; a poller warp on the GPU picks it up,
+ * helper warps pull the ids out of pinned host memory (that is the H2D transfer), the step runs, and the loss and two
+ * sequence words are stored back into mapped host memory (the D2H transfer):
+ *   wait = 1  returns when the whole step is complete (every parameter updated);
+ *   wait = 2  returns as soon as the batch loss is out (the Adam phase may still be running);
+ *   wait = 0  returns at once; up to 16 steps may be in flight, wr_bprmf_ctx_wait(step, ...) collects a loss later
+ *             (step = 0 for the context's first wr_bprmf_ctx_step, 1 for the next, ...).
+ * host_ids: [3, B] int64.  Mapped pinned memory (torch `.pin_memory()`) is read in place and must stay untouched until
+ * the step is complete; anything else is first copied into the context's own pinned ring (the collate copy).
+ * The kernel writes M / V back and leaves when wr_bprmf_ctx_sync / wr_bprmf_ctx_destroy close it, or by itself after 5 ms
+ * without a new batch (the next step relaunches it).  WHILE IT IS RESIDENT THE ADAM MOMENTS LIVE IN SHARED MEMORY: call
+ * wr_bprmf_ctx_sync before anything else reads M / V or writes the tables.  Tables that do not qualify for the resident
+ * kernel fall back to one launch per step (ids must then be mapped pinned memory: WR_E_ALIGN otherwise).
  */
 typedef struct wr_bprmf_ctx wr_bprmf_ctx;
 int wr_bprmf_ctx_create(float *P, float *M, float *V, float *G, int64_t n_users, int64_t n_items, int D, float gamma,
@@ -130,6 +154,8 @@ int wr_bprmf_ctx_create(float *P, float *M, float *V, float *G, int64_t n_users,
                         wr_bprmf_ctx **out);
 int wr_bprmf_ctx_step(wr_bprmf_ctx *ctx, const int64_t *host_ids, int64_t B, int64_t adam_t, int wait,
                       float *host_loss_out);
+int wr_bprmf_ctx_wait(wr_bprmf_ctx *ctx, int64_t step, int wait, float *host_loss_out);
+int wr_bprmf_ctx_sync(wr_bprmf_ctx *ctx);
 int wr_bprmf_ctx_destroy(wr_bprmf_ctx *ctx);
 
 /* ---- LightGCN propagation ------------------------------------------------------------------------------

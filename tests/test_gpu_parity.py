@@ -198,6 +198,110 @@ def test_bprmf_epoch_call_equals_the_step_loop(ws):
     assert ws.status() == 0
 
 
+def _two_kernel_epoch(P0, ids, B, nU, t0, lr, l2, ws):
+    """The same steps through the two independent kernels (wr_bpr_fwd_bwd + wr_adam_l2_sweep)."""
+    P = dv(P0)
+    M, V, G = (torch.zeros_like(P) for _ in range(3))
+    N = ids.shape[1]
+    steps = (N + B - 1) // B
+    losses = torch.zeros(steps, device=DEV)
+    for s in range(steps):
+        lo, hi = s * B, min(N, (s + 1) * B)
+        _lib.bpr_fwd_bwd(P[:nU], P[nU:], ids[0, lo:hi].contiguous(), ids[1, lo:hi].contiguous(),
+                         ids[2, lo:hi].contiguous(), G[:nU], G[nU:], losses[s:s + 1], ws)
+        _lib.adam_l2_sweep(P, M, V, G, t0 + s + 1, lr, l2)
+    return P, M, V, losses
+
+
+@pytest.mark.parametrize('D,B,N', [(64, 2048, 20000), (16, 100, 1234), (32, 2048, 6000), (128, 4096, 9000),
+                                   (256, 2048, 5000), (64, 1, 7), (64, 18944, 40000)])
+def test_resident_epoch_kernel_vs_two_kernel_steps(D, B, N, ws):
+    """csrc/epoch_kernel.cu (one launch per epoch: state in shared memory, helper-staged ids, two grid barriers per
+    step) against wr_bpr_fwd_bwd + wr_adam_l2_sweep issued step by step: losses of every step, P, M, V after the
+    epoch; then a second resident epoch continues from the state the first one wrote back."""
+    rng = np.random.RandomState(D + B)
+    nU, nI = 700, 900
+    P0 = (rng.randn(nU + nI, D) * 0.1).astype(np.float32)
+    ids = dv(np.stack([(nU * rng.rand(N) ** 2).astype(np.int64), rng.randint(0, nI, N), rng.randint(1, nI, N)]).astype(np.int64))
+    Pa = dv(P0)
+    Ma, Va, Ga = (torch.zeros_like(Pa) for _ in range(3))
+    steps = (N + B - 1) // B
+    la = torch.full((steps,), -1.0, device=DEV)
+    assert _lib.bprmf_epoch(Pa, Ma, Va, Ga, ids, B, nU, 3, 1e-3, 1e-6, la, ws) == steps
+    Pb, Mb, Vb, lb = _two_kernel_epoch(P0, ids, B, nU, 3, 1e-3, 1e-6, ws)
+    assert_close(host(la), host(lb), 'losses', rtol=2e-6)
+    assert_close(host(Pa), host(Pb), 'P', rtol=1e-5, atol_scale=2e-6)
+    assert_close(host(Ma), host(Mb), 'M', rtol=1e-5, atol_scale=2e-6)
+    assert_close(host(Va), host(Vb), 'V', rtol=1e-5, atol_scale=2e-6)
+    assert float(Ga.abs().max()) == 0.0
+    # a second epoch from the written-back state equals the per-step form of the same call
+    Pc, Mc, Vc, Gc = Pa.clone(), Ma.clone(), Va.clone(), Ga.clone()
+    lc = torch.zeros(steps, device=DEV)
+    _lib.bprmf_epoch(Pa, Ma, Va, Ga, ids, B, nU, 3 + steps, 1e-3, 1e-6, la, ws)
+    _lib.bprmf_epoch(Pc, Mc, Vc, Gc, ids, B, nU, 3 + steps, 1e-3, 1e-6, lc, ws, resident=False)
+    assert_close(host(la), host(lc), 'losses (2nd epoch)', rtol=2e-6)
+    assert_close(host(Pa), host(Pc), 'P (2nd epoch)', rtol=1e-5, atol_scale=2e-6)
+    assert ws.status() == 0
+
+
+def test_resident_epoch_kernel_reports_bad_ids(ws):
+    rng = np.random.RandomState(1)
+    nU, nI, D, N, B = 50, 60, 64, 300, 128
+    P = dv((rng.randn(nU + nI, D) * 0.1).astype(np.float32))
+    M, V, G = (torch.zeros_like(P) for _ in range(3))
+    ids = np.stack([rng.randint(0, nU, N), rng.randint(0, nI, N), rng.randint(1, nI, N)]).astype(np.int64)
+    ids[1, 200] = nI                                          # one positive outside its table: the row is skipped
+    losses = torch.zeros(3, device=DEV)
+    _lib.bprmf_epoch(P, M, V, G, dv(ids), B, nU, 0, 1e-3, 0.0, losses, ws)
+    assert ws.status() & 1
+    assert np.isfinite(host(losses)).all() and np.isfinite(host(P)).all()
+
+
+def test_host_fed_stream_pipelined_pageable_and_idle_relaunch(ws):
+    """wr_bprmf_ctx_* on the resident kernel: 40 steps pushed without waiting (the 16-slot ring wraps, flow control),
+    pageable id buffers (collated into the context's pinned ring), losses collected afterwards; a pause longer than
+    the kernel's idle limit (it writes its state back and leaves; the next push relaunches it); then the device-fed
+    step continues from the same state.  Reference: the same batches through wr_bprmf_step."""
+    import time
+    corpus = ml100k_corpus()
+    models = []
+    for _ in range(2):
+        args = model_args(BPRMF, lr=1e-3, l2=1e-6)
+        utils.init_seed(3407)
+        m = BPRMF(args, corpus).to(DEV)
+        m.fuse()
+        m.optimizer = BaseRunner(args)._build_optimizer(m)
+        models.append(m)
+    rng = np.random.RandomState(11)
+    batches = []
+    for step in range(44):
+        B = 2048 if step % 7 else 333
+        batches.append(np.stack([rng.randint(0, corpus.n_users, B), rng.randint(1, corpus.n_items, B),
+                                 rng.randint(1, corpus.n_items, B)]).astype(np.int64))
+    ref = []
+    for ids in batches:
+        d = dv(ids)
+        ref.append(float(models[1].train_step({'user_id': d[0], 'pos_item': d[1], 'neg_items': d[2]})))
+    for k, ids in enumerate(batches[:40]):
+        models[0].train_step_host(torch.from_numpy(ids), wait=0)          # pageable
+        if k >= 8:
+            assert models[0].host_step_loss(k - 8) == pytest.approx(ref[k - 8], rel=2e-6)
+    for k in range(32, 40):
+        assert models[0].host_step_loss(k) == pytest.approx(ref[k], rel=2e-6)
+    time.sleep(0.05)                                                      # > idle limit: the kernel has left
+    pinned = [torch.from_numpy(ids).pin_memory() for ids in batches[40:43]]
+    for k, pt in zip(range(40, 43), pinned):
+        assert models[0].train_step_host(pt) == pytest.approx(ref[k], rel=2e-6)      # relaunch, pinned in place
+    d = dv(batches[43])
+    last = float(models[0].train_step({'user_id': d[0], 'pos_item': d[1], 'neg_items': d[2]}))   # closes the stream first
+    assert last == pytest.approx(ref[43], rel=2e-6)
+    for name in ('P', 'M', 'V'):
+        assert_close(host(getattr(models[0].tables, name)), host(getattr(models[1].tables, name)), name, rtol=1e-5,
+                     atol_scale=2e-6)
+    assert float(models[0].tables.G.abs().max()) == 0.0
+    assert models[0].tables.ws.status() == 0
+
+
 @pytest.mark.parametrize('D', [16, 32, 64, 128, 256, 48, 8])
 @pytest.mark.parametrize('B', [1, 31, 480, 2048])
 def test_bpr_fwd_bwd_vs_oracle(D, B, ws):

@@ -60,8 +60,10 @@ def test_argument_errors_need_no_gpu():
     small, big = lib.wr_neg_sample_scratch_bytes(10_000, 3706), lib.wr_neg_sample_scratch_bytes(1_000_000, 3706)
     assert 0 < small < big and big > 1_000_000 * 12
     assert lib.wr_neg_sample_mt19937(None, 0, 10, 16, 4, 100, 16, 16, 16, None, None, 16, 1 << 20, 16, None) == -1
-    assert lib.wr_bprmf_epoch(16, 16, 16, 16, None, 100, 10, 8, 4, 4, 1e-10, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, 16, 16, None) == -1
-    assert lib.wr_bprmf_epoch(16, 16, 16, 16, 16, 100, 0, 8, 4, 4, 1e-10, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, 16, 16, None) == -2
+    assert lib.wr_bprmf_epoch(16, 16, 16, 16, None, 100, 10, 8, 4, 4, 1e-10, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, 16, None, 0, 16, None) == -1
+    assert lib.wr_bprmf_epoch(16, 16, 16, 16, 16, 100, 0, 8, 4, 4, 1e-10, 1e-3, 0.0, 0.9, 0.999, 1e-8, 0, 16, None, 0, 16, None) == -2
+    assert lib.wr_bprmf_epoch_scratch_bytes(100, 10) == 10 * 32 and lib.wr_bprmf_epoch_scratch_bytes(0, 10) == 0
+    assert lib.wr_bprmf_ctx_wait(None, 0, 1, None) == -1 and lib.wr_bprmf_ctx_sync(None) == -1
     assert lib.wr_allgather_shards(None, 16, 64, None) == -1
     assert lib.wr_inbox_scatter(None, 16, 16, 2, 100, 64, None) == -1
     assert lib.wr_inbox_scatter(16, 16, 16, 9, 100, 64, None) == -2          # more ranks than one box holds

@@ -30,13 +30,17 @@ SIGNATURES = {
     'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f64, _f64, _f32, _f32, _f32, _p, _p]),
     'wr_bprmf_step': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32, _f32,
                              _f32, _p, _p, _p, _p]),
+    'wr_bprmf_epoch_scratch_bytes': (_sz, [_i64, _i64]),
+    'wr_debug_epoch_trace': (_int, [_p, _p]),
     'wr_bprmf_epoch': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _i64, _i64, _f32, _f64, _f32, _f64, _f64, _f32, _i64,
-                              _p, _p, _p]),
+                              _p, _p, _sz, _p, _p]),
     'wr_bprmf_step_host': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32,
                                   _f32, _f32, _p, _p, _p, _int]),
     'wr_bprmf_ctx_create': (_int, [_p, _p, _p, _p, _i64, _i64, _int, _f32, _f64, _f32, _f64, _f64, _f32, _p, _p,
                                    _c.POINTER(_p)]),
     'wr_bprmf_ctx_step': (_int, [_p, _p, _i64, _i64, _int, _c.POINTER(_f32)]),
+    'wr_bprmf_ctx_wait': (_int, [_p, _i64, _int, _c.POINTER(_f32)]),
+    'wr_bprmf_ctx_sync': (_int, [_p]),
     'wr_bprmf_ctx_destroy': (_int, [_p]),
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
     'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
@@ -198,14 +202,19 @@ def bprmf_step(P, M, V, G, user, pos, neg, n_users, step, lr, l2, loss_out, ws, 
 
 
 def bprmf_epoch(P, M, V, G, ids, batch, n_users, adam_t0, lr, l2, losses, ws, beta1=0.9, beta2=0.999, eps=1e-8,
-                gamma=1e-10):
-    """Every step of an epoch from one call; ids: contiguous int64 [3, N] device tensor in batch order."""
+                gamma=1e-10, resident=True):
+    """Every step of an epoch from one call; ids: contiguous int64 [3, N] device tensor in batch order.  Tables that
+    fit the SMs' shared memory run as ONE resident launch (resident=False forces one launch per step)."""
     N = ids.shape[1]
     if ids.dim() != 2 or ids.shape[0] != 3 or losses.numel() < (N + batch - 1) // batch:
         raise WhisprError('ids must be [3, N] and losses hold one float per step')
-    check(load().wr_bprmf_epoch(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), ptr(ids, I64), N, batch, P.shape[1],
-                                n_users, P.shape[0] - n_users, gamma, lr, l2, beta1, beta2, eps, adam_t0,
-                                ptr(losses, F32), ws.ptr, stream_ptr()))
+    lib = load()
+    nbytes = lib.wr_bprmf_epoch_scratch_bytes(N, batch) if resident else 0
+    scratch = torch.empty(nbytes // 16 * 2 + 2, dtype=torch.int64, device=P.device) if nbytes else None   # 16 B aligned
+    check(lib.wr_bprmf_epoch(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), ptr(ids, I64), N, batch, P.shape[1],
+                             n_users, P.shape[0] - n_users, gamma, lr, l2, beta1, beta2, eps, adam_t0,
+                             ptr(losses, F32), None if scratch is None else scratch.data_ptr(), nbytes, ws.ptr,
+                             stream_ptr()))
     return (N + batch - 1) // batch
 
 
@@ -227,24 +236,40 @@ def bprmf_step_host(host_ids, dev_ids, host_loss, P, M, V, G, n_users, step, lr,
 
 
 class BprmfContext:
-    """wr_bprmf_ctx: the host-fed BPRMF step (pinned ids in, loss out) with everything constant bound once."""
+    """wr_bprmf_ctx: host-fed BPRMF training on the resident kernel (pinned or pageable ids in, loss out)."""
 
     def __init__(self, P, M, V, G, n_users, lr, l2, ws, beta1=0.9, beta2=0.999, eps=1e-8, gamma=1e-10):
         self._keep = (P, M, V, G, ws)
         self._h = _p()
         self._loss = _f32(0.0)
-        self._step = load().wr_bprmf_ctx_step
-        check(load().wr_bprmf_ctx_create(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), n_users,
-                                         P.shape[0] - n_users, P.shape[1], gamma, lr, l2, beta1, beta2, eps, ws.ptr,
-                                         stream_ptr(), ctypes.byref(self._h)))
+        lib = load()
+        self._step, self._wait = lib.wr_bprmf_ctx_step, lib.wr_bprmf_ctx_wait
+        self.steps = 0
+        check(lib.wr_bprmf_ctx_create(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), n_users,
+                                      P.shape[0] - n_users, P.shape[1], gamma, lr, l2, beta1, beta2, eps, ws.ptr,
+                                      stream_ptr(), ctypes.byref(self._h)))
 
     def step(self, host_ids_ptr, B, adam_t, wait=1):
-        """host_ids_ptr: address of a pinned [3, B] int64 buffer.  wait: 1 = until the step is complete, 2 = until
-        the loss is out (the Adam phase may still be running), 0 = not at all.  Returns the batch loss (float)."""
+        """host_ids_ptr: address of a [3, B] int64 host buffer.  wait: 1 = until the step is complete, 2 = until the
+        loss is out (the Adam phase may still be running), 0 = not at all (collect with wait()).  Returns the batch
+        loss (float; meaningless for wait=0)."""
         rc = self._step(self._h, host_ids_ptr, B, adam_t, int(wait), ctypes.byref(self._loss))
         if rc:
             check(rc)
+        self.steps += 1
         return self._loss.value
+
+    def wait(self, step, wait=1):
+        """Loss of the context's `step`-th step (0-based), once it is complete (1) / its loss is out (2)."""
+        rc = self._wait(self._h, step, int(wait), ctypes.byref(self._loss))
+        if rc:
+            check(rc)
+        return self._loss.value
+
+    def sync(self):
+        """Close the resident kernel: M / V are back in global memory and the caller's stream is ordered behind it."""
+        if self._h:
+            check(load().wr_bprmf_ctx_sync(self._h))
 
     def close(self):
         if self._h:

@@ -6,6 +6,8 @@
 #include "../../include/whisprrec_b200.h"
 
 #define WR_MAX_PARTIAL_BLOCKS 2048
+#define WR_EP_PART_DEPTH 4      // steps whose per-CTA loss partials may be waiting for their reduction
+#define WR_EP_MAX_GRID 256      // CTAs of the resident kernel (one per SM)
 
 // Device scratch block handed in by the caller (wr_workspace_bytes()).
 struct WrWorkspace {
@@ -14,6 +16,16 @@ struct WrWorkspace {
     float norms[4];                            // EmbLoss: ||U0_b||, ||P0_b||, ||N0_b||
     float partial[3 * WR_MAX_PARTIAL_BLOCKS];  // per-block partial sums, summed in block order (deterministic)
     double dpartial[2 * 8 * 64];               // wr_metrics
+    // ---- resident BPRMF kernel (epoch_kernel.cu); every word is left zero by the last CTA to leave ----
+    uint32_t ep_pad0;
+    uint32_t ep_pad1;
+    uint32_t ep_abort;                         // a wait gave up: every CTA leaves
+    uint32_t ep_depart;                        // departures (workers + helper of every CTA)
+    uint32_t ep_loss_flag[WR_EP_PART_DEPTH];   // step + 1 of the last loss reduced out of each partial slot
+    float ep_partial[WR_EP_PART_DEPTH * WR_EP_MAX_GRID];
+    uint32_t ep_fetched[16];                   // streaming: helper warps that have copied their piece of step s's ids, at
+                                               // [(s - first) % 16]; cumulative per slot (helpers run < 16 steps apart)
+    uint32_t ep_flag[WR_EP_MAX_GRID * 32];     // grid barrier: CTA c's arrival number at [32 c] (one 128-byte line each)
 };
 
 #define WR_CHECK_LAUNCH()                        \
@@ -86,6 +98,70 @@ __device__ __forceinline__ float4 fma4(float s, float4 x, float4 a) {
     return make_float4(fmaf(s, x.x, a.x), fmaf(s, x.y, a.y), fmaf(s, x.z, a.z), fmaf(s, x.w, a.w));
 }
 
+// ---- pointwise math shared by the step kernels ----
+__device__ __forceinline__ void bpr_pointwise(float sp, float sn, float gamma, float coef, float &loss, float &c) {
+    // utils/loss.py:38: -log(gamma + sigmoid(pos - neg)); d/ds+ = -(sig (1-sig)) / (gamma + sig)
+    const float x = sp - sn;
+    const float sig = 1.0f / (1.0f + expf(-x));
+    loss = -logf(gamma + sig);
+    c = -(sig * (1.0f - sig)) / (gamma + sig) * coef;
+}
+
+struct AdamScalars {
+    float l2, w1, beta2, w2, eps, step_size, bc2_sqrt;
+};
+
+__device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g, const AdamScalars &s) {
+    g = fmaf(s.l2, p, g);                    // grad.add(param, alpha=weight_decay)
+    m = fmaf(s.w1, g - m, m);                // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(s.w2 * g, g, v * s.beta2);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+    const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
+    p = p + (-s.step_size * m) / denom;      // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+// ~1 ulp quotient / square root from the MUFU approximations plus one Newton step: the IEEE sequences of `/` and sqrtf
+// cost ~25 instructions each, which makes a cache-resident Adam phase issue-bound (scripts/prof_resident.py).
+__device__ __forceinline__ float div_nr(float n, float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    const float q = n * r;
+    return fmaf(fmaf(-d, q, n), r, q);
+}
+__device__ __forceinline__ float sqrt_nr(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    const float s = x * r;
+    const float t = fmaf(fmaf(-s, s, x), 0.5f * r, s);
+    return x > 1e-37f ? t : 0.f;             // 0 (r = inf) and denormals
+}
+// adam_elem with div_nr / sqrt_nr and the bias-correction division folded into a multiplication (inv_bc2 = 1 / bc2_sqrt)
+__device__ __forceinline__ void adam_elem_nr(float &p, float &m, float &v, float g, const AdamScalars &s, float inv_bc2) {
+    g = fmaf(s.l2, p, g);
+    m = fmaf(s.w1, g - m, m);
+    v = fmaf(s.w2 * g, g, v * s.beta2);
+    const float denom = fmaf(sqrt_nr(v), inv_bc2, s.eps);
+    p = p + div_nr(-s.step_size * m, denom);
+}
+
+// ---- scoped loads / stores for the in-kernel meeting points ----
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // The last block to arrive returns true (after all other blocks' prior global writes are visible).
 __device__ __forceinline__ bool last_block_arrives(uint32_t *ticket, bool *smem_flag) {
     __syncthreads();
@@ -110,6 +186,11 @@ struct RowGroup {
     __device__ static __forceinline__ void load(const float *row, int sub, float4 (&r)[VPL]) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) r[v] = ldg4(row + 4 * (sub + v * LPR));
+    }
+    // tables that the same kernel (or a peer) rewrites: read through L2, never the non-coherent path
+    __device__ static __forceinline__ void load_cg(const float *row, int sub, float4 (&r)[VPL]) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) r[v] = __ldcg(reinterpret_cast<const float4 *>(row + 4 * (sub + v * LPR)));
     }
     __device__ static __forceinline__ void zero(float4 (&r)[VPL]) {
 #pragma unroll

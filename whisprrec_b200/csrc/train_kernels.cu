@@ -24,14 +24,6 @@ struct BprParamsT {
 };
 using BprParams = BprParamsT<LocalTabs>;
 
-__device__ __forceinline__ void bpr_pointwise(float sp, float sn, float gamma, float coef, float &loss, float &c) {
-    // utils/loss.py:38: -log(gamma + sigmoid(pos - neg)); d/ds+ = -(sig (1-sig)) / (gamma + sig)
-    const float x = sp - sn;
-    const float sig = 1.0f / (1.0f + expf(-x));
-    loss = -logf(gamma + sig);
-    c = -(sig * (1.0f - sig)) / (gamma + sig) * coef;
-}
-
 // Deterministic epilogue shared by the loss kernels: per-block partials, summed in block order by the last block.
 __device__ __forceinline__ void finish_loss(float local, float *red, bool *flag, WrWorkspace *ws, int slot,
                                             float B, float *loss_out, int accumulate) {
@@ -256,18 +248,6 @@ __global__ void __launch_bounds__(256) embloss_scatter_kernel(EmbParamsT<TABS> p
 // ------------------------------------------------------------------------------------------------------
 // Dense Adam with coupled L2 and fused zero_grad: one streaming pass, 32 B of traffic per parameter.
 // ------------------------------------------------------------------------------------------------------
-struct AdamScalars {
-    float l2, w1, beta2, w2, eps, step_size, bc2_sqrt;
-};
-
-__device__ __forceinline__ void adam_elem(float &p, float &m, float &v, float g, const AdamScalars &s) {
-    g = fmaf(s.l2, p, g);                    // grad.add(param, alpha=weight_decay)
-    m = fmaf(s.w1, g - m, m);                // exp_avg.lerp_(grad, 1 - beta1)
-    v = fmaf(s.w2 * g, g, v * s.beta2);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
-    const float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
-    p = p + (-s.step_size * m) / denom;      // param.addcdiv_(exp_avg, denom, value=-step_size)
-}
-
 template <int UNROLL>
 __global__ void __launch_bounds__(256) adam_sweep_kernel(float4 *__restrict__ P, float4 *__restrict__ M,
                                                           float4 *__restrict__ V, float4 *__restrict__ G,
@@ -370,12 +350,6 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(float *G, const i
 // G) while those loads are in flight, meets at a grid barrier (cooperative launch: all CTAs are resident),
 // and finishes with the Adam+L2 update of the elements it already holds -- G comes back as L2 hits.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // Cross-GPU synchronisation state of the single-launch step on row-sharded tables (world > 1).
 struct StepSync {
     uint32_t *flags[WR_MAX_WORLD];  // rank g's [2][WR_MAX_WORLD] words: [0][r] = r's gradients have landed (epoch e),
@@ -383,22 +357,7 @@ struct StepSync {
     float *slots[WR_MAX_WORLD];     // rank g's [2 (epoch parity)][WR_MAX_WORLD] loss shares
     int world, rank;
     uint32_t epoch;                 // the step number: 1, 2, 3, ... (the same on every rank)
-    uint32_t *notify;               // optional word in mapped host memory, set to notify_value ...
-    uint32_t notify_value;
-    int notify_early;               // ... as soon as the loss is out (1) / when the whole step is complete (0)
 };
-
-__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 template <int LPR, int VPL, class TABS>
 __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, float4 *P, float4 *M, float4 *V, float4 *G,
@@ -452,10 +411,10 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
                         (uint64_t)j < (uint64_t)p.n_items;
         if (valid && !ok && sub == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
         float4 ue[VPL], pe[VPL], ne[VPL];
-        if (ok) {
-            RG::load(p.tabs.urow(u, D), sub, ue);
-            RG::load(p.tabs.irow(i, D), sub, pe);
-            RG::load(p.tabs.irow(j, D), sub, ne);
+        if (ok) {     // P is rewritten by phase 2 (and by the peers' Adam phases): coherent loads, not ld.global.nc
+            RG::load_cg(p.tabs.urow(u, D), sub, ue);
+            RG::load_cg(p.tabs.irow(i, D), sub, pe);
+            RG::load_cg(p.tabs.irow(j, D), sub, ne);
         } else {
             RG::zero(ue);
             RG::zero(pe);
@@ -536,10 +495,6 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
         }
         if (threadIdx.x == 0) {
             p.loss_out[0] = p.accumulate_loss ? p.loss_out[0] + loss_sum : loss_sum;
-            if (sy.notify && sy.notify_early) {   // the host may read the loss (and reuse the id buffer) during the Adam phase
-                __threadfence_system();
-                st_release_sys(sy.notify, sy.notify_value);
-            }
         }
     } else if (sy.world > 1) {
         if (threadIdx.x == 0) {
@@ -580,7 +535,7 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
             G[i2] = z;
         }
     }
-    const bool announce = sy.world > 1 || (sy.notify && !sy.notify_early);
+    const bool announce = sy.world > 1;
     if (announce) __syncthreads();              // the departure below speaks for the whole CTA's stores
     if (threadIdx.x == 0) {
         if (announce) __threadfence();
@@ -588,10 +543,6 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
         if (t == gridDim.x - 1) {
             p.ws->ticket[3] = 0;
             p.ws->ticket[4] = 0;
-            if (sy.notify && !sy.notify_early) {    // every CTA has left: the step is complete (their departures were
-                __threadfence_system();            // fenced), tell the host
-                st_release_sys(sy.notify, sy.notify_value);
-            }
             if (sy.world > 1) {                 // this rank's rows of P are final: peers may gather them for step e+1
                 __threadfence_system();
                 for (int g = 0; g < sy.world; ++g) st_release_sys(sy.flags[g] + WR_MAX_WORLD + sy.rank, sy.epoch);
@@ -634,6 +585,11 @@ static int launch_bpr(BprParamsT<TABS> &p, int D, cudaStream_t st) {
 }  // namespace wr
 
 using namespace wr;
+
+int wr_bprmf_step_impl(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
+                       const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
+                       double beta1, double beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
+                       float *loss_out, void *ws, void *stream);
 
 int wr_check_shards(const wr_shards *s) {
     if (s->world < 1 || s->world > WR_MAX_WORLD || s->rank < 0 || s->rank >= s->world) return WR_E_SIZE;
@@ -874,14 +830,35 @@ static int dispatch_step_fused(BprParamsT<TABS> &bp, int D, float *P, float *M, 
 // step is bound by launch / DRAM latency); larger ones stream at HBM bandwidth through the two-kernel path.
 #define WR_FUSED_STEP_MAX_ELEMS ((int64_t)8 << 20)
 
+int wr_epoch_single_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
+                         const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
+                         double beta1, double beta2, float eps, float step_size, float bc2_sqrt, float *loss_out,
+                         void *ws, cudaStream_t st);      // epoch_kernel.cu
+
 extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
                              const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma,
                              float l2, double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
                              const float *dev_scalars, float *loss_out, void *ws, void *stream) {
     if (!P || !M || !V || !G || !user || !pos || !neg || !loss_out || !ws) return WR_E_NULL;
-    if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    if (B <= 0 || n_users <= 0 || n_items <= 0 || n_users >= INT32_MAX || n_items >= INT32_MAX) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
     if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
+    if (!dev_scalars) {
+        // tables whose Adam state fits in the SMs' shared memory: one launch of the resident kernel (epoch_kernel.cu)
+        const int rc = wr_epoch_single_step(P, M, V, G, user, pos, neg, B, D, n_users, n_items, gamma, l2, beta1, beta2,
+                                            eps, step_size, bc2_sqrt, loss_out, ws, (cudaStream_t)stream);
+        if (rc != -1000) return rc;
+    }
+    return wr_bprmf_step_impl(P, M, V, G, user, pos, neg, B, D, n_users, n_items, gamma, l2, beta1, beta2, eps, step_size,
+                              bc2_sqrt, dev_scalars, loss_out, ws, stream);
+}
+
+// The per-step launches: one cooperative launch (parameter loads first, BPR, grid barrier, Adam) for tables of up to
+// 8 Mi elements, two kernels beyond that.
+int wr_bprmf_step_impl(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
+                       const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
+                       double beta1, double beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
+                       float *loss_out, void *ws, void *stream) {
     const int64_t n_elems = (n_users + n_items) * D;
     const bool fused_shape = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
     if (!fused_shape || n_elems > WR_FUSED_STEP_MAX_ELEMS) {
@@ -951,142 +928,6 @@ extern "C" int wr_bprmf_step_host(const int64_t *host_ids, int64_t *dev_ids, flo
     if (e != cudaSuccess) return (int)e;
     if (sync) e = cudaStreamSynchronize(st);
     return (int)e;
-}
-
-// A whole epoch of BPRMF steps launched from one call (BaseRunner.fit's loop, BaseRunner.py:194-200): batches are
-// consecutive column slices of ids[3][N] (device), the last one ragged; losses[s] receives the loss of step s.
-extern "C" int wr_bprmf_epoch(float *P, float *M, float *V, float *G, const int64_t *ids, int64_t N, int64_t batch,
-                              int D, int64_t n_users, int64_t n_items, float gamma, double lr, float l2, double beta1,
-                              double beta2, float eps, int64_t adam_t0, float *losses, void *ws, void *stream) {
-    if (!ids || !losses) return WR_E_NULL;
-    if (N <= 0 || batch <= 0 || adam_t0 < 0) return WR_E_SIZE;
-    int64_t s = 0;
-    for (int64_t lo = 0; lo < N; lo += batch, ++s) {
-        const int64_t B = N - lo < batch ? N - lo : batch;
-        const double t = (double)(adam_t0 + s + 1);
-        // torch/optim/adam.py evaluates these in Python floats (C doubles, libm pow): the same calls here
-        const float step_size = (float)(lr / (1.0 - pow(beta1, t)));
-        const float bc2_sqrt = (float)pow(1.0 - pow(beta2, t), 0.5);
-        const int rc = wr_bprmf_step(P, M, V, G, ids + lo, ids + N + lo, ids + 2 * N + lo, B, D, n_users, n_items, gamma,
-                                     l2, beta1, beta2, eps, step_size, bc2_sqrt, nullptr, losses + s, ws, stream);
-        if (rc) return rc;
-    }
-    return WR_OK;
-}
-
-// ---- host-fed step with no copy engine and no stream synchronisation in the loop ----------------------------------
-struct wr_bprmf_ctx {
-    float *P, *M, *V, *G;
-    int64_t n_users, n_items;
-    int D;
-    float gamma, l2, eps;
-    double beta1, beta2, lr;
-    void *ws;
-    cudaStream_t stream;
-    float *host_loss;          // mapped pinned: [0] = loss
-    uint32_t *host_flag;       // mapped pinned: last step whose loss has been delivered
-    float *dev_loss;           // device word for the copy-engine path (large tables)
-    uint32_t seq;
-    const void *checked[4];    // id buffers already verified to be mapped pinned memory
-};
-
-extern "C" int wr_bprmf_ctx_create(float *P, float *M, float *V, float *G, int64_t n_users, int64_t n_items, int D,
-                                   float gamma, double lr, float l2, double beta1, double beta2, float eps, void *ws,
-                                   void *stream, wr_bprmf_ctx **out) {
-    if (!P || !M || !V || !G || !ws || !out) return WR_E_NULL;
-    if (n_users <= 0 || n_items <= 0) return WR_E_SIZE;
-    if (D <= 0 || (D & 3)) return WR_E_DIM;
-    wr_bprmf_ctx *c = new wr_bprmf_ctx{P, M, V, G, n_users, n_items, D, gamma, l2, eps, beta1, beta2, lr, ws,
-                                       (cudaStream_t)stream, nullptr, nullptr, nullptr, 0, {nullptr, nullptr, nullptr, nullptr}};
-    void *h = nullptr;
-    cudaError_t e = cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (e == cudaSuccess) {
-        memset(h, 0, 64);
-        c->host_loss = (float *)h;
-        c->host_flag = (uint32_t *)h + 8;
-        e = cudaMalloc((void **)&c->dev_loss, sizeof(float));
-    }
-    if (e != cudaSuccess) {
-        if (h) cudaFreeHost(h);
-        delete c;
-        return (int)e;
-    }
-    *out = c;
-    return WR_OK;
-}
-
-extern "C" int wr_bprmf_ctx_destroy(wr_bprmf_ctx *c) {
-    if (!c) return WR_E_NULL;
-    cudaStreamSynchronize(c->stream);
-    cudaFreeHost(c->host_loss);
-    cudaFree(c->dev_loss);
-    delete c;
-    return WR_OK;
-}
-
-static int ctx_ids_are_mapped(wr_bprmf_ctx *c, const void *p) {
-    for (int i = 0; i < 4; ++i)
-        if (c->checked[i] == p) return 1;
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    if (a.type != cudaMemoryTypeHost || a.devicePointer != p) return 0;   // pinned, and the same address on the device
-    c->checked[c->seq & 3] = p;
-    return 1;
-}
-
-extern "C" int wr_bprmf_ctx_step(wr_bprmf_ctx *c, const int64_t *host_ids, int64_t B, int64_t adam_t, int wait,
-                                 float *host_loss_out) {
-    if (!c || !host_ids) return WR_E_NULL;
-    if (B <= 0 || adam_t <= 0) return WR_E_SIZE;
-    // torch/optim/adam.py evaluates these in Python floats (C doubles, libm pow): the same calls here
-    const float step_size = (float)(c->lr / (1.0 - pow(c->beta1, (double)adam_t)));
-    const float bc2_sqrt = (float)pow(1.0 - pow(c->beta2, (double)adam_t), 0.5);
-    const int64_t n_elems = (c->n_users + c->n_items) * c->D;
-    const int D = c->D;
-    const bool fused_shape = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
-    if (!ctx_ids_are_mapped(c, host_ids)) return WR_E_ALIGN;
-    ++c->seq;
-    if (!fused_shape || n_elems > WR_FUSED_STEP_MAX_ELEMS) {
-        // large tables: the kernels read the ids straight from the mapped buffer too; the loss comes back by copy
-        int rc = wr_bprmf_step(c->P, c->M, c->V, c->G, host_ids, host_ids + B, host_ids + 2 * B, B, D, c->n_users,
-                               c->n_items, c->gamma, c->l2, c->beta1, c->beta2, c->eps, step_size, bc2_sqrt, nullptr,
-                               c->dev_loss, c->ws, c->stream);
-        if (rc) return rc;
-        cudaError_t e = cudaMemcpyAsync(c->host_loss, c->dev_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && wait) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) return (int)e;
-        if (wait && host_loss_out) *host_loss_out = c->host_loss[0];
-        return WR_OK;
-    }
-    BprParams bp{{c->P, c->P + c->n_users * D, c->G, c->G + c->n_users * D}, host_ids, host_ids + B, host_ids + 2 * B,
-                 B, c->n_users, c->n_items, c->gamma, 1.0f / (float)B, (float)B, c->host_loss, 0, (WrWorkspace *)c->ws};
-    AdamScalars s{c->l2, (float)(1.0 - c->beta1), (float)c->beta2, (float)(1.0 - c->beta2), c->eps, step_size, bc2_sqrt};
-    StepSync sy{};
-    sy.world = 1;
-    sy.notify = c->host_flag;
-    sy.notify_value = c->seq;
-    sy.notify_early = wait == 2;
-    const int rc = dispatch_step_fused(bp, D, c->P, c->M, c->V, c->G, n_elems >> 2, s, nullptr, sy, c->stream);
-    if (rc) return rc;
-    if (!wait) return WR_OK;
-    // the kernel raises the flag as soon as the loss is written (before its Adam phase); poll it, and look at the
-    // stream now and then so that a faulted launch cannot spin us forever
-    volatile uint32_t *flag = c->host_flag;
-    for (uint32_t spins = 0; *flag != c->seq; ++spins) {
-        if ((spins & 0xffffu) == 0xffffu) {
-            const cudaError_t q = cudaStreamQuery(c->stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) return (int)q;
-            if (q == cudaSuccess && *flag != c->seq) return (int)cudaErrorUnknown;
-        }
-#if defined(__x86_64__)
-        __builtin_ia32_pause();
-#endif
-    }
-    if (host_loss_out) *host_loss_out = *(volatile float *)c->host_loss;
-    return WR_OK;
 }
 
 extern "C" int wr_gather_rows(const float *T, const int64_t *idx, int64_t B, int D, int64_t n_rows, float *out,

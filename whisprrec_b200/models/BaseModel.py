@@ -43,12 +43,14 @@ class FusedAdam(object):
         return None
 
     def step(self, dev_scalars=None):
+        self.model.quiesce()
         t = self.model.tables
         self.step_count += 1
         _lib.adam_l2_sweep(t.P, t.M, t.V, t.G, self.step_count, self.lr, self.weight_decay, self.betas[0],
                            self.betas[1], self.eps, dev_scalars=dev_scalars)
 
     def state_dict(self):
+        self.model.quiesce()
         t = self.model.tables
         return {'step': self.step_count, 'exp_avg': t.M.clone(), 'exp_avg_sq': t.V.clone()}
 
@@ -107,6 +109,7 @@ class BaseModel(nn.Module):
         """BaseModel.py:48-53: state_dict only (same keys / shapes / dtype as the reference).  Sharded: the rows
         are collected from their owners first and rank 0 writes the file."""
         model_path = self.model_path if model_path is None else model_path
+        self.quiesce()
         st = getattr(self, 'sharded', None)
         if st is not None:
             self.unshard()
@@ -125,6 +128,9 @@ class BaseModel(nn.Module):
             t = self.tables
             st.load_full(t.users(t.P), t.items(t.P))
         logging.info('Load model from ' + model_path)
+
+    def quiesce(self):
+        """Nothing of this model runs asynchronously to its stream by default (BPRMF's host-fed kernel overrides)."""
 
     def count_variables(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
@@ -212,6 +218,7 @@ class GeneralModel(BaseModel):
         """Distribute the (replicated-at-init) tables over the ranks of `peers`; from here on fit() / evaluate()
         run the sharded kernels.  Every rank must call this with identically initialised parameters."""
         from .. import sharded as S
+        self.quiesce()
         t = self.fuse()
         lay = S.ShardLayout(t.n_users, t.n_items, peers.world, peers.rank)
         st = S.ShardedTables(peers, lay, t.D)
@@ -252,6 +259,7 @@ class GeneralModel(BaseModel):
 
     def eval_tables(self):
         """(user table, item table) that full-ranking evaluation scores with."""
+        self.quiesce()
         t = self.fuse()
         return t.users(t.P), t.items(t.P)
 

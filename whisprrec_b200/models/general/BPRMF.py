@@ -45,8 +45,16 @@ class BPRMF(GeneralModel):
     def forward(self, user, item):
         return self.get_user_embedding(user), self.get_item_embedding(item)
 
+    def quiesce(self):
+        """Host-fed training keeps the Adam moments in the SMs' shared memory while its kernel is resident
+        (train_step_host); anything else that touches the tables closes it first."""
+        ctx = getattr(self, '_host_ctx', None)
+        if ctx is not None:
+            ctx.sync()
+
     def predict(self, feed_dict, loss_out=None):
         """BPRMF.py:69-80 + the backward of BaseRunner.py:198 in one launch; gradient lands in tables.G."""
+        self.quiesce()
         t = self.fuse()
         out = t.loss if loss_out is None else loss_out
         _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), feed_dict['user_id'], feed_dict['pos_item'],
@@ -56,6 +64,7 @@ class BPRMF(GeneralModel):
     def train_step(self, feed_dict, loss_out=None):
         """One whole iteration of BaseRunner.fit (BaseRunner.py:196-199: zero_grad, predict, backward,
         optimizer.step) as a single wr_bprmf_step call; the loss stays on the device."""
+        self.quiesce()
         t = self.fuse()
         opt = self.optimizer
         out = t.loss if loss_out is None else loss_out
@@ -67,7 +76,9 @@ class BPRMF(GeneralModel):
 
     def train_epoch(self, ids, batch_size, losses):
         """All steps of an epoch (BaseRunner.py:194-200 for every batch) from one C call; `ids` is the epoch's int64
-        [3, N] device tensor in batch order, `losses` a device float per step."""
+        [3, N] device tensor in batch order, `losses` a device float per step.  Cache-sized tables: ONE resident
+        launch for the whole epoch (csrc/epoch_kernel.cu)."""
+        self.quiesce()
         t = self.fuse()
         opt = self.optimizer
         steps = _lib.bprmf_epoch(t.P, t.M, t.V, t.G, ids, batch_size, t.n_users, opt.step_count, opt.lr,
@@ -76,13 +87,15 @@ class BPRMF(GeneralModel):
         return steps
 
     def train_step_host(self, host_ids, wait=1):
-        """The same iteration fed from the host: `host_ids` is a pinned int64 [3, B] tensor holding the batch's
+        """The same iteration fed from the host: `host_ids` is an int64 [3, B] host tensor holding the batch's
         user / positive / negative ids (what collate_batch produces, BaseModel.py:96-127).  Covers
         utils.batch_to_gpu (utils.py:33-37), the step and `loss.detach().cpu()` (BaseRunner.py:200) in one C call
-        (wr_bprmf_ctx_step): the kernel reads the ids from the pinned buffer itself and drops the loss into mapped
-        host memory, so there is no copy-engine hop and no stream synchronisation.  wait=1: returns when the step is
-        complete; wait=2: as soon as the loss is out (its Adam phase overlaps the host's next batch).  Returns the
-        batch loss as a float."""
+        (wr_bprmf_ctx_step) with no launch, copy-engine hop or stream synchronisation per step: a kernel that stays
+        resident between calls pulls the ids out of pinned host memory and drops the loss into mapped host memory.
+        Pinned tensors are read in place (leave them alone until the step is complete); pageable ones are collated
+        into the context's pinned ring first.  wait=1: returns when the step is complete; wait=2: as soon as the loss
+        is out; wait=0: at once (up to 16 steps in flight; `host_step_loss(k)` collects the k-th step's loss).
+        Returns the batch loss as a float."""
         ctx = getattr(self, '_host_ctx', None)
         opt = self.optimizer
         if ctx is None or ctx._keep[0] is not self.tables.P:       # first call, or the tables were re-fused
@@ -91,9 +104,13 @@ class BPRMF(GeneralModel):
                                                      beta1=opt.betas[0], beta2=opt.betas[1], eps=opt.eps)
         if host_ids.dtype != torch.int64 or host_ids.dim() != 2 or host_ids.shape[0] != 3 or \
                 not host_ids.is_contiguous() or host_ids.is_cuda:
-            raise _lib.WhisprError('host_ids must be a contiguous pinned int64 [3, B] host tensor')
+            raise _lib.WhisprError('host_ids must be a contiguous int64 [3, B] host tensor')
         opt.step_count += 1
         return ctx.step(host_ids.data_ptr(), host_ids.shape[1], opt.step_count, wait)
+
+    def host_step_loss(self, k, wait=1):
+        """Loss of the k-th train_step_host call of this model (0-based), for calls made with wait=0."""
+        return self._host_ctx.wait(k, wait)
 
     def sharded_train_step(self, user, pos, neg, B_global, lr, l2):
         from ... import sharded as S
@@ -102,6 +119,7 @@ class BPRMF(GeneralModel):
     def full_predict(self, feed_dict):
         """BPRMF.py:82-91: the dense [B, n_items] score matrix (compatibility API; the runner's evaluation
         uses the fused rank kernel and never materialises it)."""
+        self.quiesce()
         t = self.fuse()
         user = feed_dict['user_id']
         pos = feed_dict.get('pos_item', torch.zeros_like(user))
