@@ -86,14 +86,10 @@ int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t n_elems, fl
                      float eps, float step_size, float bc2_sqrt, const float *dev_scalars, void *stream);
 
 /* wr_bprmf_step: one whole iteration of BaseRunner.fit for BPRMF (BaseRunner.py:196-199: zero_grad, predict,
- * backward, Adam.step) on the fused table P = [U; I] ([n_users + n_items, D], M / V / G alike).  Three forms of the
- * same arithmetic, chosen by size:
- *   - the Adam state fits in the SMs' shared memory (48 B per 4 parameters per array, ~29 MB over 148 SMs), the three id
- *     rows are equally spaced and B <= 128 x SMs: one launch of the resident kernel (csrc/epoch_kernel.cu) -- one CTA
- *     per SM, P / M / V slices in shared memory, BPR phase, grid barrier, Adam+L2 with the gradient re-zeroed;
- *   - tables of up to 8 Mi elements: one cooperative launch with the state streamed through L2;
- *   - larger: wr_bpr_fwd_bwd followed by wr_adam_l2_sweep.
- * loss_out[0] is overwritten.  dev_scalars != NULL selects the second / third form (graph replay).
+ * backward, Adam.step) on the fused table P = [U; I] ([n_users + n_items, D], M / V / G alike).  Tables of up to
+ * 8 Mi elements take ONE cooperative launch (L2 prefetch of the CTA's P / M / V / G spans, BPR forward+backward, grid
+ * barrier, Adam+L2 with the gradient re-zeroed); larger ones are wr_bpr_fwd_bwd followed by wr_adam_l2_sweep.  Same
+ * arithmetic either way.  loss_out[0] is overwritten.  (A whole epoch of such steps: wr_bprmf_epoch.)
  */
 int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
                   const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
@@ -102,8 +98,9 @@ int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, c
 
 /* wr_bprmf_epoch: the step loop of BaseRunner.fit (BaseRunner.py:194-200) in one call: batch s is columns
  * [s * batch, min(N, (s + 1) * batch)) of ids[3][N] (DEVICE, rows user / pos / neg), Adam's t runs from adam_t0 + 1,
- * losses[s] (DEVICE, ceil(N / batch) floats) receives the loss of step s.  When the tables qualify for the resident
- * kernel (see wr_bprmf_step) the whole epoch is ONE launch: the Adam moments stay in shared memory from the first step
+ * losses[s] (DEVICE, ceil(N / batch) floats) receives the loss of step s.  When the Adam state fits in the SMs' shared
+ * memory (48 B per 4 parameters, ~29 MB over 148 SMs), D is 16 / 32 / 64 / 128 / 256 and batch <= 128 x SMs, the
+ * whole epoch is ONE launch of the resident kernel (csrc/epoch_kernel.cu): the Adam moments stay in shared memory from the first step
  * to the last, the next steps' ids are staged by a helper warp per CTA while the current step runs, two grid barriers
  * per step; otherwise one wr_bprmf_step per batch.  scratch: 16-byte aligned DEVICE memory of
  * wr_bprmf_epoch_scratch_bytes(N, batch) bytes (the per-step descriptors: batch slice + Adam scalars of that step,
@@ -174,6 +171,23 @@ int wr_csr_norm_weights(const int64_t *rowptr, const int32_t *col, const float *
  * zero_add != 0 clears add[r] after reading it (recycles the pooled-gradient buffer for the next step).
  * X must not alias Y / acc_out.
  */
+/* wr_csr_build: the graph construction of LightGCN.py:54-88 on the device.  From E (user, item)
+ * pairs (int64, any order, duplicates allowed -- the reference builds R from per-user sets, so a pair counts once) it
+ * produces the CSR STRUCTURE of the [N, N] bipartite adjacency [[0, R], [R^T, 0]], N = n_users + n_items:
+ *   rowptr [N + 1] int64;  col [2 E] int32 (the first *nnz_out entries are used), ascending inside every row:
+ *   user row u lists n_users + i for its items i, item row i lists its users;  *nnz_out (DEVICE) = 2 x distinct pairs.
+ * Hand-written and deterministic: stable LSD radix sort of (row << 32 | col) keys (8-bit digits, only the digits that
+ * can be non-zero; per-tile histograms, multi-level exclusive scan, match-any ranked scatter), adjacent-unique
+ * compaction, row pointers from the key boundaries -- no atomics on the output.  Ids outside their table raise
+ * WR_STATUS_INDEX_OUT_OF_RANGE and are dropped.  The fp32 weights are a separate step because d^-1/2 must come from the
+ * reference's own NumPy call to match it bit for bit: degrees = diff(rowptr) -> np.power(fp32(deg) + 1e-10, -0.5) ->
+ * wr_csr_norm_weights.  scratch: wr_csr_build_scratch_bytes(E) bytes of device memory (two key buffers + histograms).
+ */
+size_t wr_csr_build_scratch_bytes(int64_t E);
+int wr_csr_build(const int64_t *edge_u, const int64_t *edge_i, int64_t E, int64_t n_users, int64_t n_items,
+                 int64_t *rowptr, int32_t *col, int64_t *nnz_out, void *scratch, size_t scratch_bytes, void *ws,
+                 void *stream);
+
 typedef struct wr_spmm_plan {
     /* HOST struct of DEVICE pointers: how rows with more than long_threshold non-zeros are cut into slices so
      * that no warp walks more than one slice (power-law graphs: a 10^6-edge item row would otherwise be the tail

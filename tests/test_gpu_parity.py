@@ -461,6 +461,97 @@ def test_csr_norm_weights_bit_exact():
     assert host(out).tobytes() == val.tobytes()               # bit-equal to the reference on every edge
 
 
+def test_csr_build_on_device_is_bit_exact_with_the_host_builder(ws):
+    """wr_csr_build (radix sort / dedup / row pointers on the device) + the reference's NumPy d^-1/2 +
+    wr_csr_norm_weights against the host builder and the oracle on the ml-100k train pairs, fed shuffled and with
+    duplicates: structure identical, weights bit-equal to the reference recipe on every edge."""
+    from whisprrec_b200.models.general.LightGCN import build_norm_adj_device
+    c = load('ml100k_corpus.npz')
+    nU, nI = int(c['n_users']), int(c['n_items'])
+    rowptr, col, val = O.build_norm_adj_csr(nU, nI, c['train_user'], c['train_item'])
+    rng = np.random.RandomState(0)
+    extra = rng.randint(0, len(c['train_user']), 5000)
+    u = np.concatenate([c['train_user'], c['train_user'][extra]]).astype(np.int64)
+    i = np.concatenate([c['train_item'], c['train_item'][extra]]).astype(np.int64)
+    perm = rng.permutation(len(u))
+    d_rowptr, d_col, d_val, d_dinv = build_norm_adj_device(nU, nI, dv(u[perm]), dv(i[perm]), ws)
+    assert (host(d_rowptr) == rowptr).all()
+    assert (host(d_col) == col).all()
+    assert host(d_val).tobytes() == val.tobytes()
+    assert host(d_dinv).tobytes() == O.deg_inv_sqrt(np.diff(rowptr)).tobytes()
+
+
+@pytest.mark.parametrize('nU,nI,E', [(200_000, 50_000, 1_500_000), (70_000, 300, 400_000), (3, 5, 9), (1, 1, 1),
+                                     (5000, 70_000, 4097)])
+def test_csr_build_power_law_graph_vs_numpy(nU, nI, E, ws):
+    """Power-law edge lists with duplicates, users / items without any edge, id ranges that need 1..3 radix digits:
+    rowptr / col equal to a NumPy lexsort construction of the same adjacency."""
+    from whisprrec_b200.utils import synthetic
+    rng = np.random.RandomState(E)
+    if E > 100:
+        uu, ii = synthetic.power_law_pairs(nU, nI, E, seed=E)
+        u, i = uu.numpy(), ii.numpy()
+        dup = rng.randint(0, len(u), len(u) // 10)
+        u, i = np.concatenate([u, u[dup]]), np.concatenate([i, i[dup]])
+    else:
+        u, i = rng.randint(0, nU, E).astype(np.int64), rng.randint(0, nI, E).astype(np.int64)
+    perm = rng.permutation(len(u))
+    u, i = u[perm], i[perm]
+    d_rowptr, d_col = _lib.csr_build(dv(u), dv(i), nU, nI, ws)
+    pairs = np.unique(np.stack([u, i], 1), axis=0)                      # user-major, items ascending
+    by_item = pairs[np.lexsort((pairs[:, 0], pairs[:, 1]))]
+    deg = np.concatenate([np.bincount(pairs[:, 0], minlength=nU), np.bincount(pairs[:, 1], minlength=nI)])
+    rowptr = np.zeros(nU + nI + 1, dtype=np.int64)
+    np.cumsum(deg, out=rowptr[1:])
+    col = np.concatenate([nU + pairs[:, 1], by_item[:, 0]]).astype(np.int32)
+    assert (host(d_rowptr) == rowptr).all()
+    assert d_col.numel() == len(col) and (host(d_col) == col).all()
+    assert ws.status() == 0
+
+
+def test_csr_build_reports_ids_outside_their_table(ws):
+    u = dv(np.array([0, 1, 2, 7], dtype=np.int64))
+    i = dv(np.array([1, 0, 9, 1], dtype=np.int64))
+    rowptr, col = _lib.csr_build(u, i, 3, 4, ws)                        # (2, 9) and (7, 1) are out of range: dropped
+    assert ws.status() & 1
+    assert host(rowptr).tolist() == [0, 1, 2, 2, 3, 4, 4, 4] and host(col).tolist() == [4, 3, 1, 0]
+
+
+def test_propagation_engine_power_law_L3_D128_vs_sparse_oracle(ws):
+    """The scale path's pieces at a size the oracle still finishes: device-built adjacency of a 1.3e6-nnz power-law
+    graph (split long rows), L = 3, D = 128, one fwd+bwd against the sparse restatement of LightGCN.py:134-175."""
+    from whisprrec_b200.models.BaseModel import FusedTables
+    from whisprrec_b200.models.general.LightGCN import PropagationEngine, build_norm_adj_device
+    from whisprrec_b200.utils import synthetic
+    nU, nI, D, L, B = 60_000, 9_000, 128, 3, 4096
+    uu, ii = synthetic.power_law_pairs(nU, nI, 700_000, seed=5)
+    rowptr, col, val, dinv = build_norm_adj_device(nU, nI, uu.to(DEV), ii.to(DEV), ws)
+    h_rowptr = host(rowptr)
+    assert np.diff(h_rowptr).max() > 1000 and col.numel() > 1_200_000        # popular items: rows that get sliced
+    o_rowptr, o_col, o_val = O.build_norm_adj_csr(nU, nI, uu.numpy(), ii.numpy())
+    assert (h_rowptr == o_rowptr).all() and (host(col) == o_col).all() and host(val).tobytes() == o_val.tobytes()
+    rng = np.random.RandomState(2)
+    U0 = (rng.randn(nU, D) * 0.1).astype(np.float32)
+    I0 = (rng.randn(nI, D) * 0.1).astype(np.float32)
+    sel = rng.randint(0, len(uu), B)
+    user, pos = uu.numpy()[sel].astype(np.int64), ii.numpy()[sel].astype(np.int64)
+    neg = rng.randint(1, nI, B).astype(np.int64)
+    t = FusedTables(dv(U0), dv(I0))
+    eng = PropagationEngine(t, rowptr, col, val, h_rowptr, L, 1e-5)
+    assert eng.plan.n_chunks > 0
+    loss = torch.zeros(1, device=DEV)
+    eng.fwd_bwd(dv(user), dv(pos), dv(neg), loss)
+    A = O.csr_to_torch(o_rowptr, o_col, o_val, nU + nI)
+    o_loss, o_gU, o_gI = O.lightgcn_fwd_bwd(A, U0, I0, user, pos, neg, L, 1e-5)
+    o_pool = O.lightgcn_propagate(A, torch.from_numpy(np.concatenate([U0, I0])), L)
+    assert_close(host(eng.pool), o_pool.numpy(), 'pooled tables')
+    assert_close(host(loss)[0], float(o_loss), 'loss')
+    assert_close(host(t.G[:nU]), o_gU.numpy(), 'gU', rtol=2e-5, atol_scale=2e-6)
+    assert_close(host(t.G[nU:]), o_gI.numpy(), 'gI', rtol=2e-5, atol_scale=2e-6)
+    assert float(eng.pool_grad.abs().max()) == 0.0
+    assert ws.status() == 0
+
+
 def lightgcn_from_case(s, tag):
     lr, l2, reg_w, L, D = float(s['hp'][0]), float(s['hp'][1]), float(s['hp'][2]), int(s['hp'][3]), int(s['hp'][4])
     nU, nI = s['U0'].shape[0], s['I0'].shape[0]

@@ -42,6 +42,8 @@ SIGNATURES = {
     'wr_bprmf_ctx_wait': (_int, [_p, _i64, _int, _c.POINTER(_f32)]),
     'wr_bprmf_ctx_sync': (_int, [_p]),
     'wr_bprmf_ctx_destroy': (_int, [_p]),
+    'wr_csr_build_scratch_bytes': (_sz, [_i64]),
+    'wr_csr_build': (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p, _p]),
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
     'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
@@ -281,6 +283,27 @@ class BprmfContext:
             self.close()
         except Exception:  # noqa: BLE001 - interpreter shutdown
             pass
+
+
+def csr_build(users, items, n_users, n_items, ws):
+    """wr_csr_build: (user, item) int64 device tensors -> (rowptr int64 [N + 1], col int32 [nnz]) of the bipartite
+    adjacency, rows and columns ascending, duplicate pairs dropped.  Synchronises once (nnz comes back to the host)."""
+    E = users.numel()
+    if items.numel() != E:
+        raise WhisprError('users / items must have the same length')
+    dev = users.device
+    N = int(n_users) + int(n_items)
+    lib = load()
+    rowptr = torch.empty(N + 1, dtype=I64, device=dev)
+    col = torch.empty(2 * E, dtype=I32, device=dev)
+    nnz = torch.zeros(1, dtype=I64, device=dev)
+    nbytes = lib.wr_csr_build_scratch_bytes(E)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.wr_csr_build(ptr(users, I64), ptr(items, I64), E, n_users, n_items, ptr(rowptr, I64), ptr(col, I32),
+                           ptr(nnz, I64), scratch.data_ptr(), nbytes, ws.ptr, stream_ptr()))
+    n = int(nnz.item())
+    del scratch
+    return rowptr, col[:n]
 
 
 def csr_norm_weights(rowptr, col, dinv, val):

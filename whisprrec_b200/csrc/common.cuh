@@ -40,7 +40,17 @@ static inline bool wr_aligned16(const void *p) { return (reinterpret_cast<uintpt
 
 namespace wr {
 
-constexpr int kSMs = 148;
+// SMs of the current device (148 on a B200), asked once per translation unit: grids are sized in multiples of it.
+static inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+#define kSMs (::wr::sm_count())
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

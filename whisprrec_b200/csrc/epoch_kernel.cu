@@ -15,7 +15,8 @@
 //     (the H2D transfer) and deliver loss + completion words to mapped host memory (the D2H transfer).  The kernel leaves
 //     when the host closes the stream or has not fed it for `idle_ns`.
 //
-// The same kernel with one step per launch is wr_bprmf_step for such tables.
+// Single steps (wr_bprmf_step) stay on the L2-streamed cooperative kernel of train_kernels.cu: with a cold L2 and one
+// step per launch there is nothing for the shared-memory state to amortise (measured: 18.5 vs 14.3 us, scripts/prof_resident.py).
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -54,7 +55,6 @@ struct EpochParams {
     int64_t n4, chunk;                 // float4 per array; float4 per CTA
     int64_t n_users, n_items;
     float gamma, l2, w1, beta2, w2, eps;
-    StepDesc one;                      // the step of a single-step launch (desc == nullptr)
     const StepDesc *desc;              // device ring
     uint32_t desc_ring;
     uint32_t first_step, preset_count; // not streaming: steps [first_step, preset_count) exist from the start
@@ -260,13 +260,11 @@ __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_rea
             const uint32_t cons = lds_acquire(s_consumed);
             if (n - cons < (uint32_t)EP_STAGE_DEPTH) {
                 StepDesc d;
-                if (p.desc) {
+                {
                     const uint4 *src = reinterpret_cast<const uint4 *>(p.desc + n % p.desc_ring);
                     const uint4 a = __ldcg(src), b = __ldcg(src + 1);
                     memcpy(&d, &a, 16);
                     memcpy(reinterpret_cast<char *>(&d) + 16, &b, 16);
-                } else {
-                    d = p.one;
                 }
                 if (streaming) {       // the device copy: [3, B] packed
                     d.ids = p.dev_ids + (size_t)(n % p.host_ring) * 3 * p.dev_ids_cap;
@@ -651,26 +649,6 @@ static inline void adam_step_scalars(double lr, double beta1, double beta2, doub
 }  // namespace wr
 
 using namespace wr;
-
-// Called by wr_bprmf_step (train_kernels.cu): one step on the resident kernel when the tables qualify.
-// Returns -1000 when they do not (the caller takes its own path).
-int wr_epoch_single_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
-                         const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
-                         double beta1, double beta2, float eps, float step_size, float bc2_sqrt, float *loss_out,
-                         void *ws, cudaStream_t st) {
-    if (pos - user != neg - pos) return -1000;       // the three id rows must be equally spaced
-    EpochConfig cfg;
-    const int64_t n_elems = (n_users + n_items) * D;
-    const int rc = epoch_config(n_elems, D, B, &cfg);
-    if (rc) return rc;
-    EpochParams p;
-    epoch_fill(p, cfg, P, M, V, G, n_elems, n_users, n_items, gamma, l2, beta1, beta2, eps, ws);
-    p.one = StepDesc{user, pos - user, (int32_t)B, step_size, bc2_sqrt, 1u};
-    p.first_step = 0;
-    p.preset_count = 1;
-    p.losses = loss_out;
-    return epoch_launch(cfg, p, st);
-}
 
 extern "C" int wr_debug_epoch_trace(uint64_t *dev_trace, uint64_t *dev_cta_trace) {
     g_epoch_trace = dev_trace;

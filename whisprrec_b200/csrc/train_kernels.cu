@@ -373,8 +373,8 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // ---- phase 0: pull this CTA's spans of P / M / V towards L2 (one bulk prefetch per 4 KB span) ----
-    if (threadIdx.x < 3) {
-        const float4 *arr = threadIdx.x == 0 ? P : (threadIdx.x == 1 ? M : V);
+    if (threadIdx.x < 4) {      // G too: the gradient REDs then meet lines that are already on their way
+        const float4 *arr = threadIdx.x == 0 ? P : (threadIdx.x == 1 ? M : (threadIdx.x == 2 ? V : G));
         for (int64_t c = (int64_t)blockIdx.x * blockDim.x; c < n4; c += stride) {
             const uint32_t bytes = (uint32_t)min((int64_t)blockDim.x, n4 - c) * 16u;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(arr + c), "r"(bytes) : "memory");
@@ -453,7 +453,17 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
         if (sy.world > 1) __threadfence_system(); else __threadfence();
         atomicAdd(&p.ws->ticket[3], 1u);
         if (sy.world == 1 || blockIdx.x == 0) {
-            while (ld_acquire_u32(&p.ws->ticket[3]) < gridDim.x) {}
+            uint64_t t0 = 0;
+            for (uint32_t spins = 1; ld_acquire_u32(&p.ws->ticket[3]) < gridDim.x; ++spins) {
+                if ((spins & 1023u) == 0) {          // a CTA that never arrives must not hang the GPU
+                    const uint64_t now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > WR_PEER_TIMEOUT_NS) {
+                        atomicOr(&p.ws->status, WR_STATUS_PEER_TIMEOUT);
+                        break;
+                    }
+                }
+            }
             __threadfence();
         }
     }
@@ -498,7 +508,17 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
         }
     } else if (sy.world > 1) {
         if (threadIdx.x == 0) {
-            while (ld_acquire_u32(&p.ws->ticket[5]) != sy.epoch) {}
+            uint64_t t0 = 0;
+            for (uint32_t spins = 1; ld_acquire_u32(&p.ws->ticket[5]) != sy.epoch; ++spins) {
+                if ((spins & 1023u) == 0) {
+                    const uint64_t now = global_timer_ns();
+                    if (t0 == 0) t0 = now;
+                    if (now - t0 > 2 * WR_PEER_TIMEOUT_NS) {
+                        atomicOr(&p.ws->status, WR_STATUS_PEER_TIMEOUT);
+                        break;
+                    }
+                }
+            }
             __threadfence();
         }
     }
@@ -830,11 +850,6 @@ static int dispatch_step_fused(BprParamsT<TABS> &bp, int D, float *P, float *M, 
 // step is bound by launch / DRAM latency); larger ones stream at HBM bandwidth through the two-kernel path.
 #define WR_FUSED_STEP_MAX_ELEMS ((int64_t)8 << 20)
 
-int wr_epoch_single_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
-                         const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma, float l2,
-                         double beta1, double beta2, float eps, float step_size, float bc2_sqrt, float *loss_out,
-                         void *ws, cudaStream_t st);      // epoch_kernel.cu
-
 extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, const int64_t *pos,
                              const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items, float gamma,
                              float l2, double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
@@ -843,12 +858,6 @@ extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64
     if (B <= 0 || n_users <= 0 || n_items <= 0 || n_users >= INT32_MAX || n_items >= INT32_MAX) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
     if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
-    if (!dev_scalars) {
-        // tables whose Adam state fits in the SMs' shared memory: one launch of the resident kernel (epoch_kernel.cu)
-        const int rc = wr_epoch_single_step(P, M, V, G, user, pos, neg, B, D, n_users, n_items, gamma, l2, beta1, beta2,
-                                            eps, step_size, bc2_sqrt, loss_out, ws, (cudaStream_t)stream);
-        if (rc != -1000) return rc;
-    }
     return wr_bprmf_step_impl(P, M, V, G, user, pos, neg, B, D, n_users, n_items, gamma, l2, beta1, beta2, eps, step_size,
                               bc2_sqrt, dev_scalars, loss_out, ws, stream);
 }

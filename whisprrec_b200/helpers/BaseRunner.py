@@ -242,9 +242,10 @@ class BaseRunner(object):
         n = batches.shape[1]
         for s, lo in enumerate(starts):
             hi = min(n, lo + self.batch_size)
+            if hi - lo < st.layout.world:        # the same test on every rank: nobody enters the step alone
+                raise NotImplementedError('a (last) batch of %d rows is smaller than the %d ranks; choose a batch size '
+                                          'that does not leave such a remainder' % (hi - lo, st.layout.world))
             a, b = st.layout.batch_slice(hi - lo)
-            if b == a:
-                raise NotImplementedError('a batch smaller than the number of ranks')
             loss = model.sharded_train_step(batches[0, lo + a:lo + b], batches[1, lo + a:lo + b],
                                             batches[2, lo + a:lo + b], hi - lo, self.learning_rate, self.l2)
             losses[s:s + 1].copy_(loss[:1])

@@ -35,37 +35,34 @@ def build_norm_adj_csr(n_users, n_items, train_ptr, train_idx):
     rowptr = np.zeros(U + I + 1, dtype=np.int64)
     np.cumsum(deg, out=rowptr[1:])
     col = np.concatenate([U + items, users[order]]).astype(np.int32)
-    rowsum = deg.astype(np.float32) + 1e-10
+    return rowptr, col, reference_dinv(deg)
+
+
+def reference_dinv(deg):
+    """d^-1/2 exactly as LightGCN.py:89-93 computes it: NumPy's fp32 `power` on fp32(deg) + 1e-10 (that routine is not
+    correctly rounded, so only the same NumPy call on the same values reproduces the reference bit for bit)."""
+    rowsum = np.asarray(deg).astype(np.float32) + 1e-10
     dinv = np.power(rowsum, -0.5).astype(np.float32)
     dinv[np.isinf(dinv)] = 0.
-    return rowptr, col, dinv
+    return dinv
 
 
-def build_norm_adj_device(n_users, n_items, users, items):
-    """The same CSR + weights built on the device from (user, item) id tensors (int64, distinct pairs): the graph
-    construction of LightGCN.py:54-97 for graphs the host builder cannot hold (10^8 - 10^9 edges).
+def build_norm_adj_device(n_users, n_items, users, items, ws=None):
+    """The graph construction of LightGCN.py:54-97 on the device, for edge lists the host builder cannot hold
+    (10^8 - 10^9 edges): wr_csr_build (hand-written radix sort / dedup / row pointers, csrc/csr_build.cu) for the
+    structure, the reference's own NumPy call for d^-1/2 (degrees cross the bus once: 4 bytes per node each way),
+    wr_csr_norm_weights for the fp32 weights.  users / items: int64 device tensors (duplicate pairs count once).
 
-    Returns (rowptr int64 [N+1], col int32 [2E], val fp32 [2E], dinv fp32 [N]), columns ascending inside a row.
-    `dinv` uses torch's fp32 pow on the device; NumPy's (used for reference-exact small graphs) may differ in the last
-    bit, so parity tests against the reference go through build_norm_adj_csr."""
+    Returns (rowptr int64 [N+1], col int32 [nnz], val fp32 [nnz], dinv fp32 [N]) -- bit-identical to
+    build_norm_adj_csr + wr_csr_norm_weights on the same pairs."""
     dev = users.device
-    U, I = int(n_users), int(n_items)
-    N = U + I
-    order = torch.argsort(users * I + items)                       # user-major, items ascending
-    u_sorted, i_sorted = users[order], items[order]
-    del order
-    order_i = torch.argsort(items * U + users)                     # item-major, users ascending
-    iu_sorted = users[order_i]
-    del order_i
-    deg = torch.cat([torch.bincount(users, minlength=U), torch.bincount(items, minlength=I)])
-    rowptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(deg, 0, out=rowptr[1:])
-    col = torch.cat([(U + i_sorted).to(torch.int32), iu_sorted.to(torch.int32)])
-    del u_sorted, i_sorted, iu_sorted
-    dinv = torch.pow(deg.to(torch.float32) + 1e-10, -0.5)
-    dinv[torch.isinf(dinv)] = 0.
+    ws = _lib.Workspace(dev) if ws is None else ws
+    rowptr, col = _lib.csr_build(users, items, int(n_users), int(n_items), ws)
+    deg = (rowptr[1:] - rowptr[:-1]).to(torch.int32).cpu().numpy()
+    dinv = torch.from_numpy(reference_dinv(deg)).to(dev)
     val = torch.empty(col.numel(), dtype=torch.float32, device=dev)
     _lib.csr_norm_weights(rowptr, col, dinv, val)
+    ws.raise_on_status()
     return rowptr, col, val, dinv
 
 

@@ -274,8 +274,10 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
                                 lr, l2, tabs.step_flag_ptrs, tabs.step_slot_ptrs, tabs.loss, tabs.ws,
                                 epoch=tabs._sync_epoch)
         return tabs.loss
-    B = user.numel()
-    staged = tabs.layout.world > 1 and B >= 8192 and tabs.D in (16, 32, 64, 128, 256)
+    # decided from values every rank shares (slices of one batch differ by a row: a per-rank test could split the ranks
+    # between the two protocols, and the staged one allocates collectively)
+    per_rank = (int(B_global) + tabs.layout.world - 1) // tabs.layout.world
+    staged = tabs.layout.world > 1 and per_rank >= 8192 and tabs.D in (16, 32, 64, 128, 256)
     if staged:
         # large batches: remote gradient rows are written into the owners' inboxes and reduced there after the barrier
         inbox = tabs.inbox(B_global)
