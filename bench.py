@@ -13,13 +13,19 @@ over every table row): ONE cooperative launch, wr_bprmf_step (wr_bprmf_step_shar
 rows per GPU and the cross-GPU synchronisation inside the kernel).
 
 value    : interactions/s with the epoch's batches already resident in HBM, device-timed (CUDA events around every
-           step, L2 flushed between steps by writing a 512 MB buffer, outside the events), max over ranks.
+           step, L2 flushed between steps by writing a 512 MB buffer, outside the events), max over ranks.  One
+           cooperative launch per step (wr_bprmf_step).
 e2e      : the same through the reference-facing API with HOST batches -- model.train_step_host -> wr_bprmf_ctx_step:
-           the kernel reads the step's ids from pinned (mapped) host memory and delivers the loss to mapped host memory;
-           the call returns when the whole step is complete.  Host-timed, same L2 flush.
+           every step's ids start in ORDINARY (pageable) host memory, are collated into the context's pinned ring, pulled
+           over PCIe by the resident training kernel, and the batch loss comes back through mapped host memory; the call
+           returns when the whole step is complete.  Host-timed, L2 flushed between steps.  `e2e.pipelined` is the same
+           loop with the host running up to 12 steps ahead (what a training loop does; no flush is possible there).
 roofline : the step kernel's algorithmic bytes (24 B D + 24 B + 32 D (U + I)) over its event-timed
-           duration against the measured HBM copy peak; `traffic` = its DRAM bytes from ncu.
-extra    : epoch-level fit, eval (fp32 / tcgen05), LightGCN step, the HBM-bound 10M x 2M shape; multi-GPU extras.
+           duration against the measured HBM copy peak (`frac`), and the same with the DRAM bytes ncu counted for that
+           kernel (`achieved_dram`, `traffic`: looked up in profiles/r02_kernel_traffic.json, null when absent).
+           `resident_epoch` is the epoch-level form (one launch for 327 steps; tables L2-resident by construction).
+extra    : epoch-level fit, eval (fp32 / tcgen05), LightGCN step, the HBM-bound 10M x 2M shape, the reference's step as
+           torch CUDA eager ops on the same B200; multi-GPU extras incl. a sharded-vs-single-GPU parity check.
 """
 import argparse
 import json
@@ -37,7 +43,17 @@ sys.path.insert(0, ROOT)
 
 B, D, LR, L2 = 2048, 64, 1e-3, 1e-6
 CACHE = os.environ.get('WR_CACHE', '/tmp/wr_cache')
-TRAFFIC_PER_LAUNCH = 10067456   # dram__bytes_read.sum + dram__bytes_write.sum of one bprmf_step_kernel launch (ncu --set full, profiles/r01_ncu_full_v2_step_and_eval_raw.csv); the 10 MB of writes leave L2 after the kernel
+TRAFFIC_FILE = os.path.join(ROOT, 'profiles', 'r02_kernel_traffic.json')   # ncu --set full: dram bytes per launch, by kernel + shape
+
+
+def measured_traffic(key):
+    """{'dram_read', 'dram_write', 'duration_us', 'source'} of one launch of `key` from the committed ncu summary."""
+    try:
+        return json.load(open(TRAFFIC_FILE)).get(key)
+    except (OSError, ValueError):
+        return None
+
+
 WORKLOAD = 'BPRMF emb=64 B=2048 Adam(lr=1e-3,l2=1e-6) on ml-1m-shaped synthetic (6040 users x 3706 items, 668862 train rows)'
 
 
@@ -139,6 +155,65 @@ def algorithmic_bytes_bpr(b, d):
     return 24 * b * d + 24 * b        # 3 gathered rows + 3 gradient rows of 4D bytes, 3 int64 ids
 
 
+def roofline_block(step_bytes, step_avg_s, hbm_peak, peak_src, ep_us_per_step):
+    achieved = step_bytes / step_avg_s / 1e9
+    tr = measured_traffic('bprmf_step_kernel<16,1,LocalTabs>@ml1m_b2048_flushed')
+    traffic = None if tr is None else tr['dram_read'] + tr['dram_write']
+    out = {'bound': 'hbm', 'kernel': 'bprmf_step_kernel<16,1,LocalTabs>', 'achieved': achieved, 'peak': hbm_peak,
+           'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
+           'achieved_dram': None if traffic is None else traffic / step_avg_s / 1e9,
+           'frac_dram': None if traffic is None else traffic / step_avg_s / 1e9 / hbm_peak,
+           'traffic_source': None if tr is None else tr.get('source'),
+           'peak_source': peak_src, 'bytes_per_launch': step_bytes, 'avg_launch_us': step_avg_s * 1e6,
+           'note': 'one launch per step with a cold L2: a latency chain (ids -> rows -> REDs -> grid barrier -> Adam) on 23 MB, '
+                   'of which ~8 us is the launch/event floor (scripts/prof_resident.py); the same arithmetic where HBM is '
+                   'the bound: extra.bprmf_10Mx2M_d128_b65536',
+           'resident_epoch': {'kernel': 'bprmf_epoch_kernel<16,1>', 'us_per_step': ep_us_per_step,
+                              'achieved': step_bytes / (ep_us_per_step * 1e-6) / 1e9,
+                              'frac': step_bytes / (ep_us_per_step * 1e-6) / 1e9 / hbm_peak,
+                              'note': 'ALGORITHMIC bytes over the per-step time of the one-launch epoch; the tables stay in '
+                                      'L2 / shared memory between steps (that is the design), so this is not a DRAM rate'}}
+    return out
+
+
+def torch_eager_b200(corpus, dev, batches, n_steps=60):
+    """the reference's own step as torch CUDA eager ops on this B200 -- nn.Embedding gathers, the row
+    dots, BPRLoss (utils/loss.py:33-39), autograd, torch.optim.Adam(weight_decay) (BaseRunner.py:120-124,196-199) --
+    i.e. what `main.py --gpu 0` executes per batch, on the same batches, model-only (no DataLoader)."""
+    import torch.nn as nn
+    torch.manual_seed(3407)
+    ue, ie = nn.Embedding(corpus.n_users, D).to(dev), nn.Embedding(corpus.n_items, D).to(dev)
+    opt = torch.optim.Adam(list(ue.parameters()) + list(ie.parameters()), lr=LR, weight_decay=L2)
+    spe = batches.shape[1] // B
+
+    def step(s):
+        lo = (s % spe) * B
+        u, p, n = batches[0, lo:lo + B], batches[1, lo:lo + B], batches[2, lo:lo + B]
+        opt.zero_grad()
+        uu = ue(u)
+        sp, sn = (uu * ie(p)).sum(-1), (uu * ie(n)).sum(-1)
+        loss = -torch.log(1e-10 + torch.sigmoid(sp - sn)).mean()
+        loss.backward()
+        opt.step()
+        return loss
+    for s in range(10):
+        step(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for s in range(n_steps):
+        loss = step(10 + s)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    lh = float(loss)
+    return {'interactions_per_s': n_steps * B / wall, 'ms_per_step_wall': wall / n_steps * 1e3,
+            'ms_per_step_device': e0.elapsed_time(e1) / n_steps, 'steps': n_steps, 'loss_finite': bool(np.isfinite(lh)),
+            'how': 'torch %s CUDA eager, fp32, back-to-back steps without a per-step sync (the reference syncs every step: '
+                   'BaseRunner.py:200), tables L2-resident' % torch.__version__}
+
+
 def run_ours(a, rank, world, local_rank):
     from whisprrec_b200.utils import synthetic
     from whisprrec_b200 import _lib as _lib_mod
@@ -201,35 +276,42 @@ def run_ours(a, rank, world, local_rank):
     assert np.isfinite(losses.cpu().numpy()).all()
     value = world * a.steps * B / (total_ms * 1e-3)
 
-    # ---- e2e: host batches -> pinned H2D -> predict -> step -> loss D2H, every step ----
+    # ---- e2e: every step's ids start in pageable host memory; collate -> pinned ring -> PCIe -> step -> loss on the host ----
     host_batches = batches.cpu()
-    pinned = torch.empty((steps_per_epoch, 3, B), dtype=torch.int64).pin_memory()
-    for s in range(steps_per_epoch):
-        pinned[s].copy_(host_batches[:, s * B:(s + 1) * B])
-    e2e_s = 0.0
-    views = [pinned[s] for s in range(steps_per_epoch)]        # the epoch's collated batches, in pinned host memory
+    n_buf = min(steps_per_epoch, 64)
+    pageable = [host_batches[:, s * B:(s + 1) * B].contiguous() for s in range(n_buf)]      # what collate_batch hands over
+    pinned = [t_.pin_memory() for t_ in pageable]
     cur = torch.cuda.current_stream()
-    for s in range(a.warmup + a.steps):
-        flush.zero_()
-        cur.synchronize()            # the flush only: the resident training kernel lives on its own stream
-        t0 = time.perf_counter()
-        # pinned ids in, batch loss out: one C-ABI call (wr_bprmf_ctx_step).  The kernel loads the ids from the pinned
-        # buffer over PCIe itself and stores the loss into mapped host memory, which the call waits for.
-        loss_host = model.train_step_host(views[s % steps_per_epoch])      # returns when the whole step is complete
-        if s >= a.warmup:
-            e2e_s += time.perf_counter() - t0
+
+    def e2e_loop(bufs, n_warm, n_timed, do_flush):
+        tot = 0.0
+        for s in range(n_warm + n_timed):
+            if do_flush:
+                flush.zero_()
+                cur.synchronize()        # the flush only: the resident training kernel lives on its own stream
+            t0 = time.perf_counter()
+            loss = model.train_step_host(bufs[s % n_buf])       # returns when the whole step is complete
+            if s >= n_warm:
+                tot += time.perf_counter() - t0
+        return tot, loss
+    e2e_s, loss_host = e2e_loop(pageable, max(a.warmup, 10), a.steps, True)
+    e2e_pinned_s, _ = e2e_loop(pinned, 5, a.steps, True)
+    e2e_warm_s, _ = e2e_loop(pageable, 5, a.steps, False)
+    # the host running ahead (a training loop): push without waiting, collect the loss 12 steps later
+    n_pipe = max(a.steps, 400)
     model.quiesce()
-    torch.cuda.synchronize()
-    # steady state of a real epoch loop: no flush, the call returns as soon as the loss is out (wait=2) and the next
-    # launch overlaps the Adam phase of this one; bracketed by synchronisations, tables L2-resident
-    torch.cuda.synchronize()
+    k0 = model._host_ctx.steps
     t0 = time.perf_counter()
-    for s in range(a.steps):
-        loss_host3 = model.train_step_host(views[s % steps_per_epoch], wait=2)
+    for s in range(n_pipe):
+        model.train_step_host(pageable[s % n_buf], wait=0)
+        if s >= 12:
+            loss_pipe = model.host_step_loss(k0 + s - 12)
+    for s in range(n_pipe - 12, n_pipe):
+        loss_pipe = model.host_step_loss(k0 + s)
+    e2e_pipe_s = time.perf_counter() - t0
     model.quiesce()
     torch.cuda.synchronize()
-    e2e_pipe_s = time.perf_counter() - t0
-    # the same with the copy engines and a stream synchronisation per step (wr_bprmf_step_host), for comparison
+    # the copy-engine form with a stream synchronisation per step (wr_bprmf_step_host), for comparison
     t = model.tables
     stage, pl = torch.empty(3 * B, dtype=torch.int64, device=dev), torch.zeros(1).pin_memory()
     e2e_copy_s = 0.0
@@ -238,18 +320,29 @@ def run_ours(a, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         model.optimizer.step_count += 1
-        _lib_mod.bprmf_step_host(views[s % steps_per_epoch], stage, pl, t.P, t.M, t.V, t.G, t.n_users,
+        _lib_mod.bprmf_step_host(pinned[s % n_buf], stage, pl, t.P, t.M, t.V, t.G, t.n_users,
                                  model.optimizer.step_count, LR, L2, t.loss, t.ws)
         loss_host2 = float(pl[0])
         if s >= a.warmup:
             e2e_copy_s += time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    assert np.isfinite(loss_host)
+    assert np.isfinite(loss_host) and np.isfinite(loss_pipe) and np.isfinite(loss_host2)
+    t.ws.raise_on_status()
     e2e_value = world * a.steps * B / e2e_s
+
+    # ---- the epoch-level form of the same steps: ONE resident launch for all 327 (what BaseRunner.fit calls) ----
+    ep_losses = torch.zeros(steps_per_epoch + 1, device=dev)
+    ids_epoch = batches[:, :steps_per_epoch * B].contiguous()
+    ep_ms = []
+    for r in range(7):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.train_epoch(ids_epoch, B, ep_losses)
+        e1.record()
+        torch.cuda.synchronize()
+        ep_ms.append(e0.elapsed_time(e1))
+    assert np.isfinite(ep_losses[:steps_per_epoch].cpu().numpy()).all()
+    ep_us_per_step = float(np.median(ep_ms[2:])) * 1e3 / steps_per_epoch
 
     step_bytes = algorithmic_bytes_adam(n_rows, D) + algorithmic_bytes_bpr(B, D)
     step_avg_s = float(step_ms.mean()) * 1e-3
@@ -262,29 +355,34 @@ def run_ours(a, rank, world, local_rank):
                    'l2_flush': '512 MB written between timed steps (tables are 10 MB, L2-resident otherwise)',
                    'parallelism': 'single GPU' if world == 1 else 'replicas x%d' % world},
         'e2e': {'value': e2e_value, 'unit': 'interactions/s', 'h2d_bytes_per_step': 3 * B * 8,
-                'd2h_bytes_per_step': 8, 'ms_per_step': e2e_s / a.steps * 1e3,
-                'how': 'model.train_step_host -> wr_bprmf_ctx_step: ids read by the kernel from pinned (mapped) host '
-                       'memory, loss + sequence word written to mapped host memory and polled; every call returns when '
-                       'its step is complete (all parameter updates done)',
-                'pipelined_l2_resident': {'value': world * a.steps * B / e2e_pipe_s, 'ms_per_step': e2e_pipe_s / a.steps * 1e3,
-                                          'how': 'back-to-back steps, no L2 flush, wait=2 (return when the loss is out)'},
+                'd2h_bytes_per_step': 12, 'ms_per_step': e2e_s / a.steps * 1e3,
+                'how': 'model.train_step_host -> wr_bprmf_ctx_step on the resident kernel: ids start in PAGEABLE host '
+                       'memory (collated into the pinned ring inside the call), are pulled over PCIe by the kernel\'s helper '
+                       'warps, loss + completion words come back through mapped host memory; every call returns when its '
+                       'step is complete; L2 flushed (512 MB) before every step, outside the timer',
+                'pinned_in_place': {'value': world * a.steps * B / e2e_pinned_s, 'ms_per_step': e2e_pinned_s / a.steps * 1e3,
+                                    'how': 'the same with the ids already in pinned memory (read in place, no collate copy)'},
+                'no_flush': {'value': world * a.steps * B / e2e_warm_s, 'ms_per_step': e2e_warm_s / a.steps * 1e3,
+                             'how': 'pageable ids, every step waited for, tables L2-resident (no flush)'},
+                'pipelined': {'value': world * n_pipe * B / e2e_pipe_s, 'ms_per_step': e2e_pipe_s / n_pipe * 1e3, 'steps': n_pipe,
+                              'how': 'pageable ids, wait=0: the host runs up to 12 steps ahead and reads every loss 12 steps '
+                                     'later (a training loop); no flush is possible between pipelined steps'},
                 'copy_engine_form': {'value': world * a.steps * B / e2e_copy_s, 'ms_per_step': e2e_copy_s / a.steps * 1e3,
                                      'how': 'wr_bprmf_step_host: cudaMemcpyAsync H2D + step + cudaMemcpyAsync D2H + '
                                             'cudaStreamSynchronize'}},
         'gpu_launches': a.steps,
         'clocks': clocks,
-        'roofline': {'bound': 'hbm', 'kernel': 'bprmf_step_kernel', 'achieved': achieved, 'peak': hbm_peak,
-                     'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': TRAFFIC_PER_LAUNCH,
-                     'peak_source': peak_src, 'bytes_per_launch': step_bytes, 'avg_launch_us': step_avg_s * 1e6,
-                     'note': 'the whole step is one launch; 23 MB per launch is latency-bound (launch + two dependent '
-                             'DRAM round trips + a grid barrier), see extra.bprmf_10Mx2M_d128_b65536 for the '
-                             'bandwidth-bound shape of the same arithmetic'},
+        'roofline': roofline_block(step_bytes, step_avg_s, hbm_peak, peak_src, ep_us_per_step),
         'kernels_ms': {'bprmf_step': float(step_ms.mean()), 'step_median': float(np.median(step_ms))},
     }
     if rank == 0 and world == 1:
         line['cpu_baseline'] = cpu_baseline(corpus, budget_s=a.cpu_budget)
         if not a.no_extras:
             line['extra'] = extras(corpus, dev, model, runner, data, hbm_peak)
+            try:
+                line['extra']['torch_eager_b200'] = torch_eager_b200(corpus, dev, batches)
+            except Exception as e:  # noqa: BLE001
+                line['extra']['torch_eager_b200'] = {'error': repr(e)}
     if rank == 0:
         emit(line)
     if world > 1:
@@ -327,6 +425,7 @@ def run_ours_sharded(a, rank, world, local_rank):
         dist.barrier()
         torch.cuda.synchronize()
 
+    parity = sharded_parity(model, runner, data, st, peers, batches, GB, lo_r, dev)
     for s in range(a.warmup):
         flush.zero_()
         step(s)
@@ -420,12 +519,57 @@ def run_ours_sharded(a, rank, world, local_rank):
                                              'adam_l2_sweep': float(seg[:, 2].mean()),
                                              'barrier_after_adam': float(seg[:, 3].mean())}},
     }
+    line['extra'] = {'parity': parity}
     if not a.no_extras:
-        line['extra'] = extras_sharded(peers, dev, hbm_peak, flush)
+        line['extra'].update(extras_sharded(peers, dev, hbm_peak, flush))
     if rank == 0:
         emit(line)
     peers.close()
     dist.destroy_process_group()
+
+
+def sharded_parity(model, runner, data, st, peers, batches, GB, lo_r, dev):
+    """Before anything is timed: three global batches through the sharded step on the N GPUs and through the single-GPU
+    step on this rank's full replica of the tables (still in place from before model.shard()), then the sharded
+    full-ranking evaluation of the dev split against the single-GPU kernel on the gathered tables.  Asserted on every
+    rank (a failure aborts the bench) and reported under extra.parity."""
+    import torch.distributed as dist
+    from whisprrec_b200 import _lib
+    t = model.tables
+    Pf, Mf, Vf, Gf = t.P.clone(), t.M.clone(), t.V.clone(), t.G.clone()
+    lossf = torch.zeros(1, device=dev)
+    worst_loss, worst_p = 0.0, 0.0
+    for k in range(3):
+        lo = k * GB
+        u, p, n = batches[0, lo:lo + GB], batches[1, lo:lo + GB], batches[2, lo:lo + GB]
+        loss = model.sharded_train_step(u[lo_r:lo_r + B].contiguous(), p[lo_r:lo_r + B].contiguous(),
+                                        n[lo_r:lo_r + B].contiguous(), GB, LR, L2)
+        _lib.bpr_fwd_bwd(Pf[:t.n_users], Pf[t.n_users:], u.contiguous(), p.contiguous(), n.contiguous(),
+                         Gf[:t.n_users], Gf[t.n_users:], lossf, t.ws)
+        _lib.adam_l2_sweep(Pf, Mf, Vf, Gf, st.step_count, LR, L2)
+        a_, b_ = float(loss[0]), float(lossf[0])
+        worst_loss = max(worst_loss, abs(a_ - b_) / abs(b_))
+        gu, gi = st.gather_full()
+        full = torch.cat([gu, gi])
+        err = ((full - Pf).abs() - 1e-5 * Pf.abs()).max().item() / float(Pf.abs().max())
+        worst_p = max(worst_p, err)
+        peers.barrier()
+    assert worst_loss <= 2e-6, ('sharded loss differs from the single-GPU step', worst_loss)
+    assert worst_p <= 2e-6, ('sharded parameters differ from the single-GPU step', worst_p)
+    # evaluation: item-sharded ranks against the single-GPU kernel on the same (gathered) tables -- identical
+    (user, pos), (hptr, hidx) = runner._eval_inputs(data['dev'])
+    got = runner.rank_topk(data['dev'])[0]
+    gu, gi = st.gather_full()
+    want = _lib.eval_rank_topk(gu.contiguous(), gi.contiguous(), user, pos, hptr, hidx, t.ws)[0]
+    mism = int((got != want).sum().item())
+    assert mism == 0, ('sharded eval ranks differ from the single-GPU kernel', mism)
+    ok = torch.tensor([1], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    st.ws.raise_on_status()
+    return {'ok': bool(ok.item()), 'steps': 3, 'loss_rel_err_max': worst_loss, 'loss_bound': 2e-6,
+            'param_excess_over_1e-5_rel_max': worst_p, 'param_bound': '|a-b| <= 1e-5 |b| + 2e-6 max|b|',
+            'eval_rows': int(user.numel()), 'eval_rank_mismatches': mism,
+            'against': 'wr_bpr_fwd_bwd + wr_adam_l2_sweep and wr_eval_rank_topk on one GPU, same batches'}
 
 
 def extras_sharded(peers, dev, hbm_peak, flush):
@@ -471,6 +615,15 @@ def extras_sharded(peers, dev, hbm_peak, flush):
         del tabs
     except Exception as e:  # noqa: BLE001
         out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {'error': repr(e)}
+    try:    # BASELINE.json configs[3]: LightGCN L=3 D=128, 10M x 2M x 494M edges, rows sharded over the N GPUs
+        import argparse as _ap
+        from scripts.bench_lightgcn_scale import run as lightgcn_scale
+        torch.cuda.empty_cache()
+        cfg = _ap.Namespace(users=10_000_000, items=2_000_000, edges=500_000_000, dim=128, layers=3, batch=65536, steps=3, warmup=1)
+        out['lightgcn_cfg4_10Mx2Mx494M_L3_d128_sharded'] = lightgcn_scale(cfg, rank, world, dev, peers)
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['lightgcn_cfg4_10Mx2Mx494M_L3_d128_sharded'] = {'error': repr(e)}
     try:
         _, tensor_peak, _ = peaks()
         for d in (64, 128):
@@ -551,6 +704,8 @@ def run_reference(a, rank):
     torch and cannot travel to the GPU box, so this is the oracle port of it, on all host threads."""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: this arm must use the host's cores whatever launched it
+    torch.set_num_threads(os.cpu_count() or 1)
     from whisprrec_b200.utils import synthetic
     corpus = synthetic.ml1m_shaped_corpus(cache_dir=os.path.join(CACHE, 'ref'))
     U, I, cols = cpu_problem(corpus)
@@ -591,6 +746,7 @@ def timed(fn, reps, flush=None):
 
 def extras(corpus, dev, model, runner, data, hbm_peak):
     from whisprrec_b200 import _lib
+    from whisprrec_b200.utils import synthetic
     out = {}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     try:    # full-ranking eval of the dev split, fp32-exact kernel
@@ -625,8 +781,7 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
     except Exception as e:  # noqa: BLE001
         out['epoch_fit'] = {'error': repr(e)}
     try:    # ml-100k (the reference's own CPU-runnable case, BASELINE.json configs[0]): whole epochs and the dev evaluation
-        from tests.helpers import ml100k_corpus
-        c100 = ml100k_corpus()
+        c100 = synthetic.corpus_from_npz(os.path.join(ROOT, 'tests', 'golden', 'ml100k_corpus.npz'))
         res = {}
         for name, over in (('BPRMF', {}), ('LightGCN', {'gcn_layers': 2})):
             m100, r100, d100 = make_model(c100, dev, name, **over)
@@ -715,6 +870,15 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
         del lg, batches
     except Exception as e:  # noqa: BLE001
         out['lightgcn_L2'] = {'error': repr(e)}
+    try:    # BASELINE.json configs[3] on ONE GPU: LightGCN L=3 D=128 on the 10M x 2M x 494M-edge power-law graph (65 GB)
+        import argparse as _ap
+        from scripts.bench_lightgcn_scale import run as lightgcn_scale
+        torch.cuda.empty_cache()
+        cfg = _ap.Namespace(users=10_000_000, items=2_000_000, edges=500_000_000, dim=128, layers=3, batch=65536, steps=3, warmup=1)
+        out['lightgcn_cfg4_10Mx2Mx494M_L3_d128'] = lightgcn_scale(cfg, 0, 1, dev)
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out['lightgcn_cfg4_10Mx2Mx494M_L3_d128'] = {'error': repr(e)}
     try:    # the same two training kernels where HBM really is the bound: 10M users x 2M items, D=128
         nU, nI, d, b = 10_000_000, 2_000_000, 128, 65536
         P = torch.empty((nU + nI, d), device=dev).normal_(0, 0.01)

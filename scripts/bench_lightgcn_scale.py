@@ -40,6 +40,23 @@ def main():
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
     torch.cuda.set_device(dev)
+    peers = None
+    if world > 1:
+        import torch.distributed as dist
+        from whisprrec_b200 import sharded as S
+        dist.init_process_group('nccl', device_id=dev)
+        peers = S.PeerGroup(dev)
+    line = run(a, rank, world, dev, peers)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        peers.close()
+        dist.destroy_process_group()
+
+
+def run(a, rank, world, dev, peers=None):
+    """One measurement; `a` carries users / items / edges / dim / layers / batch / steps / warmup.  world > 1 needs an
+    initialised process group and a PeerGroup.  Returns the result line (every rank; rank 0 prints it)."""
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
     U, I, D, L, B = a.users, a.items, a.dim, a.layers, a.batch
@@ -78,8 +95,6 @@ def main():
     else:
         import torch.distributed as dist
         from whisprrec_b200 import sharded as S
-        dist.init_process_group('nccl', device_id=dev)
-        peers = S.PeerGroup(dev)
         lay = S.ShardLayout(U, I, world, rank)
         tabs = S.ShardedTables(peers, lay, D)
         tabs.P.copy_((torch.rand((lay.n_local, D), device=dev, generator=g) * 2 - 1) * bound)
@@ -117,18 +132,15 @@ def main():
         return 2 * L * P + 2 * (L + 2) * n_rows * 4 * D + 32 * D * n_rows + 48 * B * D + 12 * B
     per_gpu = step_bytes(n_local, nnz_local)
     gbs = per_gpu / (ms * 1e-3) / 1e9
-    if rank == 0:
-        print(json.dumps({
-            'workload': 'LightGCN L=%d D=%d on synthetic power-law graph' % (L, D), 'users': U, 'items': I, 'edges': E,
-            'nodes': N, 'nnz': nnz, 'n_gpus': world, 'batch_per_gpu': B, 'ms_per_step': ms,
-            'interactions_per_s': world * B / (ms * 1e-3), 'steps_per_s': 1e3 / ms,
-            'algorithmic_bytes_per_gpu_step': per_gpu, 'algorithmic_gbs_per_gpu': gbs,
-            'frac_of_hbm_peak': gbs / peaks['hbm_gbs'], 'hbm_peak_gbs': peaks['hbm_gbs'],
-            'compulsory_bytes_per_pass': nnz_local * 8 + n_local * (4 + 8 * D), 'graph_build_s': t_graph,
-            'mem_gb': torch.cuda.max_memory_allocated() / 1e9}))
-    if world > 1:
-        peers.close()
-        dist.destroy_process_group()
+    return {
+        'workload': 'LightGCN L=%d D=%d on synthetic power-law graph' % (L, D), 'users': U, 'items': I, 'edges': E,
+        'nodes': N, 'nnz': nnz, 'n_gpus': world, 'batch_per_gpu': B, 'ms_per_step': ms,
+        'interactions_per_s': world * B / (ms * 1e-3), 'steps_per_s': 1e3 / ms,
+        'algorithmic_bytes_per_gpu_step': per_gpu, 'algorithmic_gbs_per_gpu': gbs,
+        'frac_of_hbm_peak': gbs / peaks['hbm_gbs'], 'hbm_peak_gbs': peaks['hbm_gbs'],
+        'compulsory_bytes_per_pass': nnz_local * 8 + n_local * (4 + 8 * D),
+        'compulsory_bytes_per_gpu_step': 2 * L * (nnz_local * 8 + n_local * (4 + 8 * D)) + 2 * (L + 2) * n_local * 4 * D + 32 * D * n_local,
+        'graph_build_s': t_graph, 'mem_gb': torch.cuda.max_memory_allocated() / 1e9}
 
 
 if __name__ == '__main__':

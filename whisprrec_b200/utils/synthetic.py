@@ -71,6 +71,18 @@ def ml1m_shaped_corpus(seed=3407, cache_dir=None):
     return R.BaseReader.from_frames(*parts)
 
 
+def corpus_from_npz(path):
+    """BaseReader from an .npz of (user, item) pair arrays per split (`train_user`, `train_item`, `dev_*`, `test_*`,
+    ids already remapped) -- the layout of tests/golden/ml100k_corpus.npz."""
+    from ..helpers.BaseReader import BaseReader
+    c = np.load(path, allow_pickle=False)
+    frames = []
+    for ph in ('train', 'dev', 'test'):
+        u, i = np.asarray(c[ph + '_user'], dtype=np.int64), np.asarray(c[ph + '_item'], dtype=np.int64)
+        frames.append(pd.DataFrame({'user_id': u, 'item_id': i, 'timestamp': np.zeros(len(u), dtype=np.int64)}))
+    return BaseReader.from_frames(*frames)
+
+
 def power_law_pairs(n_users, n_items, n_edges, seed=3407, alpha=1.8, zipf=0.8, device='cpu'):
     """Distinct (user, item) pairs of a power-law bipartite graph, as int64 torch tensors on `device`.
 
