@@ -201,6 +201,9 @@ typedef struct wr_spmm_plan {
     const int32_t *slot_chunks;   /* [n_long] slices per split row */
     int32_t *slot_arrivals;       /* [n_long] zeroed; left zeroed by every call */
     float *slot_partial;          /* [n_long, D] zeroed; left zeroed by every call */
+    const uint32_t *hot_bits;     /* nullable: bitmap over the N columns; rows of X whose bit is set are loaded with an L2
+                                     evict_last policy, the col / val streams with evict_first.  For tables far larger than
+                                     L2: mark the highest-degree nodes, as many as fit in ~2/3 of L2 */
 } wr_spmm_plan;
 
 int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D, const float *X,

@@ -452,6 +452,29 @@ def test_csr_spmm_vs_oracle(D):
     assert_close(host(dacc), acc + ref, 'in-place layer sum', rtol=1e-5, atol_scale=2e-6)
 
 
+def test_csr_spmm_hot_row_cache_policy_changes_nothing_but_the_cache(ws):
+    """The L2 evict_last / evict_first variant of the SpMM (plan.hot_bits: tables far larger than L2) computes bit for
+    bit what the plain loads do."""
+    from whisprrec_b200.models.general.LightGCN import build_norm_adj_device
+    from whisprrec_b200.utils import synthetic
+    nU, nI, D = 30_000, 4_000, 128
+    uu, ii = synthetic.power_law_pairs(nU, nI, 300_000, seed=9)
+    rowptr, col, val, _ = build_norm_adj_device(nU, nI, uu.to(DEV), ii.to(DEV), ws)
+    h_rowptr = host(rowptr)
+    X = torch.randn((nU + nI, D), device=DEV) * 0.1
+    plain = _lib.SpmmPlan(h_rowptr, D, DEV, hot_budget_bytes=80 << 20)          # table below L2 size: no bitmap
+    hinted = _lib.SpmmPlan(h_rowptr, D, DEV, hot_budget_bytes=2 << 20, hot_min_table_bytes=0)
+    assert plain.hot_bits is None and hinted.hot_bits is not None and 0 < hinted.n_hot <= (2 << 20) // (4 * D)
+    ya, yb = torch.empty_like(X), torch.empty_like(X)
+    pa, pb = torch.empty_like(X), torch.empty_like(X)
+    _lib.csr_spmm(rowptr, col, val, X, Y=ya, acc_in=X, acc_out=pa, acc_div=3.0, plan=plain)
+    _lib.csr_spmm(rowptr, col, val, X, Y=yb, acc_in=X, acc_out=pb, acc_div=3.0, plan=hinted)
+    # rows cut into slices are combined with REDs (order varies run to run); everything else is bit-identical
+    short = torch.from_numpy(np.diff(h_rowptr) <= 128).to(DEV)
+    assert torch.equal(ya[short], yb[short]) and torch.equal(pa[short], pb[short])
+    assert_close(host(yb), host(ya), 'sliced rows', rtol=1e-5, atol_scale=2e-6)
+
+
 def test_csr_norm_weights_bit_exact():
     c = load('ml100k_corpus.npz')
     rowptr, col, val = O.build_norm_adj_csr(c['n_users'], c['n_items'], c['train_user'], c['train_item'])

@@ -315,7 +315,7 @@ class _PlanStruct(ctypes.Structure):
     """Mirror of `wr_spmm_plan` (include/whisprrec_b200.h)."""
     _fields_ = [('long_threshold', _i64), ('n_chunks', _i64), ('n_long', _i64),
                 ('chunk_row', _p), ('chunk_beg', _p), ('chunk_len', _p), ('chunk_slot', _p), ('slot_chunks', _p),
-                ('slot_arrivals', _p), ('slot_partial', _p)]
+                ('slot_arrivals', _p), ('slot_partial', _p), ('hot_bits', _p)]
 
 
 class SpmmPlan:
@@ -325,7 +325,8 @@ class SpmmPlan:
     zeroed scratch live as long as the plan does.
     """
 
-    def __init__(self, rowptr_host, D, device, threshold=128, chunk=128):
+    def __init__(self, rowptr_host, D, device, threshold=128, chunk=128, hot_budget_bytes=0,
+                 hot_min_table_bytes=96 << 20):
         import numpy as np
         deg = np.diff(rowptr_host)
         long_rows = np.nonzero(deg > threshold)[0]
@@ -333,25 +334,47 @@ class SpmmPlan:
         per_row = (deg[long_rows] + chunk - 1) // chunk
         self.n_chunks = int(per_row.sum())
         self.struct = None
-        if self.n_chunks == 0:
+        # optional (off by default: measured a 5 % LOSS at 10M x 2M x 494M edges, profiles/r02_spmm_hot_rows.json -- the
+        # 80 MB hottest rows carry only 31 % of the reads and the bitmap test costs more than the hits save): the
+        # highest-degree nodes (the adjacency is symmetric: a node's column is read once per edge of its row) get their
+        # rows loaded with an L2 evict_last policy, as many as fit in the budget
+        self.hot_bits, self.n_hot = None, 0
+        n = len(deg)
+        if hot_budget_bytes and n * D * 4 > hot_min_table_bytes:
+            k = min(n, int(hot_budget_bytes) // (D * 4))
+            if k > 0:
+                thr = np.partition(deg, n - k)[n - k]
+                hot = deg > thr
+                room = k - int(hot.sum())
+                if room > 0:
+                    ties = np.nonzero(deg == thr)[0][:room]
+                    hot[ties] = True
+                self.n_hot = int(hot.sum())
+                bits = np.packbits(np.pad(hot, (0, (-n) % 32)), bitorder='little').view(np.uint32)
+                self.hot_bits = torch.from_numpy(np.ascontiguousarray(bits).view(np.int32)).to(device)
+        if self.n_chunks == 0 and self.hot_bits is None:
             return
-        slot = np.repeat(np.arange(self.n_long, dtype=np.int32), per_row)
-        first = np.zeros(self.n_long, dtype=np.int64)
-        np.cumsum(per_row[:-1], out=first[1:])
-        k = np.arange(self.n_chunks, dtype=np.int64) - first[slot]          # slice number inside its row
-        beg = rowptr_host[long_rows][slot] + k * chunk
-        length = np.minimum(chunk, rowptr_host[long_rows + 1][slot] - beg)
-        # longest-first over slots keeps the last wave short
         to = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(device)
-        self.chunk_row, self.chunk_beg = to(long_rows[slot], np.int32), to(beg, np.int64)
-        self.chunk_len, self.chunk_slot = to(length, np.int32), to(slot, np.int32)
-        self.slot_chunks = to(per_row, np.int32)
-        self.slot_arrivals = torch.zeros(self.n_long, dtype=I32, device=device)
-        self.slot_partial = torch.zeros((self.n_long, D), dtype=F32, device=device)
-        self.struct = _PlanStruct(self.threshold, self.n_chunks, self.n_long, self.chunk_row.data_ptr(),
-                                  self.chunk_beg.data_ptr(), self.chunk_len.data_ptr(), self.chunk_slot.data_ptr(),
-                                  self.slot_chunks.data_ptr(), self.slot_arrivals.data_ptr(),
-                                  self.slot_partial.data_ptr())
+        if self.n_chunks:
+            slot = np.repeat(np.arange(self.n_long, dtype=np.int32), per_row)
+            first = np.zeros(self.n_long, dtype=np.int64)
+            np.cumsum(per_row[:-1], out=first[1:])
+            k = np.arange(self.n_chunks, dtype=np.int64) - first[slot]          # slice number inside its row
+            beg = rowptr_host[long_rows][slot] + k * chunk
+            length = np.minimum(chunk, rowptr_host[long_rows + 1][slot] - beg)
+            self.chunk_row, self.chunk_beg = to(long_rows[slot], np.int32), to(beg, np.int64)
+            self.chunk_len, self.chunk_slot = to(length, np.int32), to(slot, np.int32)
+            self.slot_chunks = to(per_row, np.int32)
+            self.slot_arrivals = torch.zeros(self.n_long, dtype=I32, device=device)
+            self.slot_partial = torch.zeros((self.n_long, D), dtype=F32, device=device)
+            self.struct = _PlanStruct(self.threshold, self.n_chunks, self.n_long, self.chunk_row.data_ptr(),
+                                      self.chunk_beg.data_ptr(), self.chunk_len.data_ptr(), self.chunk_slot.data_ptr(),
+                                      self.slot_chunks.data_ptr(), self.slot_arrivals.data_ptr(),
+                                      self.slot_partial.data_ptr(), None)
+        else:
+            self.struct = _PlanStruct(self.threshold, 0, 0, None, None, None, None, None, None, None, None)
+        if self.hot_bits is not None:
+            self.struct.hot_bits = self.hot_bits.data_ptr()
 
     def ref(self):
         return None if self.struct is None else ctypes.addressof(self.struct)

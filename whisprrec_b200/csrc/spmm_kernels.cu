@@ -40,13 +40,28 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParamsT<XACC> &p, int6
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
     constexpr int EPS = RG::GROUPS;  // edges per step
+    // Tables far larger than L2 (power-law graphs at scale): the rows of the highest-degree nodes are re-read thousands
+    // of times per pass, the rest a few dozen times with reuse distances of gigabytes.  plan.hot_bits marks the former;
+    // they are loaded with an L2 evict_last policy (they stay), the index / weight streams with evict_first.
+    const uint32_t *hot_bits = p.plan.hot_bits;
+    uint64_t pol_keep = 0, pol_stream = 0;
+    if (hot_bits) {
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    }
     for (int64_t base = beg; base < end; base += 32) {
         const int cnt = (int)min((int64_t)32, end - base);
         int c = 0;
         float w = 0.f;
         if (lane < cnt) {
-            c = __ldg(p.col + base + lane);
-            w = __ldg(p.val + base + lane);
+            if (hot_bits) {
+                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(c) : "l"(p.col + base + lane), "l"(pol_stream));
+                asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(w) : "l"(p.val + base + lane), "l"(pol_stream));
+                if ((__ldg(hot_bits + (c >> 5)) >> (c & 31)) & 1u) c |= (int)0x80000000u;      // carried in the sign bit
+            } else {
+                c = __ldg(p.col + base + lane);
+                w = __ldg(p.val + base + lane);
+            }
         }
         for (int j = 0; j < cnt; j += EPS * UNROLL) {
             float4 x[UNROLL][VPL];
@@ -54,10 +69,25 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParamsT<XACC> &p, int6
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u) {
                 const int e = j + u * EPS + grp;
-                const int cc = __shfl_sync(0xffffffffu, c, e & 31);
+                int cc = __shfl_sync(0xffffffffu, c, e & 31);
                 ww[u] = __shfl_sync(0xffffffffu, w, e & 31);
                 if (e < cnt) {
-                    RG::load(p.X.row(cc, D), sub, x[u]);
+                    if (hot_bits) {
+                        const bool hot = cc < 0;
+                        cc &= 0x7fffffff;
+                        const float *row = p.X.row(cc, D);
+                        if (hot) {
+#pragma unroll
+                            for (int v = 0; v < VPL; ++v)
+                                asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                                             : "=f"(x[u][v].x), "=f"(x[u][v].y), "=f"(x[u][v].z), "=f"(x[u][v].w)
+                                             : "l"(row + 4 * (sub + v * LPR)), "l"(pol_keep));
+                        } else {
+                            RG::load(row, sub, x[u]);
+                        }
+                    } else {
+                        RG::load(p.X.row(cc, D), sub, x[u]);
+                    }
                 } else {
                     RG::zero(x[u]);
                     ww[u] = 0.f;
@@ -211,6 +241,7 @@ static int spmm_launch(SpmmParamsT<XACC> &p, int D, const wr_spmm_plan *host_pla
         if (q.long_threshold < 1 || q.n_long < 1 || !wr_aligned16(q.slot_partial)) return WR_E_SIZE;
         p.plan = q;
     }
+    if (host_plan && fast) p.plan.hot_bits = host_plan->hot_bits;
     int64_t g = (p.N + 7) / 8;
     if (g > 16 * kSMs) g = 16 * kSMs;
     p.row_blocks = (int)g;
