@@ -346,6 +346,48 @@ int wr_bpr_fwd_bwd_sharded_staged(const wr_shards *host_T, const wr_shards *host
 int wr_inbox_scatter(float *G, const float *inbox_rows, int32_t *inbox_idx, int world, int64_t cap, int D,
                      void *stream);
 
+/* wr_xchg_request / wr_xchg_serve / wr_bpr_fwd_bwd_exchanged: the training step's "all-to-all of indices and embedding
+ * rows"  made of posted NVLink stores only.  Loads from peer memory are what does not scale
+ * (measured on 8 B200s: random 512-byte row gathers from multi-GB peer mappings reach 30-80 GB/s per GPU -- a TLB miss
+ * and a 3.5 us round trip each -- while peer stores stream at link bandwidth), so for batches of >= 8,192 rows per GPU:
+ *   wr_xchg_request: every (batch entry, role) of this rank's slice -> owner o, owner-local row r; the entry
+ *       (r << 2 | role) is appended to this rank's list in owner o's request array (host_req[o]: rank o's
+ *       [world][cap] int32, we write row [rank]; host_req_cnt[o]: rank o's [world] counts) and where[3 b + role] =
+ *       o * cap + k remembers the position.  cnt_local: [world] uint32 device scratch, zero on entry, zero on exit.
+ *   -- wr_peer_barrier --
+ *   wr_xchg_serve: the owner reads every requested row from its LOCAL shard T_local and stores it into the requester's
+ *       receive buffer (host_recv[r]: rank r's [world][cap][D] fp32; we write block [rank], in request order).
+ *   -- wr_peer_barrier --
+ *   wr_bpr_fwd_bwd_exchanged: wr_bpr_fwd_bwd_sharded_staged with the three rows of entry b read from
+ *       recv[where[3 b + role]] (local memory); gradient rows go to the owners' inboxes as before.
+ * cap >= 3 x the largest per-rank batch.  Ids outside their table raise WR_STATUS_INDEX_OUT_OF_RANGE (entry skipped).
+ */
+int wr_xchg_request(const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B, int64_t n_users,
+                    int64_t n_items, int world, int rank, int32_t *const host_req[WR_MAX_WORLD],
+                    uint32_t *const host_req_cnt[WR_MAX_WORLD], int64_t cap, uint32_t *cnt_local, int32_t *where,
+                    void *ws, void *stream);
+int wr_xchg_serve(const float *T_local, int D, int world, int rank, const int32_t *req_local,
+                  const uint32_t *req_cnt_local, int64_t cap, float *const host_recv[WR_MAX_WORLD], void *stream);
+int wr_bpr_fwd_bwd_exchanged(const float *recv, const int32_t *where, const wr_shards *host_Gd,
+                             float *const host_inbox_rows[WR_MAX_WORLD], int32_t *const host_inbox_idx[WR_MAX_WORLD],
+                             int64_t cap, const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B,
+                             int64_t B_global, int D, float gamma, float grad_scale, float *loss_out, void *ws,
+                             void *stream);
+
+/* wr_embloss_owner_sumsq / wr_embloss_owner_scatter: EmbLoss (utils/loss.py:83-98, LightGCN.py:165-175) computed by the
+ * OWNERS of the ego rows from the request lists of wr_xchg_request, which hold every occurrence of every row of the
+ * batch with its role -- no row crosses NVLink:
+ *   sumsq_out[0..3) = this rank's sums of squares of the requested user / positive / negative ego rows (the ranks' sums
+ *                     meet in wr_peer_barrier);
+ *   scatter: G_local[row] += reg_weight / B_global * T_local[row] / sqrt(sumsq_global[role]) per occurrence; if
+ *            loss_out != NULL, loss_out[0] += reg_weight * (sum of the three norms) / B_global.
+ */
+int wr_embloss_owner_sumsq(const float *T_local, int D, int world, const int32_t *req_local,
+                           const uint32_t *req_cnt_local, int64_t cap, float *sumsq_out, void *ws, void *stream);
+int wr_embloss_owner_scatter(const float *T_local, float *G_local, int D, int world, const int32_t *req_local,
+                             const uint32_t *req_cnt_local, int64_t cap, float reg_weight, int64_t B_global,
+                             const float *sumsq_global, float *loss_out, void *stream);
+
 /* wr_bprmf_step_sharded: wr_bprmf_step on row-sharded tables -- ONE cooperative launch per rank and step, with the
  * two cross-GPU meeting points inside the kernel: (1) the grid barrier between the BPR phase and the Adam phase is
  * extended across the GPUs by CTA 0 (every rank's remote gradient REDs have landed, the loss shares are exchanged),
@@ -389,13 +431,20 @@ int wr_gather_rows_sharded(const wr_shards *host_T, int which, const int64_t *id
 int wr_allgather_shards(const wr_shards *host_src, float *dst, int D, void *stream);
 
 /* wr_csr_spmm_sharded: wr_csr_spmm for this rank's rows of the adjacency (local row l is node l * world + rank of
- * the user block for l < rows_u_local, else of the item block), column ids GLOBAL node ids; X rows are read from
- * their owners through host_X (the fused "all-gather of the layer output + SpMM": no gathered copy of X ever
- * exists); Y / add / acc_in / acc_out are this rank's local [n_local, D] slabs.
+ * the user block for l < rows_u_local, else of the item block), column ids GLOBAL node ids; X rows are read through
+ * host_X -- in place from their owners (small tables), or from a local all-gathered copy (base[g] pointing into it);
+ * Y / add / acc_in / acc_out are this rank's local [n_local, D] slabs.
+ * host_push (nullable): host_push[g] = where rank g keeps ITS copy of this rank's shard of Y ([n_local, D], peer-mapped;
+ * entry [rank] ignored).  Every finished row of Y is then also stored there from the epilogue -- the all-gather of the
+ * layer output fused into the SpMM as posted NVLink writes, so the next layer needs no gather pass (measured at 8 GPUs on
+ * the 10M x 2M x 494M-edge graph: a separate gather costs as much as the SpMM itself, 10.3 vs 11.1 ms per layer).
+ * The caller double-buffers the copies (peers may still be reading the previous layer's) and runs wr_peer_barrier
+ * before the next layer reads them.
  */
 int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_local, int D,
                         const wr_shards *host_X, float *Y, float *add, int zero_add, const float *acc_in,
-                        float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream);
+                        float *acc_out, float acc_div, const wr_spmm_plan *host_plan,
+                        float *const host_push[WR_MAX_WORLD], void *stream);
 
 /* wr_eval_rank_topk_shard: wr_eval_rank_topk against ONE item shard.
  *   Urows   [R, D]  the eval rows' user embeddings, already gathered (wr_gather_rows_sharded)

@@ -212,7 +212,9 @@ def run_gpu():
             assert np.mean(host(got_tc[0]) != host(want_tc[0])) < 2e-3, 'sharded tensor-core ranks'
 
         # ---------------- LightGCN: L = 2 sharded steps against the oracle on the whole batch ----------------
-        for gather_first in (False, True):     # neighbour rows read in place over NVLink / all-gathered first
+        # third pass: a batch of 8,192 rows per rank -> the row exchange (owners deliver the pooled rows, EmbLoss computed
+        # by the owners of the ego rows from the request lists), with the fused all-gather of the layer outputs
+        for gather_first, B in ((False, B), (True, B), (True, 8192 * world)):
             L, reg = 2, 1e-5
             rowptr, col, val = O.build_norm_adj_csr(nU, nI, pairs[:, 0], pairs[:, 1])
             dinv = O.deg_inv_sqrt(np.diff(rowptr))
@@ -241,9 +243,11 @@ def run_gpu():
             assert_close(host(pu), o_pool[:nU], 'sharded pooled users', rtol=1e-4, atol_scale=1e-4)
             assert_close(host(pi), o_pool[nU:], 'sharded pooled items', rtol=1e-4, atol_scale=1e-4)
             assert tabs2.ws.status() == 0
+            if B >= 8192 * world:
+                assert getattr(tabs2, '_xchg', None) is not None and int(tabs2._inbox['idx'].abs().max()) == 0
         peers.host_sync()
         if rank == 0:
-            print(f'dist_worker gpu ok: world {world} nU {nU} nI {nI} D {D} B {B}')
+            print(f'dist_worker gpu ok: world {world} nU {nU} nI {nI} D {D}')
     # ---------------- the reference-facing classes on sharded tables: one ml-100k epoch against the goldens ----------------
     from tests.helpers import load, ml100k_corpus, model_args
     from whisprrec_b200.helpers.BaseRunner import BaseRunner

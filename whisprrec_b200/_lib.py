@@ -64,6 +64,11 @@ SIGNATURES = {
     'wr_peer_barrier': (_int, [_p, _int, _int, _c.c_uint32, _p, _p, _int, _p, _p, _p]),
     'wr_bpr_fwd_bwd_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
     'wr_bpr_fwd_bwd_sharded_staged': (_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_xchg_request': (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _i64, _p, _p, _p, _p]),
+    'wr_xchg_serve': (_int, [_p, _int, _int, _int, _p, _p, _i64, _p, _p]),
+    'wr_bpr_fwd_bwd_exchanged': (_int, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_embloss_owner_sumsq': (_int, [_p, _int, _int, _p, _p, _i64, _p, _p, _p]),
+    'wr_embloss_owner_scatter': (_int, [_p, _p, _int, _int, _p, _p, _i64, _f32, _i64, _p, _p, _p]),
     'wr_inbox_scatter': (_int, [_p, _p, _p, _int, _i64, _int, _p]),
     'wr_bprmf_step_sharded_supported': (_int, [_i64, _int]),
     'wr_bprmf_step_sharded': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _f64, _f64, _f32, _f32,
@@ -72,7 +77,7 @@ SIGNATURES = {
     'wr_embloss_scatter_sharded': (_int, [_p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _p, _p, _p, _p]),
     'wr_gather_rows_sharded': (_int, [_p, _int, _p, _i64, _int, _p, _p, _p]),
     'wr_allgather_shards': (_int, [_p, _p, _int, _p]),
-    'wr_csr_spmm_sharded': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
+    'wr_csr_spmm_sharded': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p, _p]),
     'wr_eval_rank_topk_shard': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p,
                                        _p, _p, _p]),
     'wr_rowdot': (_int, [_p, _p, _i64, _int, _int, _p, _p]),
@@ -569,6 +574,45 @@ def bpr_fwd_bwd_sharded_staged(T, Gd, inbox_row_ptrs, inbox_idx_ptrs, cap, user,
                                                stream_ptr()))
 
 
+def _ptr_array(ptrs, world):
+    FA = _p * MAX_WORLD
+    return FA(*(list(ptrs) + [None] * (MAX_WORLD - world)))
+
+
+def xchg_request(user, pos, neg, n_users, n_items, world, rank, req_ptrs, cnt_ptrs, cap, cnt_local, where, ws):
+    ra, ca = _ptr_array(req_ptrs, world), _ptr_array(cnt_ptrs, world)
+    check(load().wr_xchg_request(ptr(user, I64), ptr(pos, I64), ptr(neg, I64), user.numel(), n_users, n_items, world, rank,
+                                 ctypes.addressof(ra), ctypes.addressof(ca), cap, ptr(cnt_local, I32), ptr(where, I32),
+                                 ws.ptr, stream_ptr()))
+
+
+def xchg_serve(T_local, world, rank, req_local, cnt_local, cap, recv_ptrs):
+    va = _ptr_array(recv_ptrs, world)
+    check(load().wr_xchg_serve(ptr(T_local, F32), T_local.shape[1], world, rank, ptr(req_local, I32), ptr(cnt_local, I32),
+                               cap, ctypes.addressof(va), stream_ptr()))
+
+
+def bpr_fwd_bwd_exchanged(recv, where, Gd, inbox_row_ptrs, inbox_idx_ptrs, cap, user, pos, neg, B_global, D, loss_out, ws,
+                          gamma=1e-10, grad_scale=1.0):
+    world = Gd.world
+    ra, ia = _ptr_array(inbox_row_ptrs, world), _ptr_array(inbox_idx_ptrs, world)
+    check(load().wr_bpr_fwd_bwd_exchanged(ptr(recv, F32), ptr(where, I32), ctypes.addressof(Gd), ctypes.addressof(ra),
+                                          ctypes.addressof(ia), cap, ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
+                                          user.numel(), B_global, D, gamma, grad_scale, ptr(loss_out, F32), ws.ptr,
+                                          stream_ptr()))
+
+
+def embloss_owner_sumsq(T_local, world, req_local, cnt_local, cap, sumsq_out, ws):
+    check(load().wr_embloss_owner_sumsq(ptr(T_local, F32), T_local.shape[1], world, ptr(req_local, I32), ptr(cnt_local, I32),
+                                        cap, ptr(sumsq_out, F32), ws.ptr, stream_ptr()))
+
+
+def embloss_owner_scatter(T_local, G_local, world, req_local, cnt_local, cap, reg_weight, B_global, sumsq_global, loss_out):
+    check(load().wr_embloss_owner_scatter(ptr(T_local, F32), ptr(G_local, F32), T_local.shape[1], world, ptr(req_local, I32),
+                                          ptr(cnt_local, I32), cap, reg_weight, B_global, ptr(sumsq_global, F32),
+                                          ptr(loss_out, F32), stream_ptr()))
+
+
 def inbox_scatter(G, inbox_rows, inbox_idx, world, cap):
     check(load().wr_inbox_scatter(ptr(G, F32), ptr(inbox_rows, F32), ptr(inbox_idx, I32), world, cap, G.shape[1],
                                   stream_ptr()))
@@ -618,10 +662,17 @@ def allgather_shards(src, dst, D):
 
 
 def csr_spmm_sharded(rowptr, col, val, n_local, D, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None,
-                     acc_div=1.0, plan=None):
+                     acc_div=1.0, plan=None, push_ptrs=None):
+    """push_ptrs: list of `world` raw pointers (entry [rank] ignored / None): every peer's copy of this rank's shard of Y,
+    written from the SpMM epilogue (the fused all-gather)."""
+    pa = None
+    if push_ptrs is not None:
+        FA = _p * MAX_WORLD
+        pa = FA(*(list(push_ptrs) + [None] * (MAX_WORLD - len(push_ptrs))))
     check(load().wr_csr_spmm_sharded(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), n_local, D, ctypes.addressof(X),
                                      ptr(Y, F32), ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32),
-                                     acc_div, None if plan is None else plan.ref(), stream_ptr()))
+                                     acc_div, None if plan is None else plan.ref(),
+                                     None if pa is None else ctypes.addressof(pa), stream_ptr()))
 
 
 def rowdot(A, B, round_bf16=False):

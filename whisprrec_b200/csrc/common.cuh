@@ -214,6 +214,10 @@ struct LocalTabs {
     float *gU, *gI;
     __device__ __forceinline__ const float *urow(int64_t u, int D) const { return U + u * D; }
     __device__ __forceinline__ const float *irow(int64_t i, int D) const { return I + i * D; }
+    // row of batch entry b in role `which` (0 user, 1 positive, 2 negative) whose id is `id`
+    __device__ __forceinline__ const float *row(int64_t, int which, int64_t id, int D) const {
+        return (which == 0 ? U : I) + id * D;
+    }
     __device__ __forceinline__ float *gurow(int64_t u, int D) const { return gU + u * D; }
     __device__ __forceinline__ float *girow(int64_t i, int D) const { return gI + i * D; }
     // gradient contribution `v` to floats [off, off+4) of a row; (b, which) name the batch row and its role
@@ -243,6 +247,9 @@ struct ShardTabs {
     wr_shards t, g;
     __device__ __forceinline__ const float *urow(int64_t u, int D) const { return shard_user_row(t, u, D); }
     __device__ __forceinline__ const float *irow(int64_t i, int D) const { return shard_item_row(t, i, D); }
+    __device__ __forceinline__ const float *row(int64_t, int which, int64_t id, int D) const {
+        return which == 0 ? shard_user_row(t, id, D) : shard_item_row(t, id, D);
+    }
     __device__ __forceinline__ float *gurow(int64_t u, int D) const { return shard_user_row(g, u, D); }
     __device__ __forceinline__ float *girow(int64_t i, int D) const { return shard_item_row(g, i, D); }
     __device__ __forceinline__ void add_user(int64_t u, int D, int off, float4 v, int64_t, int) const {
@@ -262,8 +269,15 @@ struct StageTabs {
     float *inbox_rows[WR_MAX_WORLD];     // rank o's [world][cap][D]
     int32_t *inbox_idx[WR_MAX_WORLD];    // rank o's [world][cap]
     int64_t cap;                         // slots per sender (>= 3 x the largest per-rank batch)
+    // rows already delivered by their owners (wr_xchg_*): batch entry b's row in role `which` is recv[where[3 b + which]]
+    const float *recv;
+    const int32_t *where;
     __device__ __forceinline__ const float *urow(int64_t u, int D) const { return shard_user_row(t, u, D); }
     __device__ __forceinline__ const float *irow(int64_t i, int D) const { return shard_item_row(t, i, D); }
+    __device__ __forceinline__ const float *row(int64_t b, int which, int64_t id, int D) const {
+        if (recv) return recv + (int64_t)where[3 * b + which] * D;
+        return which == 0 ? shard_user_row(t, id, D) : shard_item_row(t, id, D);
+    }
     __device__ __forceinline__ float *gurow(int64_t u, int D) const { return shard_user_row(g, u, D); }
     __device__ __forceinline__ float *girow(int64_t i, int D) const { return shard_item_row(g, i, D); }
     __device__ __forceinline__ void put(uint32_t owner, int64_t local_row, int D, int off, float4 v, int64_t b,

@@ -30,6 +30,10 @@ struct SpmmParamsT {
     float acc_div;
     wr_spmm_plan plan;       // by value; long_threshold = INT64_MAX when there is no plan
     int row_blocks;          // CTAs [0, row_blocks) walk rows, the rest walk the chunks of split rows
+    // fused all-gather of the output (multi-GPU): every finished row of Y is also stored into each peer's copy of this
+    // rank's shard (posted NVLink writes behind the arithmetic), so the next layer starts without a gather pass
+    float *push[WR_MAX_WORLD];
+    int n_push;
 };
 using SpmmParams = SpmmParamsT<LocalX>;
 
@@ -119,7 +123,10 @@ __device__ __forceinline__ void spmm_row_epilogue(const SpmmParamsT<XACC> &p, in
         y = add4(y, *ap);
         if (p.zero_add) *ap = f4_zero();
     }
-    if (p.Y) *reinterpret_cast<float4 *>(p.Y + off) = y;
+    if (p.Y) {
+        *reinterpret_cast<float4 *>(p.Y + off) = y;
+        for (int g = 0; g < p.n_push; ++g) *reinterpret_cast<float4 *>(p.push[g] + off) = y;
+    }
     if (p.acc_out) {
         const float4 a = add4(*reinterpret_cast<const float4 *>(p.acc_in + off), y);
         // ATen's mean is sum().div_(count): a true division, not a multiply by the reciprocal
@@ -281,13 +288,14 @@ extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const floa
     if (rc) return rc;
     if (!wr_aligned16(X)) return WR_E_ALIGN;
     if (X == Y || X == acc_out) return WR_E_SIZE;
-    SpmmParams p{rowptr, col, val, N, {X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0};
+    SpmmParams p{rowptr, col, val, N, {X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, {}, 0};
     return spmm_launch(p, D, host_plan, (cudaStream_t)stream);
 }
 
 extern "C" int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_local, int D,
                                    const wr_shards *host_X, float *Y, float *add, int zero_add, const float *acc_in,
-                                   float *acc_out, float acc_div, const wr_spmm_plan *host_plan, void *stream) {
+                                   float *acc_out, float acc_div, const wr_spmm_plan *host_plan,
+                                   float *const host_push[WR_MAX_WORLD], void *stream) {
     if (!host_X) return WR_E_NULL;
     int rc = wr_check_shards(host_X);
     if (rc) return rc;
@@ -295,7 +303,15 @@ extern "C" int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, co
     if (rc) return rc;
     if (n_local != host_X->rows_u_local + host_X->rows_i_local) return WR_E_SIZE;
     if (host_X->base[host_X->rank] == Y || host_X->base[host_X->rank] == acc_out) return WR_E_SIZE;
-    SpmmParamsT<ShardX> p{rowptr, col, val, n_local, {*host_X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0};
+    SpmmParamsT<ShardX> p{rowptr, col, val, n_local, {*host_X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, {}, 0};
+    if (host_push) {
+        if (!Y) return WR_E_NULL;
+        for (int g = 0; g < host_X->world; ++g) {
+            if (g == host_X->rank || !host_push[g]) continue;
+            if (!wr_aligned16(host_push[g])) return WR_E_ALIGN;
+            p.push[p.n_push++] = host_push[g];
+        }
+    }
     return spmm_launch(p, D, host_plan, (cudaStream_t)stream);
 }
 

@@ -67,9 +67,9 @@ __global__ void __launch_bounds__(256) bpr_fwd_bwd_kernel(BprParamsT<TABS> p) {
         if (valid && !ok && sub == 0) atomicOr(&p.ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
         float4 ue[VPL], pe[VPL], ne[VPL];
         if (ok) {
-            RG::load(p.tabs.urow(u, D), sub, ue);
-            RG::load(p.tabs.irow(i, D), sub, pe);
-            RG::load(p.tabs.irow(j, D), sub, ne);
+            RG::load(p.tabs.row(b, 0, u, D), sub, ue);
+            RG::load(p.tabs.row(b, 1, i, D), sub, pe);
+            RG::load(p.tabs.row(b, 2, j, D), sub, ne);
         } else {
             RG::zero(ue);
             RG::zero(pe);
@@ -708,9 +708,35 @@ extern "C" int wr_bpr_fwd_bwd_sharded_staged(const wr_shards *host_T, const wr_s
     if (rc) return rc;
     if (B <= 0 || B_global < B || cap < 3 * B) return WR_E_SIZE;
     if (!(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return WR_E_DIM;
-    BprParamsT<StageTabs> p{{*host_T, *host_Gd, {}, {}, cap}, user, pos, neg, B, host_T->n_users, host_T->n_items,
+    BprParamsT<StageTabs> p{{*host_T, *host_Gd, {}, {}, cap, nullptr, nullptr}, user, pos, neg, B, host_T->n_users, host_T->n_items,
                             gamma, grad_scale / (float)B_global, (float)B_global, loss_out, 0, (WrWorkspace *)ws};
     for (int g = 0; g < host_T->world; ++g) {
+        if (!host_inbox_rows[g] || !host_inbox_idx[g]) return WR_E_NULL;
+        if (!wr_aligned16(host_inbox_rows[g])) return WR_E_ALIGN;
+        p.tabs.inbox_rows[g] = host_inbox_rows[g];
+        p.tabs.inbox_idx[g] = host_inbox_idx[g];
+    }
+    return launch_bpr(p, D, (cudaStream_t)stream);
+}
+
+// The same with the three rows of every batch entry already delivered by their owners (wr_xchg_request / wr_xchg_serve):
+// no NVLink reads at all; gradient rows still go to the owners' inboxes.
+extern "C" int wr_bpr_fwd_bwd_exchanged(const float *recv, const int32_t *where, const wr_shards *host_Gd,
+                                        float *const host_inbox_rows[WR_MAX_WORLD],
+                                        int32_t *const host_inbox_idx[WR_MAX_WORLD], int64_t cap, const int64_t *user,
+                                        const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D,
+                                        float gamma, float grad_scale, float *loss_out, void *ws, void *stream) {
+    if (!recv || !where || !host_Gd || !host_inbox_rows || !host_inbox_idx || !user || !pos || !neg || !loss_out || !ws)
+        return WR_E_NULL;
+    const int rc = wr_check_shards(host_Gd);
+    if (rc) return rc;
+    if (B <= 0 || B_global < B || cap < 3 * B) return WR_E_SIZE;
+    if (!(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return WR_E_DIM;
+    if (!wr_aligned16(recv)) return WR_E_ALIGN;
+    BprParamsT<StageTabs> p{{*host_Gd, *host_Gd, {}, {}, cap, recv, where}, user, pos, neg, B, host_Gd->n_users,
+                            host_Gd->n_items, gamma, grad_scale / (float)B_global, (float)B_global, loss_out, 0,
+                            (WrWorkspace *)ws};
+    for (int g = 0; g < host_Gd->world; ++g) {
         if (!host_inbox_rows[g] || !host_inbox_idx[g]) return WR_E_NULL;
         if (!wr_aligned16(host_inbox_rows[g])) return WR_E_ALIGN;
         p.tabs.inbox_rows[g] = host_inbox_rows[g];

@@ -222,6 +222,33 @@ class ShardedTables(object):
             self.peers.host_sync()
         return box
 
+    def exchange(self, B_global):
+        """Symmetric buffers of the row exchange (wr_xchg_*): request lists and counts at the owners, receive buffers
+        at the requesters; sized for 3 x the largest per-rank slice of a batch of B_global rows."""
+        lay = self.layout
+        cap = 3 * ((int(B_global) + lay.world - 1) // lay.world)
+        x = getattr(self, '_xchg', None)
+        if x is None or x['cap'] < cap:
+            dev = self.peers.device
+            req, req_ptrs = self.peers.alloc((lay.world, cap), dtype=torch.int32)
+            cnt, cnt_ptrs = self.peers.alloc((64,), dtype=torch.int32)
+            recv, recv_ptrs = self.peers.alloc((lay.world, cap, self.D))
+            x = self._xchg = {'cap': cap, 'req': req, 'req_ptrs': req_ptrs, 'cnt': cnt, 'cnt_ptrs': cnt_ptrs,
+                              'recv': recv, 'recv_ptrs': recv_ptrs,
+                              'cnt_local': torch.zeros(64, dtype=torch.int32, device=dev),
+                              'where': torch.zeros(cap, dtype=torch.int32, device=dev)}
+            self.peers.host_sync()
+        return x
+
+    def fetch_rows(self, x, table_local, user, pos, neg):
+        """Steps 1 and 2 of the exchange: afterwards x['recv'][x['where'][3 b + role]] is the row of batch entry b."""
+        lay = self.layout
+        _lib.xchg_request(user, pos, neg, lay.n_users, lay.n_items, lay.world, lay.rank, x['req_ptrs'], x['cnt_ptrs'],
+                          x['cap'], x['cnt_local'], x['where'], self.ws)
+        self.peers.barrier()
+        _lib.xchg_serve(table_local, lay.world, lay.rank, x['req'], x['cnt'], x['cap'], x['recv_ptrs'])
+        self.peers.barrier()
+
     def symmetric(self):
         """A zeroed [n_local, D] fp32 table on every rank -> (local tensor, wr_shards describing all of them)."""
         lay = self.layout
@@ -279,10 +306,13 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
     per_rank = (int(B_global) + tabs.layout.world - 1) // tabs.layout.world
     staged = tabs.layout.world > 1 and per_rank >= 8192 and tabs.D in (16, 32, 64, 128, 256)
     if staged:
-        # large batches: remote gradient rows are written into the owners' inboxes and reduced there after the barrier
+        # large batches: nobody loads from peer memory.  The owners deliver the requested rows (wr_xchg_*), the batch
+        # kernel runs on local memory, and the gradient rows are written into the owners' inboxes and reduced there
         inbox = tabs.inbox(B_global)
-        _lib.bpr_fwd_bwd_sharded_staged(tabs.T, tabs.Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'], user, pos,
-                                        neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
+        x = tabs.exchange(B_global)
+        tabs.fetch_rows(x, tabs.P, user, pos, neg)
+        _lib.bpr_fwd_bwd_exchanged(x['recv'], x['where'], tabs.Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'],
+                                   user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
     else:
         _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
     loss = tabs.peers.barrier(tabs.loss_part[:1])
@@ -328,32 +358,53 @@ class ShardedLightGCN(object):
         # only local memory has those re-reads served by the L2; peer reads always cross NVLink).
         self.gather_first = (lay.world > 1 and total * 4 * tabs.D > (256 << 20)) if gather_first is None \
             else bool(gather_first) and lay.world > 1
-        self.gathered = torch.empty((lay.world, lay.n_local, tabs.D), dtype=torch.float32, device=dev) \
-            if self.gather_first else None
+        # two symmetric (peer-mapped) copies of the whole table, [world, n_local, D] each: a layer's SpMM reads one while
+        # its epilogue -- and the other ranks' -- fill the other with that layer's output (the fused all-gather)
+        self.gathered, self.gathered_ptrs = [], []
+        if self.gather_first:
+            for _ in range(2):
+                buf, ptrs = tabs.peers.alloc((lay.world, lay.n_local, tabs.D))
+                self.gathered.append(buf)
+                self.gathered_ptrs.append(ptrs)
+        self._cur = 0                 # which copy holds (or receives by all-gather) the next SpMM's input
+        self._pushed = None           # base pointer of the shard whose rows the last SpMM pushed into gathered[_cur]
         self._local_views = {}
         tabs.peers.host_sync()
 
-    def _local_view(self, X):
-        """wr_shards whose peers' bases point into the gathered local copy (own shard read in place)."""
-        key = X.base[X.rank]
+    def _local_view(self, X, which):
+        """wr_shards whose peers' bases point into the gathered local copy `which` (own shard read in place)."""
+        key = (X.base[X.rank], which)
         v = self._local_views.get(key)
         if v is None:
             v = _lib.ShardsStruct()
             ctypes.memmove(ctypes.addressof(v), ctypes.addressof(X), ctypes.sizeof(v))
-            step = self.gathered[0].numel() * 4
+            step = self.gathered[which][0].numel() * 4
             for g in range(X.world):
                 if g != X.rank:
-                    v.base[g] = self.gathered.data_ptr() + g * step
+                    v.base[g] = self.gathered[which].data_ptr() + g * step
             self._local_views[key] = v
         return v
 
-    def _spmm(self, X, **kw):
+    def _spmm(self, X, push=False, **kw):
+        """One propagation.  push=True: the output Y is the next SpMM's input -- its rows are stored into every peer's
+        other gathered copy from the epilogue, and that SpMM skips its all-gather."""
         t = self.tabs
+        push_ptrs = None
         if self.gather_first:
-            _lib.allgather_shards(X, self.gathered, t.D)
-            X = self._local_view(X)
-        _lib.csr_spmm_sharded(self.rowptr, self.col, self.val, t.layout.n_local, t.D, X, plan=self.plan, **kw)
-        t.peers.barrier()          # every rank's rows of the output exist before anyone reads them as neighbours
+            cur = self._cur
+            if self._pushed != X.base[X.rank]:            # input not delivered by the previous SpMM: pull it
+                _lib.allgather_shards(X, self.gathered[cur], t.D)
+            X = self._local_view(X, cur)
+            self._pushed = None
+            if push:
+                step = self.gathered[0][0].numel() * 4
+                push_ptrs = [None if g == t.layout.rank else self.gathered_ptrs[1 - cur][g] + t.layout.rank * step
+                             for g in range(t.layout.world)]
+                self._pushed = kw['Y'].data_ptr()
+                self._cur = 1 - cur
+        _lib.csr_spmm_sharded(self.rowptr, self.col, self.val, t.layout.n_local, t.D, X, plan=self.plan,
+                              push_ptrs=push_ptrs, **kw)
+        t.peers.barrier()          # every rank's rows of the output exist (everywhere) before anyone reads them
 
     def propagate(self):
         """LightGCN.py:134-148 on row shards: layer k+1 reads its neighbours' layer-k rows from their owners."""
@@ -365,7 +416,7 @@ class ShardedLightGCN(object):
         x = t.T
         for k in range(1, L + 1):
             y, ys = self.layer[(k - 1) & 1]
-            self._spmm(x, Y=y if k < L else None, acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
+            self._spmm(x, push=k < L, Y=y if k < L else None, acc_in=t.P if k == 1 else self.pool, acc_out=self.pool,
                        acc_div=float(L + 1) if k == L else 1.0)
             x = ys
 
@@ -373,6 +424,9 @@ class ShardedLightGCN(object):
         """LightGCN.py:150-175 + backward + Adam on this rank's slice of the batch."""
         t, L = self.tabs, self.L
         self.propagate()
+        per_rank = (int(B_global) + t.layout.world - 1) // t.layout.world
+        if L > 0 and t.layout.world > 1 and per_rank >= 8192 and t.D in (16, 32, 64, 128, 256):
+            return self._step_exchanged(user, pos, neg, B_global, lr, l2)
         if L == 0:
             _lib.bpr_fwd_bwd_sharded(t.T, t.Gd, user, pos, neg, B_global, t.D, t.loss_part, t.ws)
         else:
@@ -387,7 +441,7 @@ class ShardedLightGCN(object):
             for k in range(1, L + 1):
                 last = k == L
                 y, ys = (t.G, t.Gd) if last else self.layer[(k - 1) & 1]
-                self._spmm(h, Y=y, add=self.pool_grad, zero_add=last and L > 1)
+                self._spmm(h, push=not last, Y=y, add=self.pool_grad, zero_add=last and L > 1)
                 h = ys
             if L == 1:
                 self.pool_grad.zero_()
@@ -397,6 +451,38 @@ class ShardedLightGCN(object):
         t.adam(lr, l2)
         t.peers.barrier()
         return t.loss
+
+
+def _step_exchanged(self, user, pos, neg, B_global, lr, l2):
+    """The rest of ShardedLightGCN.step for large batches (after propagate): pooled rows delivered by their owners,
+    EmbLoss computed by the owners of the ego rows from the request lists -- no loads from peer memory, no remote REDs."""
+    t, L = self.tabs, self.L
+    world = t.layout.world
+    x, inbox = t.exchange(B_global), t.inbox(B_global)
+    t.fetch_rows(x, self.pool, user, pos, neg)
+    _lib.bpr_fwd_bwd_exchanged(x['recv'], x['where'], self.pool_Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'],
+                               user, pos, neg, B_global, t.D, t.loss_part, t.ws, grad_scale=1.0 / (L + 1))
+    _lib.embloss_owner_sumsq(t.P, world, x['req'], x['cnt'], x['cap'], t.loss_part[1:], t.ws)
+    sums = t.peers.barrier(t.loss_part)          # pooled gradient rows are in the inboxes; loss and the three norms reduced
+    t.loss.copy_(sums[:1])
+    self.sumsq[:3].copy_(sums[1:4])
+    _lib.inbox_scatter(self.pool_grad, inbox['rows'], inbox['idx'], world, inbox['cap'])
+    t.peers.barrier()                            # every rank's pooled gradient is complete before its peers pull it
+    h = self.pool_Gd
+    for k in range(1, L + 1):
+        last = k == L
+        y, ys = (t.G, t.Gd) if last else self.layer[(k - 1) & 1]
+        self._spmm(h, push=not last, Y=y, add=self.pool_grad, zero_add=last and L > 1)
+        h = ys
+    if L == 1:
+        self.pool_grad.zero_()
+    _lib.embloss_owner_scatter(t.P, t.G, world, x['req'], x['cnt'], x['cap'], self.reg_weight, B_global, self.sumsq, t.loss)
+    t.adam(lr, l2)
+    t.peers.barrier()
+    return t.loss
+
+
+ShardedLightGCN._step_exchanged = _step_exchanged
 
 
 def sharded_eval(tabs, shards, item_table_local, user, pos, hist_local, k=0, precision=0):
