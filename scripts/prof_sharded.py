@@ -72,28 +72,36 @@ if what in ('both', 'bprmf'):
     GB = B * world
     S.bprmf_step(tabs, u, p, n, GB, 1e-3, 1e-6)
 
+    rec = []
+
+    def timed(name, fn):
+        def w(*a_, **k_):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r_ = fn(*a_, **k_)
+            e1.record()
+            rec.append((name, e0, e1))
+            return r_
+        return w
+    WRAPPED = ('allgather_shards', 'csr_spmm_sharded', 'bpr_fwd_bwd_sharded', 'bpr_fwd_bwd_sharded_staged', 'inbox_scatter',
+               'embloss_sumsq_sharded', 'embloss_scatter_sharded', 'adam_l2_sweep', 'peer_barrier', 'xchg_request', 'xchg_serve',
+               'bpr_fwd_bwd_exchanged', 'embloss_owner_sumsq', 'embloss_owner_scatter')
+    for name in WRAPPED:
+        setattr(_lib, name, timed(name, getattr(_lib, name)))
+
     def step_phases():
-        ph = Phases()
-        ph.mark()
-        if world > 1:
-            inbox = tabs.inbox(GB)
-            _lib.bpr_fwd_bwd_sharded_staged(tabs.T, tabs.Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'], u, p, n, GB,
-                                            D, tabs.loss_part, tabs.ws)
-        else:
-            _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, u, p, n, GB, D, tabs.loss_part, tabs.ws)
-        ph.mark('fwd_bwd_staged')
-        peers.barrier(tabs.loss_part[:1])
-        ph.mark('barrier_1')
-        if world > 1:
-            _lib.inbox_scatter(tabs.G, inbox['rows'], inbox['idx'], world, inbox['cap'])
-        ph.mark('inbox_scatter')
-        tabs.adam(1e-3, 1e-6)
-        ph.mark('adam')
-        peers.barrier()
-        ph.mark('barrier_2')
-        return ph.ms()
+        del rec[:]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        S.bprmf_step(tabs, u, p, n, GB, 1e-3, 1e-6)
+        e1.record()
+        torch.cuda.synchronize()
+        d = {'step': e0.elapsed_time(e1)}
+        for name, a_, b_ in rec:
+            d['sum_' + name] = d.get('sum_' + name, 0.0) + a_.elapsed_time(b_)
+            d['n_' + name] = d.get('n_' + name, 0) + 1
+        return d
     out['bprmf_10Mx2M_d128_b65536'] = median_runs(step_phases)
-    out['bprmf_10Mx2M_d128_b65536']['total'] = sum(out['bprmf_10Mx2M_d128_b65536'].values())
     # the first kernel with ids that are all LOCAL to this rank (no NVLink traffic): what the arithmetic itself costs
     ul = (u // world) * world + rank
     pl_ = (p // world) * world + rank
@@ -149,20 +157,22 @@ if what in ('both', 'lightgcn'):
     torch.cuda.empty_cache()
     lg.step(bu, bp, bn, B * world, 1e-3, 0.0)
 
-    rec = []
+    if 'rec' not in globals():
+        rec = []
 
-    def timed(name, fn):
-        def w(*a_, **k_):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            r_ = fn(*a_, **k_)
-            e1.record()
-            rec.append((name, e0, e1))
-            return r_
-        return w
-    for name in ('allgather_shards', 'csr_spmm_sharded', 'bpr_fwd_bwd_sharded', 'bpr_fwd_bwd_sharded_staged', 'inbox_scatter',
-                 'embloss_sumsq_sharded', 'embloss_scatter_sharded', 'adam_l2_sweep', 'peer_barrier'):
-        setattr(_lib, name, timed(name, getattr(_lib, name)))
+        def timed(name, fn):
+            def w(*a_, **k_):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r_ = fn(*a_, **k_)
+                e1.record()
+                rec.append((name, e0, e1))
+                return r_
+            return w
+        for name in ('allgather_shards', 'csr_spmm_sharded', 'bpr_fwd_bwd_sharded', 'bpr_fwd_bwd_sharded_staged', 'inbox_scatter',
+                     'embloss_sumsq_sharded', 'embloss_scatter_sharded', 'adam_l2_sweep', 'peer_barrier', 'xchg_request',
+                     'xchg_serve', 'bpr_fwd_bwd_exchanged', 'embloss_owner_sumsq', 'embloss_owner_scatter'):
+            setattr(_lib, name, timed(name, getattr(_lib, name)))
 
     def lg_phases():
         del rec[:]

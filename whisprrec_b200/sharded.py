@@ -308,16 +308,21 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
     if staged:
         # large batches: nobody loads from peer memory.  The owners deliver the requested rows (wr_xchg_*), the batch
         # kernel runs on local memory, and the gradient rows are written into the owners' inboxes and reduced there
+        # (Running the dense Adam of the rows the batch does not touch on a second stream beside the exchange was tried:
+        # 1.54 -> 1.66 ms per step at 8 GPUs, profiles/r02_prof_sharded_n8_v4_adam_overlap_experiment.json -- both sides
+        # are HBM-bound, so nothing was hidden and the row-masked sweep is slower than the dense one.)
         inbox = tabs.inbox(B_global)
         x = tabs.exchange(B_global)
         tabs.fetch_rows(x, tabs.P, user, pos, neg)
         _lib.bpr_fwd_bwd_exchanged(x['recv'], x['where'], tabs.Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'],
                                    user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
-    else:
-        _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
-    loss = tabs.peers.barrier(tabs.loss_part[:1])
-    if staged:
+        loss = tabs.peers.barrier(tabs.loss_part[:1])
         _lib.inbox_scatter(tabs.G, inbox['rows'], inbox['idx'], tabs.layout.world, inbox['cap'])
+        tabs.adam(lr, l2)
+        tabs.peers.barrier()
+        return loss
+    _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
+    loss = tabs.peers.barrier(tabs.loss_part[:1])
     tabs.adam(lr, l2)
     tabs.peers.barrier()
     return loss
