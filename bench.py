@@ -609,9 +609,10 @@ def extras_sharded(peers, dev, hbm_peak, flush):
             'ms_per_step': ms, 'interactions_per_s': b * world / (ms * 1e-3), 'rows_per_gpu': lay.n_local,
             'algorithmic_gbs_per_gpu': step_bytes / (ms * 1e-3) / 1e9,
             'frac_of_hbm_peak': step_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
-            'note': 'total table fixed (24.6 GB of state over all GPUs), batch 65536 per GPU; remote gathers over NVLink and '
-                    'remote gradient rows written into the owners\' inboxes inside the BPR kernel, barrier, local inbox '
-                    'reduction, local Adam sweep, barrier'}
+            'note': 'total table fixed (24.6 GB of state over all GPUs), batch 65536 per GPU; row exchange (request lists to '
+                    'the owners, owners store the rows into the requesters\' buffers, batch kernel on local memory, gradient '
+                    'rows into the owners\' inboxes: posted NVLink stores only), local inbox reduction, local Adam sweep; '
+                    '4 cross-GPU barriers per step'}
         del tabs
     except Exception as e:  # noqa: BLE001
         out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {'error': repr(e)}
@@ -848,6 +849,33 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
             del Ub, Ib, us, ps, hp_, hi_
     except Exception as e:  # noqa: BLE001
         out['eval_tcgen05_sweep'] = {'error': repr(e)}
+    try:    # BASELINE.json configs[4]: 1M eval rows x {1M, 2M, 5M, 10M} items, D in {64, 128}, ranks (k = 0) on tcgen05
+        sweep = {}
+        burst = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops', 1649.7) \
+            if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 1590.0
+        Rs, nUs = 1_000_000, 1_000_000
+        for d in (64, 128):
+            g = torch.Generator(device=dev); g.manual_seed(3407)
+            Ub = torch.randn((nUs, d), device=dev, generator=g) / d ** 0.5
+            us = torch.arange(Rs, device=dev, dtype=torch.int64)
+            for nIs in (1_000_000, 2_000_000, 5_000_000, 10_000_000):
+                Ib = torch.randn((nIs, d), device=dev, generator=g)
+                ps = torch.randint(0, nIs, (Rs,), device=dev, generator=g)
+                hp_ = torch.arange(0, (nUs + 1) * 50, 50, device=dev, dtype=torch.int64)
+                hi_ = torch.sort(torch.randint(0, nIs, (nUs, 50), device=dev, generator=g), dim=1).values.to(torch.int32).reshape(-1).contiguous()
+                ws2 = _lib.Workspace(dev)
+                fn = lambda: _lib.eval_rank_topk(Ub, Ib, us, ps, hp_, hi_, ws2, precision=1)
+                fn(); torch.cuda.synchronize()
+                med, _ = timed(fn, 2)
+                tf = 2.0 * Rs * nIs * d / (med * 1e-3) / 1e12
+                sweep['1Mx%dM_d%d' % (nIs // 1_000_000, d)] = {'users_per_s': Rs / (med * 1e-3), 'ms': med, 'tflops': tf,
+                                                               'frac_of_bf16_burst_peak': tf / burst}
+                del Ib, ps, hi_
+            del Ub
+        sweep['note'] = 'embeddings N(0, 1/D), history 50 items per user, seed 3407; timed in isolation -> burst peak %.1f TFLOP/s' % burst
+        out['eval_sweep_configs4'] = sweep
+    except Exception as e:  # noqa: BLE001
+        out['eval_sweep_configs4'] = {'error': repr(e)}
     try:    # LightGCN L=2 on the same graph (BASELINE.json configs[2])
         lg, lrun, ldata = make_model(corpus, dev, 'LightGCN', gcn_layers=2)
         batches = lrun.epoch_batches(ldata['train'])
