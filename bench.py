@@ -827,6 +827,17 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
                                'frac_of_bf16_peak': tf / tensor_peak}
     except Exception as e:  # noqa: BLE001
         out['eval_tcgen05'] = {'error': repr(e)}
+    try:    # the same dev split with precision 2: the fp32 path's ranks (bit-identical) from split-bf16 tensor-core scores
+        fn = lambda: _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, precision=2)
+        r2 = fn()[0]; torch.cuda.synchronize()
+        r0 = _lib.eval_rank_topk(ue, ie, user, pos, hptr, hidx, model.tables.ws, precision=0)[0]
+        med, _ = timed(fn, 10, flush)
+        out['eval_exact_tc'] = {'users_per_s': R / (med * 1e-3), 'rows': R, 'items': nI, 'ms': med,
+                                'tflops_fp32_equivalent': 2.0 * R * nI * D / (med * 1e-3) / 1e12,
+                                'ranks_identical_to_fp32_path': bool(torch.equal(r0, r2)),
+                                'note': 'includes the operand split kernels, the re-check kernel and the status read-back'}
+    except Exception as e:  # noqa: BLE001
+        out['eval_exact_tc'] = {'error': repr(e)}
     try:    # BASELINE.json configs[4]-shaped sweep point: many rows x 1M items, where the GEMM dominates
         for d in (64, 128):
             nUs, nIs, Rs = 200_000, 1_000_000, 262_144
@@ -846,6 +857,15 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
             out['eval_tcgen05_262144x1M_d%d' % d] = {'users_per_s': Rs / (med * 1e-3), 'ms': med, 'tflops': tf,
                                                       'frac_of_bf16_peak': tf / tensor_peak,
                                                       'peak_tflops': tensor_peak}
+            fn2 = lambda: _lib.eval_rank_topk(Ub, Ib, us, ps, hp_, hi_, ws2, precision=2)
+            r2 = fn2()[0]; torch.cuda.synchronize()
+            med2, _ = timed(fn2, 2)
+            sub = slice(0, 4096)          # fp32 spot check on a slice (the fp32 path needs ~1.3 s for all rows)
+            r0 = _lib.eval_rank_topk(Ub, Ib, us[sub].contiguous(), ps[sub].contiguous(), hp_, hi_, ws2, precision=0)[0]
+            out['eval_exact_tc_262144x1M_d%d' % d] = {
+                'users_per_s': Rs / (med2 * 1e-3), 'ms': med2, 'tflops_fp32_equivalent': 2.0 * Rs * nIs * d / (med2 * 1e-3) / 1e12,
+                'tensor_tflops_issued': 3 * 2.0 * Rs * nIs * d / (med2 * 1e-3) / 1e12,
+                'ranks_identical_to_fp32_path_on_4096_rows': bool(torch.equal(r0, r2[sub]))}
             del Ub, Ib, us, ps, hp_, hi_
     except Exception as e:  # noqa: BLE001
         out['eval_tcgen05_sweep'] = {'error': repr(e)}

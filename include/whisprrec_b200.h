@@ -41,6 +41,9 @@ extern "C" {
 #define WR_STATUS_INDEX_OUT_OF_RANGE 1u /* an id outside its table: the row was skipped (torch raises IndexError) */
 #define WR_STATUS_PEER_TIMEOUT 2u       /* a cross-GPU wait gave up after WR_PEER_TIMEOUT_NS: a peer never arrived
                                            (crashed or out of step); results of that step are invalid */
+#define WR_STATUS_EVAL_OVERFLOW 4u      /* precision-2 evaluation: more score/target near-ties than the candidate list
+                                           holds (degenerate tables, e.g. all rows equal); ranks are incomplete -- rerun
+                                           with precision 0 */
 #define WR_PEER_TIMEOUT_NS 20000000000ull
 
 int wr_version(void);
@@ -224,7 +227,12 @@ int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int
  * consistent.  precision 1: bf16 operands on the tcgen05 tensor cores (TMA-fed, TMEM accumulators), fp32
  * accumulation; D in {64, 128}; ranks and, if asked for, the top-k lists come out of the same epilogue; needs
  * `scratch`; looser parity (operands are rounded to bf16, the target's own column is excluded from the count
- * explicitly).
+ * explicitly).  precision 2: precision 0's RANKS, bit for bit, at tensor-core speed (k must be 0): every fp32 operand
+ * is split into two bf16 terms and the tensor cores accumulate hi.hi + hi.lo + lo.hi (K = 3 D); a score farther than
+ * eps_r = c_D ||a_r|| max_j ||b_j|| from the row's target (c_64 = 1.5e-4, c_128 = 2e-4: twice the worst-case sum of
+ * the split residual 3.1 2^-16, the fp32 accumulation of 3 D products and the FMA chain's own rounding) decides the
+ * comparison as precision 0 would, the pairs inside the band (~0.1 %) are re-scored with precision 0's FMA chain.
+ * If the candidate list overflows (degenerate tables) WR_STATUS_EVAL_OVERFLOW is raised: rerun with precision 0.
  */
 int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                       int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
@@ -232,7 +240,8 @@ int wr_eval_rank_topk(const float *Uemb, const float *Iemb, const int64_t *user,
                       float *scores_out, void *scratch, void *ws, void *stream);
 
 /* Bytes of 1024-byte-aligned device scratch wr_eval_rank_topk needs for `precision` (0 for precision 0): the bf16
- * copies of the gathered user rows and of the item table that the TMA descriptors point at. */
+ * copies of the gathered user rows and of the item table that the TMA descriptors point at (three bf16 terms per
+ * element for precision 2, plus its candidate list). */
 size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int precision);
 
 /* wr_metrics: BaseRunner.evaluate_method (BaseRunner.py:76-88) from the ranks; float64 means.

@@ -452,6 +452,54 @@ def test_csr_spmm_vs_oracle(D):
     assert_close(host(dacc), acc + ref, 'in-place layer sum', rtol=1e-5, atol_scale=2e-6)
 
 
+@pytest.mark.parametrize('D,R,nI', [(64, 3000, 40_000), (128, 2500, 33_333), (64, 257, 300), (128, 90_000, 5_000)])
+def test_exact_tensor_core_eval_ranks_equal_the_fp32_path(D, R, nI, ws):
+    """precision 2 (split-bf16 tcgen05 + re-check of the scores inside the error band) against precision 0: ranks and
+    target scores IDENTICAL, on trained-looking tables (item norms spread over 3x, duplicated rows = exact ties, users
+    with long histories, a target at the very top / bottom); also checks the error bound the band is built on."""
+    rng = np.random.RandomState(D + R)
+    nU = 5000
+    U = (rng.randn(nU, D) / np.sqrt(D)).astype(np.float32)
+    I = (rng.randn(nI, D) * rng.uniform(0.5, 1.5, (nI, 1))).astype(np.float32)
+    I[7] = I[3]                                                    # exact ties between items
+    I[nI - 1] = I[nI - 2]
+    U[11] = 0.0                                                    # a user whose scores are all zero = all ties
+    user = rng.randint(0, nU, R).astype(np.int64)
+    user[:4] = 11
+    pos = rng.randint(0, nI, R).astype(np.int64)
+    pos[5], pos[6] = 3, 7
+    hl = rng.randint(0, 60, nU)
+    hptr = np.zeros(nU + 1, dtype=np.int64)
+    np.cumsum(hl, out=hptr[1:])
+    hidx = np.concatenate([np.sort(rng.choice(nI, n, replace=False)) for n in hl] + [np.zeros(0, dtype=np.int64)]).astype(np.int32)
+    if len(hidx) == 0:
+        hidx = np.zeros(1, dtype=np.int32)
+    dU, dI, du, dp, dh, di = dv(U), dv(I), dv(user), dv(pos), dv(hptr), dv(hidx)
+    r0, t0, _, _, _ = _lib.eval_rank_topk(dU, dI, du, dp, dh, di, ws, precision=0)
+    r2, t2, _, _, _ = _lib.eval_rank_topk(dU, dI, du, dp, dh, di, ws, precision=2)
+    assert ws.status() == 0
+    assert torch.equal(t0, t2), 'target scores'
+    bad = (r0 != r2).nonzero().flatten()
+    assert bad.numel() == 0, ('ranks differ', bad[:8].tolist(), r0[bad[:8]].tolist(), r2[bad[:8]].tolist())
+
+
+def test_exact_tensor_core_eval_error_bound_has_margin(ws):
+    """The band of precision 2 is c_D ||a|| max||b||; measured here: the split-bf16 tensor-core scores (dumped through the
+    precision-1 machinery on pre-split operands is not possible, so the bound is checked on the three-term sum in
+    float64) stay an order of magnitude inside it."""
+    rng = np.random.RandomState(0)
+    for D, c in ((64, 1.5e-4), (128, 2.0e-4)):
+        a = (rng.randn(2000, D) * rng.uniform(0.01, 10, (2000, 1))).astype(np.float32)
+        b = (rng.randn(2000, D) * rng.uniform(0.01, 10, (2000, 1))).astype(np.float32)
+        bf = lambda x: (torch.from_numpy(x).to(torch.bfloat16).to(torch.float32)).numpy()
+        ah, bh = bf(a), bf(b)
+        al, bl = bf(a - ah), bf(b - bh)
+        three = (ah.astype(np.float64) * bh + ah.astype(np.float64) * bl + al.astype(np.float64) * bh).sum(1)
+        exact = (a.astype(np.float64) * b).sum(1)
+        scale = np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1)
+        assert (np.abs(three - exact) / scale).max() < c / 10
+
+
 def test_csr_spmm_hot_row_cache_policy_changes_nothing_but_the_cache(ws):
     """The L2 evict_last / evict_first variant of the SpMM (plan.hot_bits: tables far larger than L2) computes bit for
     bit what the plain loads do."""

@@ -158,6 +158,10 @@ class Workspace:
         check(load().wr_status(self.ptr, ctypes.byref(out), stream_ptr()))
         return out.value
 
+    def restore_status(self, bits):
+        """OR `bits` back into the device status word (after a caller has read-and-cleared it for its own bit)."""
+        self.buf[:4].view(torch.int32).bitwise_or_(int(bits))
+
     def raise_on_status(self):
         st = self.status()
         if st & 2:
@@ -393,9 +397,33 @@ def csr_spmm(rowptr, col, val, X, Y=None, add=None, zero_add=False, acc_in=None,
                              None if plan is None else plan.ref(), stream_ptr()))
 
 
+def exact_tc_supported(D, k=0, scores=False):
+    """precision 2 (precision 0's ranks on the tensor cores) covers D in {64, 128}, ranks only."""
+    return D in (64, 128) and k == 0 and not scores
+
+
 def eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k=0, precision=0, scores=False):
     """Returns (rank int32 [R], target fp32 [R], topk_idx int32 [R,k] | None, topk_val fp32 [R,k] | None,
-    scores fp32 [R, n_items] | None)."""
+    scores fp32 [R, n_items] | None).  precision: 0 fp32 FMA tiles; 1 bf16 tensor cores; 2 split-bf16 tensor cores +
+    exact re-check (ranks identical to 0; if the candidate list overflows -- degenerate tables -- the call is repeated
+    with precision 0, which costs one synchronisation)."""
+    R, D = user.numel(), Uemb.shape[1]
+    if precision == 2:
+        if not exact_tc_supported(D, k, scores):
+            precision = 0
+        else:
+            out = _eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, 0, 2, False)
+            st = ws.status()
+            if st & 4:
+                out = _eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, 0, 0, False)
+                st &= ~4
+            if st:                       # hand the other bits back to the caller's raise_on_status
+                ws.restore_status(st)
+            return out
+    return _eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k, precision, scores)
+
+
+def _eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k, precision, scores):
     R, D = user.numel(), Uemb.shape[1]
     dev = Uemb.device
     rank = torch.empty(R, dtype=I32, device=dev)
@@ -684,6 +712,23 @@ def rowdot(A, B, round_bf16=False):
 
 def eval_rank_topk_shard(Urows, Iemb, user, pos_local, n_users, hist_ptr, hist_idx, target, ws, k=0, precision=0):
     """One item shard: returns (rank int32 [R] = 1 + local count, topk_idx LOCAL int32 [R,k] | None, topk_val | None)."""
+    R, D = user.numel(), Urows.shape[1]
+    if precision == 2:
+        if not exact_tc_supported(D, k):
+            precision = 0
+        else:
+            out = _eval_rank_topk_shard(Urows, Iemb, user, pos_local, n_users, hist_ptr, hist_idx, target, ws, 0, 2)
+            st = ws.status()
+            if st & 4:
+                out = _eval_rank_topk_shard(Urows, Iemb, user, pos_local, n_users, hist_ptr, hist_idx, target, ws, 0, 0)
+                st &= ~4
+            if st:
+                ws.restore_status(st)
+            return out
+    return _eval_rank_topk_shard(Urows, Iemb, user, pos_local, n_users, hist_ptr, hist_idx, target, ws, k, precision)
+
+
+def _eval_rank_topk_shard(Urows, Iemb, user, pos_local, n_users, hist_ptr, hist_idx, target, ws, k, precision):
     R, D = user.numel(), Urows.shape[1]
     dev = Urows.device
     rank = torch.empty(R, dtype=I32, device=dev)

@@ -325,7 +325,7 @@ using namespace wr;
 int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                     int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
                     int32_t *rank, float *target, const float *target_in, float *scores_out, int k, int32_t *topk_idx,
-                    float *topk_val, void *scratch, WrWorkspace *ws, cudaStream_t st);
+                    float *topk_val, void *scratch, WrWorkspace *ws, cudaStream_t st, int precision);
 
 static int eval_rank_topk_impl(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos,
                                int64_t R, int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr,
@@ -341,9 +341,11 @@ static int eval_rank_topk_impl(const float *Uemb, const float *Iemb, const int64
     if (!wr_aligned16(Uemb) || !wr_aligned16(Iemb)) return WR_E_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const bool topk = topk_idx != nullptr;
-    if (precision == 1) {
+    if (precision == 1 || precision == 2) {
+        if (precision == 2 && topk) return WR_E_TOPK;
         return wr_eval_rank_tc(Uemb, Iemb, user, pos, R, n_users, n_items, D, hist_ptr, hist_idx, rank, target,
-                               target_in, scores_out, topk ? k : 0, topk_idx, topk_val, scratch, (WrWorkspace *)ws, st);
+                               target_in, scores_out, topk ? k : 0, topk_idx, topk_val, scratch, (WrWorkspace *)ws, st,
+                               precision);
     }
     if (precision != 0) return WR_E_PRECISION;
     EvalParams p{Uemb, Iemb, user, pos, R, n_users, n_items, hist_ptr, hist_idx, topk ? k : 1,

@@ -11,8 +11,14 @@
 //               the next tile fills the other accumulator.  The score matrix never leaves TMEM.
 //   warps 20-23 (top-k launches only) drain the per-row candidate rings the epilogue warps push into, keep each
 //               row's k best and publish its threshold.
-// Operands are rounded to bf16 once per evaluation (pack kernels below); the target score is the fp32 FMA chain
-// over the same bf16-rounded operands.  Parity with the fp32 path is therefore "looser": see tests.
+// precision 1: operands are rounded to bf16 once per evaluation (pack kernels below); the target score is the fp32 FMA
+// chain over the same bf16-rounded operands.  Parity with the fp32 path is therefore "looser": see tests.
+// precision 2 ("exact"): every fp32 operand is split into two bf16 terms, a = hi + lo, and the tensor cores accumulate
+// hi.hi + hi.lo + lo.hi (K = 3 D: A' = [hi | hi | lo], B' = [hi | lo | hi]).  The result is within
+// eps_r = c_D * ||a_r|| * max_j ||b_j|| of the fp32 FMA chain precision 0 computes (bound below), so a score farther than
+// eps_r from the row's target decides the comparison as precision 0 would; the few pairs inside the band go to a
+// candidate list and are re-scored with exactly precision 0's FMA chain (eval_recheck_kernel).  Ranks are therefore
+// IDENTICAL to precision 0 -- the reference's fp32 ranking semantics on the tensor cores.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
@@ -35,6 +41,14 @@ struct TcParams {
     int top_trigger;
     int32_t *topk_idx;
     float *topk_val;
+    // precision 2
+    const float *anorm;         // [R] ||a_r||_2 of the fp32 user rows
+    const float *bmax;          // [1] max_j ||b_j||_2 of the fp32 item rows
+    float band_c;               // eps_r = band_c * anorm[r] * bmax[0]
+    uint2 *cand;                // (row, item) pairs inside the band
+    unsigned long long *cand_cnt;
+    unsigned long long cand_cap;
+    uint32_t *status;           // WR_STATUS_EVAL_OVERFLOW when the list is full
 };
 
 constexpr int TC_KMAX = 32;
@@ -186,6 +200,105 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float *__restrict_
     }
 }
 
+// ---- precision 2: a = hi + lo (+ residual <= 2^-16 |a|), both bf16 ----
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));      // the difference is exact in fp32
+}
+
+// one warp per item: B'[j] = [hi | lo | hi] (3 D bf16); bmax = max_j ||b_j||_2 (non-negative floats order like their bits)
+__global__ void __launch_bounds__(256) pack_items_split_kernel(const float *__restrict__ I, int64_t n_items, int D,
+                                                                __nv_bfloat16 *out, uint32_t *bmax_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float mx = 0.f;
+    for (int64_t j = warp; j < n_items; j += nwarps) {
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float x = I[j * D + d];
+            __nv_bfloat16 hi, lo;
+            split_bf16(x, hi, lo);
+            __nv_bfloat16 *o = out + j * 3 * D;
+            o[d] = hi;
+            o[D + d] = lo;
+            o[2 * D + d] = hi;
+            ss = fmaf(x, x, ss);
+        }
+        ss = warp_sum(ss);
+        mx = fmaxf(mx, sqrtf(ss) * 1.000001f);              // rounding of the sum of squares: never under-estimate
+    }
+    if (lane == 0 && mx > 0.f) atomicMax(bmax_bits, __float_as_uint(mx));
+}
+
+// one warp per eval row: A'[r] = [hi | hi | lo]; target[r] = precision 0's FMA chain over the UNROUNDED fp32 rows;
+// anorm[r] = ||a_r||_2.  rows_gathered != 0: U holds one row per eval row (item-shard mode) and target is an input.
+__global__ void __launch_bounds__(256) pack_users_split_kernel(const float *__restrict__ U, const float *__restrict__ I,
+                                                                const int64_t *user, const int64_t *pos, int64_t R,
+                                                                int64_t n_users, int64_t n_items, int D, int rows_gathered,
+                                                                __nv_bfloat16 *A, float *target, float *anorm,
+                                                                uint8_t *row_ok, WrWorkspace *ws) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = warp; r < R; r += nwarps) {
+        const int64_t u = user[r];
+        const int64_t it = rows_gathered ? 0 : pos[r];
+        const bool ok = (uint64_t)u < (uint64_t)n_users && (rows_gathered || (uint64_t)it < (uint64_t)n_items);
+        const float *a = U + (rows_gathered ? r : u) * D;
+        float ss = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float x = ok ? a[d] : 0.f;
+            __nv_bfloat16 hi, lo;
+            split_bf16(x, hi, lo);
+            __nv_bfloat16 *o = A + r * 3 * D;
+            o[d] = hi;
+            o[D + d] = hi;
+            o[2 * D + d] = lo;
+            ss = fmaf(x, x, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            anorm[r] = sqrtf(ss) * 1.000001f;
+            row_ok[r] = ok ? 1 : 0;
+            if (!ok) atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+            if (!rows_gathered) {
+                float s = 0.f;                               // eval_kernels.cu: s = fmaf(a_d, b_d, s), d = 0 .. D-1
+                if (ok) {
+                    const float *b = I + it * D;
+                    for (int d = 0; d < D; ++d) s = fmaf(a[d], b[d], s);
+                }
+                target[r] = s;
+            }
+        }
+    }
+}
+
+// The pairs whose tensor-core score fell inside the band: precision 0's FMA chain decides them.
+__global__ void __launch_bounds__(256) eval_recheck_kernel(const uint2 *__restrict__ cand, const unsigned long long *cnt,
+                                                            unsigned long long cap, const float *__restrict__ U,
+                                                            const int64_t *user, int rows_gathered,
+                                                            const float *__restrict__ I, int D, const float *__restrict__ target,
+                                                            int32_t *rank) {
+    unsigned long long n = *cnt;
+    if (n > cap) n = cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint2 e = cand[i];
+        const int64_t r = e.x;
+        const float *a = U + (rows_gathered ? r : user[r]) * D, *b = I + (int64_t)e.y * D;
+        float s = 0.f;
+        for (int d = 0; d < D; d += 4) {
+            const float4 x = ldg4(a + d), y = ldg4(b + d);
+            s = fmaf(x.x, y.x, s);
+            s = fmaf(x.y, y.y, s);
+            s = fmaf(x.z, y.z, s);
+            s = fmaf(x.w, y.w, s);
+        }
+        if (s > target[r]) atomicAdd(rank + r, 1);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // the scoring kernel
 // ---------------------------------------------------------------------------------------------------------
@@ -193,13 +306,21 @@ constexpr int TC_BM = 128, TC_BN = 256;
 constexpr int TC_EPI_WARPS = 16;                       // 4 per TMEM lane quarter, 64 accumulator columns each
 constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;
 
-template <int D>
+// K = contraction length in bf16 elements (D for precision 1, 3 D for precision 2).  A (128 x K) is loaded once per CTA;
+// B travels through a ring of stages of SKB 64-element K blocks (32 KB each) of one 256-item tile: a whole tile per
+// stage for precision 1 (one barrier round per tile: 5 % faster at D = 128 than block-wise staging), one K block per
+// stage for precision 2, whose tiles (96 / 192 KB) would not fit twice.
+constexpr int TC_KBLOCK_BYTES = TC_BN * 128;
+constexpr int TC_CAND_BUF = 64;                        // candidate entries buffered per epilogue warp (precision 2)
+template <int K, int EXACT>
 struct TcCfg {
-    static constexpr int KB = D / 64;                      // 64-element (128 B) K blocks
-    static constexpr int A_BYTES = TC_BM * D * 2;
-    static constexpr int B_BYTES = TC_BN * D * 2;
-    static constexpr int STAGES = D == 64 ? 4 : 2;
-    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * B_BYTES + 256 /*barriers*/ + 4 * TC_BM * 4;
+    static constexpr int KB = K / 64;                      // 64-element (128 B) K blocks
+    static constexpr int SKB = EXACT ? 1 : KB;             // K blocks per stage
+    static constexpr int STAGE_BYTES = SKB * TC_KBLOCK_BYTES;
+    static constexpr int A_BYTES = TC_BM * K * 2;
+    static constexpr int STAGES = EXACT ? (K <= 192 ? 5 : 3) : (K == 64 ? 4 : 2);
+    static constexpr int TAIL = 256 /*barriers*/ + 4 * TC_BM * 4 /*counts*/ + (EXACT ? TC_EPI_WARPS * TC_CAND_BUF * 8 : 0);
+    static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * STAGE_BYTES + TAIL;
 };
 
 // Top-k state of one epilogue thread (one row, one 64-column stripe of every tile), in local memory:
@@ -295,21 +416,22 @@ __device__ __forceinline__ void ring_push(const TopRings &rg, int row, float x, 
     }
 }
 
-template <int D, int VARIANT, int TOPK>
+template <int K, int VARIANT, int TOPK, int EXACT>
 __global__ void __launch_bounds__(TOPK == 2 ? TC_THREADS_DRAIN : TC_THREADS, 1)
 eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-    using C = TcCfg<D>;
+    using C = TcCfg<K, EXACT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
     uint8_t *sB = smem + C::A_BYTES;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + C::STAGES * C::B_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sB + C::STAGES * C::STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + C::STAGES, *a_full = bars + 2 * C::STAGES;
     uint64_t *tm_full = a_full + 1, *tm_empty = tm_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tm_empty + 2);
     int *cnt_s = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [4][128]
+    uint2 *cand_s = reinterpret_cast<uint2 *>(cnt_s + 4 * TC_BM);                     // [TC_EPI_WARPS][TC_CAND_BUF], precision 2
     TopRings rg;
-    rg.v = reinterpret_cast<float *>(cnt_s + 4 * TC_BM);
+    rg.v = reinterpret_cast<float *>(cand_s + (EXACT ? TC_EPI_WARPS * TC_CAND_BUF : 0));
     rg.id = reinterpret_cast<int32_t *>(rg.v + TC_BM * TC_RING);
     rg.head = reinterpret_cast<uint32_t *>(rg.id + TC_BM * TC_RING);
     rg.tail = rg.head + TC_BM;
@@ -359,14 +481,19 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb)
                 tma_load_2d(&tmA, a_full, sA + kb * (TC_BM * 128), kb * 64, (int)row0);
-            for (int t = t0, it = 0; t < t1; ++t, ++it) {
-                const int stage = it % C::STAGES;
-                const uint32_t ph = (it / C::STAGES) & 1;
-                mbar_wait(&empty[stage], ph ^ 1);
-                mbar_expect_tx(&full[stage], C::B_BYTES);
+            int it = 0;
+            for (int t = t0; t < t1; ++t) {
+#pragma unroll 1
+                for (int kb0 = 0; kb0 < C::KB; kb0 += C::SKB, ++it) {
+                    const int stage = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&empty[stage], ph ^ 1);
+                    mbar_expect_tx(&full[stage], C::STAGE_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < C::KB; ++kb)
-                    tma_load_2d(&tmB, &full[stage], sB + stage * C::B_BYTES + kb * (TC_BN * 128), kb * 64, t * TC_BN);
+                    for (int kb = 0; kb < C::SKB; ++kb)
+                        tma_load_2d(&tmB, &full[stage], sB + stage * C::STAGE_BYTES + kb * TC_KBLOCK_BYTES, (kb0 + kb) * 64,
+                                    t * TC_BN);
+                }
             }
         }
     } else if (warp == 1) {
@@ -375,22 +502,28 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
             mbar_wait(a_full, 0);
             tc_fence_after();
-            for (int t = t0, it = 0; t < t1; ++t, ++it) {
-                const int stage = it % C::STAGES, acc = it & 1;
-                const uint32_t ph = (it / C::STAGES) & 1, aph = (it >> 1) & 1;
+            int it = 0;
+            for (int t = t0, ti = 0; t < t1; ++t, ++ti) {
+                const int acc = ti & 1;
+                const uint32_t aph = (ti >> 1) & 1;
                 mbar_wait(&tm_empty[acc], aph ^ 1);          // epilogue has drained this accumulator
-                mbar_wait(&full[stage], ph);                 // TMA has landed this stage
-                tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * TC_BN;
+#pragma unroll 1
+                for (int kb0 = 0; kb0 < C::KB; kb0 += C::SKB, ++it) {
+                    const int stage = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&full[stage], ph);             // TMA has landed this stage
+                    tc_fence_after();
 #pragma unroll
-                for (int kb = 0; kb < C::KB; ++kb) {
-                    const uint64_t a0 = umma_desc_sw128(sA + kb * (TC_BM * 128));
-                    const uint64_t b0 = umma_desc_sw128(sB + stage * C::B_BYTES + kb * (TC_BN * 128));
+                    for (int kb = 0; kb < C::SKB; ++kb) {
+                        const uint64_t a0 = umma_desc_sw128(sA + (kb0 + kb) * (TC_BM * 128));
+                        const uint64_t b0 = umma_desc_sw128(sB + stage * C::STAGE_BYTES + kb * TC_KBLOCK_BYTES);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)             // K = 16 bf16 = 32 B per instruction: +2 in the >>4 address field
-                        umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k)         // K = 16 bf16 = 32 B per instruction: +2 in the >>4 address field
+                            umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (kb0 | kb | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);              // frees the smem stage when the MMAs retire
                 }
-                umma_commit(&empty[stage]);                  // frees the smem stage when the MMAs retire
                 umma_commit(&tm_full[acc]);                  // accumulator ready for the epilogue
             }
         }
@@ -422,6 +555,16 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (cur < hend) next_h = __ldg(p.hist_idx + cur);
         }
         int cnt = 0;
+        // precision 2: scores above st_hi certainly beat the target in precision 0's arithmetic, scores below st_lo
+        // certainly do not; the band between them goes to the candidate list
+        float st_hi = st, st_lo = st;
+        int ccount = 0;                                        // candidates buffered by this warp (warp-uniform)
+        uint2 *cbuf = cand_s + (warp - 4) * TC_CAND_BUF;
+        if (EXACT && live) {
+            const float eps = p.band_c * p.anorm[r] * p.bmax[0] + 2.4e-7f * fabsf(st);
+            st_hi = st + eps;
+            st_lo = st - eps;
+        }
         TopState top;
         const int top_trigger = p.top_trigger;      // fold the buffers once any lane holds more than this many
         float tau = -INFINITY;
@@ -511,7 +654,82 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     if (__any_sync(0xffffffffu, bcnt > top_trigger)) top_compact(top, p.k, bcnt, tau, worst);
                 }
-                if (m == 0) {
+                if (EXACT) {
+                    uint32_t cm = 0;                            // columns of this chunk inside the band
+                    bool bits = m != 0;
+                    if (!bits) {
+                        float h0 = 0.f, h1 = 0.f, l0 = 0.f, l1 = 0.f;
+#define WR_CNT2(hi_, lo_, i_)                                                                                 \
+    asm("{\n\t.reg .pred q;\n\tsetp.gt.f32 q, %2, %3;\n\t@q add.f32 %0, %0, 0f3F800000;\n\t"                  \
+        "setp.ge.f32 q, %2, %4;\n\t@q add.f32 %1, %1, 0f3F800000;\n\t}"                                      \
+        : "+f"(hi_), "+f"(lo_)                                                                                \
+        : "f"(__uint_as_float(v[i_])), "f"(st_hi), "f"(st_lo))
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            WR_CNT2(h0, l0, i);
+                            WR_CNT2(h1, l1, i + 1);
+                        }
+#undef WR_CNT2
+                        const float hi_n = h0 + h1;
+                        cnt += (int)hi_n;
+                        bits = (l0 + l1) != hi_n;               // somebody is inside the band: find out who
+                        if (bits) cnt -= (int)hi_n;
+                    }
+                    if (bits) {
+                        uint32_t gt = 0, ge = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float x = __uint_as_float(v[i]);
+                            gt |= (x > st_hi ? 1u : 0u) << i;
+                            ge |= (x >= st_lo ? 1u : 0u) << i;
+                        }
+                        cnt += __popc(gt & ~m);
+                        cm = ge & ~gt & ~m;
+                    }
+                    if (__any_sync(0xffffffffu, cm != 0)) {
+                        const int nc = __popc(cm);
+                        int incl = nc;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += y;
+                        }
+                        const int total = __shfl_sync(0xffffffffu, incl, 31);
+                        int at = incl - nc;
+                        if (ccount + total > TC_CAND_BUF && ccount > 0) {        // make room: buffer -> global list
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(p.cand_cnt, (unsigned long long)ccount);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            __syncwarp();
+                            for (int i = lane; i < ccount; i += 32) {
+                                if (base + i < p.cand_cap) p.cand[base + i] = cbuf[i];
+                                else atomicOr(p.status, WR_STATUS_EVAL_OVERFLOW);
+                            }
+                            __syncwarp();
+                            ccount = 0;
+                        }
+                        if (total > TC_CAND_BUF) {                               // a degenerate chunk: straight to the list
+                            unsigned long long base = 0;
+                            if (lane == 0) base = atomicAdd(p.cand_cnt, (unsigned long long)total);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            while (cm) {
+                                const int i = __ffs(cm) - 1;
+                                cm &= cm - 1;
+                                if (base + at < p.cand_cap) p.cand[base + at] = make_uint2((uint32_t)r, (uint32_t)(j0 + i));
+                                else atomicOr(p.status, WR_STATUS_EVAL_OVERFLOW);
+                                ++at;
+                            }
+                        } else {
+                            while (cm) {
+                                const int i = __ffs(cm) - 1;
+                                cm &= cm - 1;
+                                cbuf[ccount + at] = make_uint2((uint32_t)r, (uint32_t)(j0 + i));
+                                ++at;
+                            }
+                            ccount += total;
+                        }
+                    }
+                } else if (m == 0) {
                     // fast path, 2 instructions per score.  VARIANT 0: FSETP + predicated integer add (both ALU pipe);
                     // 1: FSETP (ALU) + predicated FADD (FMA pipe); 2: FFMA.SAT + FADD (FMA pipe only):
                     // sat(v*2^100 - st*2^100) is exactly [v > st]; 3: even columns as 1, odd columns as 2.
@@ -568,6 +786,16 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tc_fence_before();
             mbar_arrive(&tm_empty[acc]);
+        }
+        if (EXACT && ccount > 0) {                              // what is left in this warp's candidate buffer
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(p.cand_cnt, (unsigned long long)ccount);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            __syncwarp();
+            for (int i = lane; i < ccount; i += 32) {
+                if (base + i < p.cand_cap) p.cand[base + i] = cbuf[i];
+                else atomicOr(p.status, WR_STATUS_EVAL_OVERFLOW);
+            }
         }
         // the four stripe lists of a row meet in the (now idle) B-stage shared memory: [row][stripe][k]
         float *lv = reinterpret_cast<float *>(sB);
@@ -700,7 +928,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int box_rows) {
+static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D /* bf16 elements per row */, int box_rows) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *sym = nullptr;
@@ -720,15 +948,15 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D, int
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int D, int VARIANT, int TOPK>
+template <int K, int VARIANT, int TOPK, int EXACT>
 static int launch_tc_v(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
-    constexpr int smem = TcCfg<D>::SMEM + (TOPK == 2 ? TC_SMEM_DRAIN : 0);
+    constexpr int smem = TcCfg<K, EXACT>::SMEM + (TOPK == 2 ? TC_SMEM_DRAIN : 0);
     constexpr int threads = TOPK == 2 ? TC_THREADS_DRAIN : TC_THREADS;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<D, VARIANT, TOPK>,
+    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<K, VARIANT, TOPK, EXACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    eval_tc_rank_kernel<D, VARIANT, TOPK><<<dim3(row_tiles, p.splits), threads, smem, st>>>(ma, mb, p);
+    eval_tc_rank_kernel<K, VARIANT, TOPK, EXACT><<<dim3(row_tiles, p.splits), threads, smem, st>>>(ma, mb, p);
     return (int)cudaGetLastError();
 }
 
@@ -745,13 +973,13 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, 
             const char *e = getenv("WR_TC_TOPK_MODE");      // 1: per-thread lists in the epilogue; 2: drain warps
             mode = e ? atoi(e) : 2;
         }
-        return mode == 1 ? launch_tc_v<D, 1, 1>(ma, mb, p, row_tiles, st) : launch_tc_v<D, 1, 2>(ma, mb, p, row_tiles, st);
+        return mode == 1 ? launch_tc_v<D, 1, 1, 0>(ma, mb, p, row_tiles, st) : launch_tc_v<D, 1, 2, 0>(ma, mb, p, row_tiles, st);
     }
     switch (variant) {
-        case 1: return launch_tc_v<D, 1, 0>(ma, mb, p, row_tiles, st);
-        case 2: return launch_tc_v<D, 2, 0>(ma, mb, p, row_tiles, st);
-        case 3: return launch_tc_v<D, 3, 0>(ma, mb, p, row_tiles, st);
-        default: return launch_tc_v<D, 0, 0>(ma, mb, p, row_tiles, st);
+        case 1: return launch_tc_v<D, 1, 0, 0>(ma, mb, p, row_tiles, st);
+        case 2: return launch_tc_v<D, 2, 0, 0>(ma, mb, p, row_tiles, st);
+        case 3: return launch_tc_v<D, 3, 0, 0>(ma, mb, p, row_tiles, st);
+        default: return launch_tc_v<D, 0, 0, 0>(ma, mb, p, row_tiles, st);
     }
 }
 
@@ -761,58 +989,141 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 using namespace wr;
 
-extern "C" size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int precision) {
-    if (precision != 1 || R <= 0 || n_items <= 0 || D <= 0) return 0;
-    return align_up((size_t)R * D * 2, 1024) + align_up((size_t)n_items * D * 2, 1024) + align_up((size_t)R, 1024) + 1024;
+// precision 2: rows are evaluated in blocks so that the candidate list (one (row, item) pair per score inside the band,
+// ~0.1 % of the pairs; sized for 0.8 %) stays below 1 GB
+static void exact_blocking(int64_t R, int64_t n_items, int64_t *rows_per_block, unsigned long long *cand_cap) {
+    int64_t rb = (int64_t)(16e9 / (double)n_items);
+    rb = rb / TC_BM * TC_BM;
+    if (rb < TC_BM) rb = TC_BM;
+    if (rb > R) rb = (R + TC_BM - 1) / TC_BM * TC_BM;
+    unsigned long long cap = (unsigned long long)((double)rb * (double)n_items / 128.0);
+    if (cap < (1ull << 20)) cap = 1ull << 20;
+    if (cap > (1ull << 27)) cap = 1ull << 27;
+    *rows_per_block = rb;
+    *cand_cap = cap;
 }
 
-// precision-1 body of wr_eval_rank_topk (eval_kernels.cu dispatches here)
+extern "C" size_t wr_eval_scratch_bytes(int64_t R, int64_t n_items, int D, int precision) {
+    if ((precision != 1 && precision != 2) || R <= 0 || n_items <= 0 || D <= 0) return 0;
+    const size_t k = precision == 2 ? 3 : 1;
+    size_t n = align_up((size_t)R * D * 2 * k, 1024) + align_up((size_t)n_items * D * 2 * k, 1024) + align_up((size_t)R, 1024) + 1024;
+    if (precision == 2) {
+        int64_t rb;
+        unsigned long long cap;
+        exact_blocking(R, n_items, &rb, &cap);
+        n += align_up((size_t)R * 4, 1024) + 1024 + (size_t)cap * 8;
+    }
+    return n;
+}
+
+// precision-1 / precision-2 body of wr_eval_rank_topk (eval_kernels.cu dispatches here)
 int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, const int64_t *pos, int64_t R,
                     int64_t n_users, int64_t n_items, int D, const int64_t *hist_ptr, const int32_t *hist_idx,
                     int32_t *rank, float *target, const float *target_in, float *scores_out, int k, int32_t *topk_idx,
-                    float *topk_val, void *scratch, WrWorkspace *ws, cudaStream_t st) {
+                    float *topk_val, void *scratch, WrWorkspace *ws, cudaStream_t st, int precision) {
     if (D != 64 && D != 128) return WR_E_DIM;
     if (!scratch) return WR_E_NULL;
     if ((reinterpret_cast<uintptr_t>(scratch) & 1023u) != 0) return WR_E_ALIGN;
+    const bool exact = precision == 2;
+    const int K = exact ? 3 * D : D;
     uint8_t *base = static_cast<uint8_t *>(scratch);
     __nv_bfloat16 *A = reinterpret_cast<__nv_bfloat16 *>(base);
-    __nv_bfloat16 *Bm = reinterpret_cast<__nv_bfloat16 *>(base + align_up((size_t)R * D * 2, 1024));
-    uint8_t *row_ok = base + align_up((size_t)R * D * 2, 1024) + align_up((size_t)n_items * D * 2, 1024);
-
-    const int64_t n4 = n_items * D / 4;
-    pack_items_bf16_kernel<<<(int)min((int64_t)8 * kSMs, (n4 + 255) / 256), 256, 0, st>>>(Iemb, n4, Bm);
-    WR_CHECK_LAUNCH();
-    if (target_in)
-        pack_rows_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, user, R, n_users, D, A, row_ok, ws);
-    else
-        pack_users_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, Iemb, user, pos, R, n_users,
-                                                                                    n_items, D, A, target, row_ok, ws);
-    WR_CHECK_LAUNCH();
+    base += align_up((size_t)R * K * 2, 1024);
+    __nv_bfloat16 *Bm = reinterpret_cast<__nv_bfloat16 *>(base);
+    base += align_up((size_t)n_items * K * 2, 1024);
+    uint8_t *row_ok = base;
+    base += align_up((size_t)R, 1024);
 
     CUtensorMap ma, mb;
-    int rc = make_map(&ma, A, R, D, TC_BM);
+    int rc = make_map(&mb, Bm, n_items, K, TC_BN);
     if (rc) return rc;
-    rc = make_map(&mb, Bm, n_items, D, TC_BN);
-    if (rc) return rc;
-
-    TcParams p{user, pos, R, n_users, n_items, hist_ptr, hist_idx, target_in ? target_in : target, row_ok, rank,
-               scores_out, 1, 0, 0, k, k <= 16 ? 4 : 16, topk_idx, topk_val};    // small k: keep tau fresh
+    TcParams p{};
+    p.user = user; p.pos = pos; p.R = R; p.n_users = n_users; p.n_items = n_items;
+    p.hist_ptr = hist_ptr; p.hist_idx = hist_idx; p.target = target_in ? target_in : target; p.row_ok = row_ok;
+    p.rank = rank; p.scores = scores_out; p.splits = 1; p.k = k; p.top_trigger = k <= 16 ? 4 : 16;    // small k: keep tau fresh
+    p.topk_idx = topk_idx; p.topk_val = topk_val;
     if (const char *e = getenv("WR_TC_TOP_TRIGGER")) p.top_trigger = atoi(e);     // tuning knob, <= TC_TOPBUF - 32
     p.n_tiles = (int)((n_items + TC_BN - 1) / TC_BN);
-    const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
-    if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
-    const int row_tiles = (int)row_tiles64;
-    int splits = 1;
-    // few rows: split the item range over CTAs, one CTA per SM (512 TMEM columns each); rank counts merge with integer
-    // atomics.  Top-k lists are per CTA, so that mode keeps a row's items in one CTA.
-    if (row_tiles < kSMs && !topk_idx) splits = (kSMs + row_tiles - 1) / row_tiles;
-    if (splits > p.n_tiles) splits = p.n_tiles;
-    if (splits > 65535) splits = 65535;
-    p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
-    p.splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-    if (p.splits > 1) {
-        fill_rank_kernel<<<(int)min((int64_t)kSMs * 4, (R + 255) / 256), 256, 0, st>>>(rank, R, 1);
+
+    if (!exact) {
+        const int64_t n4 = n_items * D / 4;
+        pack_items_bf16_kernel<<<(int)min((int64_t)8 * kSMs, (n4 + 255) / 256), 256, 0, st>>>(Iemb, n4, Bm);
+        WR_CHECK_LAUNCH();
+        if (target_in)
+            pack_rows_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, user, R, n_users, D, A, row_ok, ws);
+        else
+            pack_users_kernel<<<(int)min((int64_t)8 * kSMs, (R + 7) / 8), 256, 0, st>>>(Uemb, Iemb, user, pos, R, n_users,
+                                                                                        n_items, D, A, target, row_ok, ws);
+        WR_CHECK_LAUNCH();
+        rc = make_map(&ma, A, R, K, TC_BM);
+        if (rc) return rc;
+        const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
+        if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
+        const int row_tiles = (int)row_tiles64;
+        int splits = 1;
+        // few rows: split the item range over CTAs, one CTA per SM (512 TMEM columns each); rank counts merge with
+        // integer atomics.  Top-k lists are per CTA, so that mode keeps a row's items in one CTA.
+        if (row_tiles < kSMs && !topk_idx) splits = (kSMs + row_tiles - 1) / row_tiles;
+        if (splits > p.n_tiles) splits = p.n_tiles;
+        if (splits > 65535) splits = 65535;
+        p.tiles_per_split = (p.n_tiles + splits - 1) / splits;
+        p.splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+        if (p.splits > 1) {
+            fill_rank_kernel<<<(int)min((int64_t)kSMs * 4, (R + 255) / 256), 256, 0, st>>>(rank, R, 1);
+            WR_CHECK_LAUNCH();
+        }
+        return D == 64 ? launch_tc<64>(ma, mb, p, row_tiles, st) : launch_tc<128>(ma, mb, p, row_tiles, st);
+    }
+
+    // ---------------- precision 2 ----------------
+    if (topk_idx || scores_out) return WR_E_TOPK;
+    float *anorm = reinterpret_cast<float *>(base);
+    base += align_up((size_t)R * 4, 1024);
+    uint32_t *bmax_bits = reinterpret_cast<uint32_t *>(base);
+    unsigned long long *cand_cnt = reinterpret_cast<unsigned long long *>(base + 16);
+    base += 1024;
+    uint2 *cand = reinterpret_cast<uint2 *>(base);
+    int64_t rb;
+    unsigned long long cap;
+    exact_blocking(R, n_items, &rb, &cap);
+    cudaError_t e = cudaMemsetAsync(bmax_bits, 0, 64, st);
+    if (e != cudaSuccess) return (int)e;
+    pack_items_split_kernel<<<(int)min((int64_t)16 * kSMs, (n_items + 7) / 8), 256, 0, st>>>(Iemb, n_items, D, Bm, bmax_bits);
+    WR_CHECK_LAUNCH();
+    pack_users_split_kernel<<<(int)min((int64_t)16 * kSMs, (R + 7) / 8), 256, 0, st>>>(
+        Uemb, Iemb, user, pos, R, n_users, n_items, D, target_in ? 1 : 0, A, target, anorm, row_ok, ws);
+    WR_CHECK_LAUNCH();
+    p.bmax = reinterpret_cast<const float *>(bmax_bits);
+    p.band_c = D == 64 ? 1.5e-4f : 2.0e-4f;
+    p.cand = cand;
+    p.cand_cnt = cand_cnt;
+    p.cand_cap = cap;
+    p.status = &ws->status;
+    for (int64_t r0 = 0; r0 < R; r0 += rb) {
+        const int64_t rn = R - r0 < rb ? R - r0 : rb;
+        TcParams q = p;
+        q.user = user + r0; q.pos = pos + r0; q.R = rn; q.target = p.target + r0; q.row_ok = row_ok + r0; q.rank = rank + r0;
+        q.anorm = anorm + r0;
+        rc = make_map(&ma, A + r0 * K, rn, K, TC_BM);
+        if (rc) return rc;
+        const int row_tiles = (int)((rn + TC_BM - 1) / TC_BM);
+        int splits = 1;
+        if (row_tiles < kSMs) splits = (kSMs + row_tiles - 1) / row_tiles;
+        if (splits > q.n_tiles) splits = q.n_tiles;
+        if (splits > 65535) splits = 65535;
+        q.tiles_per_split = (q.n_tiles + splits - 1) / splits;
+        q.splits = (q.n_tiles + q.tiles_per_split - 1) / q.tiles_per_split;
+        if (q.splits > 1) {
+            fill_rank_kernel<<<(int)min((int64_t)kSMs * 4, (rn + 255) / 256), 256, 0, st>>>(q.rank, rn, 1);
+            WR_CHECK_LAUNCH();
+        }
+        e = cudaMemsetAsync(cand_cnt, 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return (int)e;
+        rc = D == 64 ? launch_tc_v<192, 1, 0, 1>(ma, mb, q, row_tiles, st) : launch_tc_v<384, 1, 0, 1>(ma, mb, q, row_tiles, st);
+        if (rc) return rc;
+        eval_recheck_kernel<<<8 * kSMs, 256, 0, st>>>(cand, cand_cnt, cap, target_in ? Uemb + r0 * D : Uemb, q.user,
+                                                       target_in ? 1 : 0, Iemb, D, q.target, q.rank);
         WR_CHECK_LAUNCH();
     }
-    return D == 64 ? launch_tc<64>(ma, mb, p, row_tiles, st) : launch_tc<128>(ma, mb, p, row_tiles, st);
+    return WR_OK;
 }

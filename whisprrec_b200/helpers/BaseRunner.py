@@ -97,7 +97,7 @@ class BaseRunner(object):
         self.metrics = [name.strip().upper() for name in args.metric.split(',')]
         self.main_metric = '%s@%d' % (self.metrics[0], self.topk[0])      # early stopping watches this one
         self.time = None                                # [start of train(), last lap]
-        self.eval_precision = getattr(args, 'eval_precision', 0)
+        self.eval_precision = getattr(args, 'eval_precision', 2)     # the ranks of 0, on the tensor cores
         self.last_epoch_stats = {}
 
     def _check_time(self, start=False):

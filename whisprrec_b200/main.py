@@ -66,8 +66,9 @@ def parse_global_args(parser):
     parser.add_argument('--load', type=int, default=0, help='Whether load model and continue to train')
     parser.add_argument('--train', type=int, default=1, help='To train the model or not.')
     parser.add_argument('--regenerate', type=int, default=1, help='Whether to regenerate intermediate files')
-    parser.add_argument('--eval_precision', type=int, default=0,
-                        help='Scoring precision of full-ranking eval: 0 fp32-exact, 1 bf16 tensor cores')
+    parser.add_argument('--eval_precision', type=int, default=2,
+                        help='Full-ranking eval: 0 fp32 FMA tiles; 1 bf16 tensor cores (looser); 2 split-bf16 tensor cores '
+                             'with an exact re-check -- the ranks of 0 at tensor-core speed (embedding 64 / 128, else 0)')
     return parser
 
 
