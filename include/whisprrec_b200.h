@@ -158,6 +158,28 @@ int wr_bprmf_ctx_wait(wr_bprmf_ctx *ctx, int64_t step, int wait, float *host_los
 int wr_bprmf_ctx_sync(wr_bprmf_ctx *ctx);
 int wr_bprmf_ctx_destroy(wr_bprmf_ctx *ctx);
 
+/* ---- SGL (models/general/SGL.py) -------------------------------------------------------
+ * The three propagations of a step are wr_csr_spmm on the main graph and on the two edge-dropout views (which are not
+ * symmetric: the backward pass takes the transposed CSR), EmbLoss is wr_embloss_fwd_bwd; what is new:
+ * wr_bpr_logsig_sum_fwd_bwd: SGL.py:176-185, loss_out (+)= sum_b -logsigmoid(<U[u_b],I[p_b]> - <U[u_b],I[n_b]>) (a sum,
+ *   not a mean); gradients as wr_bpr_fwd_bwd, scaled by grad_scale.
+ * wr_infonce_fwd_bwd: SGL.py:196-231 for one block of rows (users of the batch against all users, or positive items
+ *   against all items), forward and backward:
+ *     a_b = normalize(T1[idx_b]), t_j = normalize(T2[j]) (F.normalize, eps 1e-12), z_b = sum_j exp(a_b . t_j / tau)
+ *     loss_out[0] += weight * sum_b (log z_b - a_b . t_{idx_b} / tau)
+ *     dT1[idx_b] += grad_scale * dL/dT1[idx_b] (RED per occurrence), dT2[j] += grad_scale * dL/dT2[j] for every j
+ *   T1 / T2 / dT1 / dT2: [N, D] fp32 blocks of the pooled view tables and their gradients; the [B, N] contraction runs as
+ *   fp32 FMA tiles over a materialised softmax weight matrix (B x N x 4 bytes <= 512 MB).
+ *   scratch: wr_infonce_scratch_bytes(B, N, D) bytes of device memory.
+ */
+int wr_bpr_logsig_sum_fwd_bwd(const float *U, const float *I, const int64_t *user, const int64_t *pos, const int64_t *neg,
+                              int64_t B, int D, int64_t n_users, int64_t n_items, float grad_scale, float *gU, float *gI,
+                              float *loss_out, int accumulate_loss, void *ws, void *stream);
+size_t wr_infonce_scratch_bytes(int64_t B, int64_t N, int D);
+int wr_infonce_fwd_bwd(const float *T1, const float *T2, const int64_t *idx, int64_t B, int64_t N, int D, float tau,
+                       float weight, float grad_scale, float *dT1, float *dT2, float *loss_out, void *scratch,
+                       size_t scratch_bytes, void *ws, void *stream);
+
 /* ---- LightGCN propagation ------------------------------------------------------------------------------
  * wr_csr_norm_weights: the value recipe of LightGCN.py:89-97: val[e] = fl32(fl32(dinv[row] * 1) * dinv[col]).
  * dinv = np.power(fp32(deg) + 1e-10, -0.5) comes from the caller (NumPy's fp32 pow is not correctly rounded,

@@ -500,6 +500,96 @@ def test_exact_tensor_core_eval_error_bound_has_margin(ws):
         assert (np.abs(three - exact) / scale).max() < c / 10
 
 
+@pytest.mark.parametrize('tag', ['sgl_d16_l2', 'sgl_d32_l3'])
+def test_sgl_steps_match_reference_golden(tag):
+    """SGL on the device against tensors of the unmodified reference: the two edge-dropout views
+    of the epoch bit for bit (Python's random stream), the three pooled tables, and three optimiser steps -- loss, dense
+    ego gradients, parameters after Adam (duplicate-heavy batches, ragged last batch)."""
+    import random
+    from oracle import sgl_oracle as SO
+    from whisprrec_b200.models.general.SGL import SGL
+    s = small_case(load('sgl_cases.npz'), tag)
+    lr, l2, reg, L, D, tau, w_ssl, drop = (float(x) for x in s['hp'])
+    L, D = int(L), int(D)
+    nU, nI = s['U0'].shape[0], s['I0'].shape[0]
+    N = nU + nI
+    tr = s['train'].astype(np.int64)
+    corpus = frames_corpus(tr, tr[:1], tr[:1], n_users=nU, n_items=nI)
+    args = model_args(SGL, lr=lr, l2=l2, reg_weight=reg, gcn_layers=L, embedding_size=D, ssl_tau=tau, ssl_weight=w_ssl,
+                      drop_ratio=drop)
+    model = SGL(args, corpus)
+    model.load_state_dict({'user_embedding.weight': torch.from_numpy(s['U0']),
+                           'item_embedding.weight': torch.from_numpy(s['I0'])})
+    model = model.to(DEV)
+    t = model.fuse()
+    model.optimizer = BaseRunner(args)._build_optimizer(model)
+    random.seed(1234)                     # utils.init_seed(1234) of the golden run; only the views draw from it
+    model.graph_construction()
+
+    def dense_of(g):
+        A = torch.sparse_csr_tensor(g.rowptr, g.col.long(), g.val, size=(N, N)).to_dense()
+        return host(A)
+    assert (dense_of(model.train_graph) == s['graph']).all()
+    for k, name in enumerate(('sub1', 'sub2')):
+        g = model.sub_graphs[k]
+        assert (dense_of(g) == s[name]).all(), name                       # structure and fp32 weights, bit for bit
+        assert (dense_of(g.T) == s[name].T).all(), name + ' transposed'
+    for g, pool, name in zip([model.train_graph] + model.sub_graphs, model.pool, ('main', 'sub1', 'sub2')):
+        model._propagate(g, pool)
+        assert_close(host(pool[:nU]), s[f'pooled_{name}_user'], name + ' users')
+        assert_close(host(pool[nU:]), s[f'pooled_{name}_item'], name + ' items')
+    for step in range(3):
+        user, pos, neg = (dv(s[f's{step}/{k}'], torch.int64) for k in ('user', 'pos', 'neg'))
+        loss = model.predict({'user_id': user, 'pos_item': pos, 'neg_items': neg})
+        assert_close(float(loss), s[f's{step}/loss'], f'loss step {step}', rtol=5e-6)
+        assert_close(host(t.G[:nU]), s[f's{step}/gU'], f'gU step {step}', rtol=3e-5, atol_scale=3e-6)
+        assert_close(host(t.G[nU:]), s[f's{step}/gI'], f'gI step {step}', rtol=3e-5, atol_scale=3e-6)
+        for g in model.pool_grad:
+            assert float(g.abs().max()) == 0.0
+        model.optimizer.step()
+        assert_close(host(t.P[:nU]), s[f's{step}/U'], f'U step {step}', rtol=3e-5, atol_scale=3e-6)
+        assert_close(host(t.P[nU:]), s[f's{step}/I'], f'I step {step}', rtol=3e-5, atol_scale=3e-6)
+    model.graph_construction()            # the next epoch's views continue Python's stream
+    assert np.count_nonzero(dense_of(model.sub_graphs[0])) == int(s['sub1_epoch2_nnz'])
+    assert t.ws.status() == 0
+
+
+def test_sgl_epoch_on_ml100k_runs_through_the_runner():
+    """`main.py --model_name SGL` protocol: one epoch of BaseRunner.fit (negatives, views, 33 steps) and a dev evaluation;
+    the InfoNCE block against the oracle's autograd on the first batch."""
+    from oracle import sgl_oracle as SO
+    from whisprrec_b200.models.general.SGL import SGL
+    corpus = ml100k_corpus()
+    args = model_args(SGL, lr=1e-3, l2=0.0)
+    utils.init_seed(3407)
+    model = SGL(args, corpus).to(DEV)
+    t = model.fuse()
+    runner = BaseRunner(args)
+    model.optimizer = runner._build_optimizer(model)
+    data = {ph: SGL.Dataset(model, corpus, ph) for ph in ('train', 'dev')}
+    # one step against the CPU oracle (autograd on the restatement) with the same views
+    data['train'].actions_before_epoch()
+    rng = np.random.RandomState(0)
+    sel = rng.randint(0, len(data['train']), 512)
+    user = np.asarray(data['train'].data['user_id'])[sel].astype(np.int64)
+    pos = np.asarray(data['train'].data['item_id'])[sel].astype(np.int64)
+    neg = np.asarray(data['train'].data['neg_items'])[sel].astype(np.int64)
+    N = corpus.n_users + corpus.n_items
+    graphs = [O.csr_to_torch(host(g.rowptr), host(g.col), host(g.val), N) for g in [model.train_graph] + model.sub_graphs]
+    U0, I0 = host(t.P[:corpus.n_users]).copy(), host(t.P[corpus.n_users:]).copy()
+    o_loss, o_gU, o_gI = SO.fwd_bwd(U0, I0, graphs, user, pos, neg, model.gcn_layers, model.reg_weight, model.ssl_tau,
+                                    model.ssl_weight)
+    loss = model.predict({'user_id': dv(user), 'pos_item': dv(pos), 'neg_items': dv(neg)})
+    assert_close(float(loss), float(o_loss), 'ml-100k SGL loss', rtol=1e-5)
+    assert_close(host(t.G[:corpus.n_users]), o_gU.numpy(), 'ml-100k SGL gU', rtol=5e-5, atol_scale=5e-6)
+    assert_close(host(t.G[corpus.n_users:]), o_gI.numpy(), 'ml-100k SGL gI', rtol=5e-5, atol_scale=5e-6)
+    t.G.zero_()
+    mean_loss = runner.fit(data['train'], epoch=1)
+    res = runner.evaluate(data['dev'], [10], ['NDCG', 'HR'])
+    assert np.isfinite(mean_loss) and 0.0 < res['HR@10'] < 1.0
+    assert t.ws.status() == 0
+
+
 def test_csr_spmm_hot_row_cache_policy_changes_nothing_but_the_cache(ws):
     """The L2 evict_last / evict_first variant of the SpMM (plan.hot_bits: tables far larger than L2) computes bit for
     bit what the plain loads do."""

@@ -26,6 +26,9 @@ SIGNATURES = {
     'wr_workspace_init': (_int, [_p, _p]),
     'wr_status': (_int, [_p, _c.POINTER(_c.c_uint32), _p]),
     'wr_bpr_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _p, _p, _p, _int, _p, _p]),
+    'wr_bpr_logsig_sum_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _p, _p, _p, _int, _p, _p]),
+    'wr_infonce_scratch_bytes': (_sz, [_i64, _i64, _int]),
+    'wr_infonce_fwd_bwd': (_int, [_p, _p, _p, _i64, _i64, _int, _f32, _f32, _f32, _p, _p, _p, _p, _sz, _p, _p]),
     'wr_embloss_fwd_bwd': (_int, [_p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _p, _p, _p, _p, _p]),
     'wr_adam_l2_sweep': (_int, [_p, _p, _p, _p, _i64, _f32, _f64, _f64, _f32, _f32, _f32, _p, _p]),
     'wr_bprmf_step': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32, _f32,
@@ -182,6 +185,26 @@ def bpr_fwd_bwd(U, I, user, pos, neg, gU, gI, loss_out, ws, gamma=1e-10, grad_sc
                                 user.numel(), D, U.shape[0], I.shape[0], gamma, grad_scale,
                                 ptr(gU, F32), ptr(gI, F32), ptr(loss_out, F32), int(accumulate_loss),
                                 ws.ptr, stream_ptr()))
+
+
+def bpr_logsig_sum_fwd_bwd(U, I, user, pos, neg, gU, gI, loss_out, ws, grad_scale=1.0, accumulate_loss=False):
+    """SGL's BPR term: sum_b -logsigmoid(s+ - s-) (SGL.py:176-185)."""
+    check(load().wr_bpr_logsig_sum_fwd_bwd(ptr(U, F32), ptr(I, F32), ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
+                                           user.numel(), U.shape[1], U.shape[0], I.shape[0], grad_scale, ptr(gU, F32),
+                                           ptr(gI, F32), ptr(loss_out, F32), int(accumulate_loss), ws.ptr, stream_ptr()))
+
+
+def infonce_fwd_bwd(T1, T2, idx, tau, weight, grad_scale, dT1, dT2, loss_out, ws, scratch=None):
+    """InfoNCE of SGL.py:196-231 for one block of rows, forward + backward (wr_infonce_fwd_bwd); returns the scratch
+    tensor so that the caller can hand it back next time."""
+    B, (N, D) = idx.numel(), T2.shape
+    nbytes = load().wr_infonce_scratch_bytes(B, N, D)
+    if scratch is None or scratch.numel() < nbytes:
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=T1.device)
+    check(load().wr_infonce_fwd_bwd(ptr(T1, F32), ptr(T2, F32), ptr(idx, I64), B, N, D, tau, weight, grad_scale,
+                                    ptr(dT1, F32), ptr(dT2, F32), ptr(loss_out, F32), scratch.data_ptr(), scratch.numel(),
+                                    ws.ptr, stream_ptr()))
+    return scratch
 
 
 def embloss_fwd_bwd(U0, I0, user, pos, neg, gU0, gI0, loss_out, ws, reg_weight):

@@ -112,6 +112,13 @@ __device__ __forceinline__ float4 fma4(float s, float4 x, float4 a) {
 __device__ __forceinline__ void bpr_pointwise(float sp, float sn, float gamma, float coef, float &loss, float &c) {
     // utils/loss.py:38: -log(gamma + sigmoid(pos - neg)); d/ds+ = -(sig (1-sig)) / (gamma + sig)
     const float x = sp - sn;
+    if (gamma < 0.f) {
+        // SGL.py:183: -logsigmoid(x) = softplus(-x) = max(-x, 0) + log1p(exp(-|x|)); d/dx = -sigmoid(-x)
+        const float e = expf(-fabsf(x));
+        loss = fmaxf(-x, 0.f) + log1pf(e);
+        c = -(x >= 0.f ? e / (1.0f + e) : 1.0f / (1.0f + e)) * coef;
+        return;
+    }
     const float sig = 1.0f / (1.0f + expf(-x));
     loss = -logf(gamma + sig);
     c = -(sig * (1.0f - sig)) / (gamma + sig) * coef;

@@ -636,6 +636,20 @@ extern "C" int wr_bpr_fwd_bwd(const float *U, const float *I, const int64_t *use
     return launch_bpr(p, D, (cudaStream_t)stream);
 }
 
+// SGL's BPR term (SGL.py:176-185): sum_b -logsigmoid(s+ - s-), no 1/B; gradient scaled by grad_scale.
+extern "C" int wr_bpr_logsig_sum_fwd_bwd(const float *U, const float *I, const int64_t *user, const int64_t *pos,
+                                         const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items,
+                                         float grad_scale, float *gU, float *gI, float *loss_out, int accumulate_loss,
+                                         void *ws, void *stream) {
+    if (!U || !I || !user || !pos || !neg || !gU || !gI || !loss_out || !ws) return WR_E_NULL;
+    if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(U) || !wr_aligned16(I) || !wr_aligned16(gU) || !wr_aligned16(gI)) return WR_E_ALIGN;
+    BprParams p{{U, I, gU, gI}, user, pos, neg, B, n_users, n_items, -1.0f /* logsigmoid form */, grad_scale, 1.0f,
+                loss_out, accumulate_loss, (WrWorkspace *)ws};
+    return launch_bpr(p, D, (cudaStream_t)stream);
+}
+
 extern "C" int wr_bpr_fwd_bwd_sharded(const wr_shards *host_T, const wr_shards *host_Gd, const int64_t *user,
                                       const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D,
                                       float gamma, float grad_scale, float *loss_out, void *ws, void *stream) {

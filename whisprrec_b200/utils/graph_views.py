@@ -1,5 +1,5 @@
 """Augmented graph views for SGL (reference src/models/general/SGL.py:67-79, src/utils/augmentor.py:77-111) -- host side of
-the next hot-path row; the SGL step kernels do not exist yet.
+the SGL row of the hot-path table (models/general/SGL.py is the device side).
 
 `edge_dropout_view` draws exactly the edges the reference keeps (Python's global `random` stream, reproduced by
 wr_pyrandom_sample in the library, ~20x faster than `random.sample` on a million edges) and normalises the result as
@@ -10,10 +10,12 @@ import numpy as np
 from .. import _lib
 
 
-def edge_dropout_view(rowptr, col, drop_ratio):
+def edge_dropout_view(rowptr, col, drop_ratio, transpose=False):
     """rowptr / col: CSR structure of the full symmetric adjacency [[0, R], [R^T, 0]] (rows and columns ascending, as
     `build_norm_adj_csr` returns it; that is also the order `adj_matrix.nonzero()` has in the reference).
-    Returns (rowptr int64 [N+1], col int32 [kept], val fp32 [kept]) of one augmented, normalised view."""
+    Returns (rowptr int64 [N+1], col int32 [kept], val fp32 [kept]) of one augmented, normalised view; with
+    transpose=True also the same three arrays of its TRANSPOSE (the view is not symmetric, and the backward pass of a
+    propagation multiplies by A^T)."""
     rowptr = np.asarray(rowptr, dtype=np.int64)
     col = np.asarray(col)
     n_nodes, nnz = len(rowptr) - 1, int(rowptr[-1])
@@ -23,9 +25,17 @@ def edge_dropout_view(rowptr, col, drop_ratio):
     deg = np.bincount(rows, minlength=n_nodes).astype(np.float32)
     dinv = np.power(deg + 1e-10, -0.5).astype(np.float32)                   # SGL.py:113-117
     dinv[np.isinf(dinv)] = 0.
-    order = np.lexsort((cols, rows))
-    rows, cols = rows[order], cols[order]
-    val = (dinv[rows] * np.float32(1.0)) * dinv[cols]                       # (D^-1/2 A) D^-1/2, two fp32 roundings
-    out_ptr = np.zeros(n_nodes + 1, dtype=np.int64)
-    np.cumsum(np.bincount(rows, minlength=n_nodes), out=out_ptr[1:])
-    return out_ptr, cols.astype(np.int32), val.astype(np.float32)
+
+    def csr(r, c):
+        order = np.lexsort((c, r))
+        r, c = r[order], c[order]
+        # (D^-1/2 A) D^-1/2, two fp32 roundings; the product is commutative, so the transposed entry gets the same bits
+        val = (dinv[r] * np.float32(1.0)) * dinv[c]
+        out_ptr = np.zeros(n_nodes + 1, dtype=np.int64)
+        np.cumsum(np.bincount(r, minlength=n_nodes), out=out_ptr[1:])
+        return out_ptr, c.astype(np.int32), val.astype(np.float32)
+    fwd = csr(rows, cols)
+    if not transpose:
+        return fwd
+    t_ptr, t_col, t_val = csr(cols, rows)
+    return fwd, (t_ptr, t_col, t_val)
