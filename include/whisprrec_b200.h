@@ -213,6 +213,19 @@ int wr_csr_build(const int64_t *edge_u, const int64_t *edge_i, int64_t E, int64_
                  int64_t *rowptr, int32_t *col, int64_t *nnz_out, void *scratch, size_t scratch_bytes, void *ws,
                  void *stream);
 
+/* wr_subgraph_csr: SGL's edge-dropout views on the device (utils/augmentor.py:77-111, SGL.py:67-79): the CSR structure
+ * (transpose = 0) or the structure of the TRANSPOSE (transpose = 1) of the sub-graph that keeps edges keep[0..K) (edge
+ * numbers in CSR order, which is the order of `adj_matrix.nonzero()` in the reference; they come from Python's random
+ * stream: wr_pyrandom_sample) of the square CSR matrix (rowptr, col) with n_rows rows.  out_rowptr [n_rows + 1], out_col
+ * [K], *nnz_out (DEVICE) = entries kept.  The views are not symmetric (the two directions of an edge are dropped
+ * independently), so the backward pass of a propagation needs the transpose.  Same radix-sort machinery and scratch size
+ * rule as wr_csr_build; weights: row degrees -> the reference's NumPy d^-1/2 -> wr_csr_norm_weights on either structure.
+ */
+size_t wr_subgraph_csr_scratch_bytes(int64_t K);
+int wr_subgraph_csr(const int64_t *rowptr, const int32_t *col, int64_t n_rows, const int64_t *keep, int64_t K,
+                    int transpose, int64_t *out_rowptr, int32_t *out_col, int64_t *nnz_out, void *scratch,
+                    size_t scratch_bytes, void *ws, void *stream);
+
 typedef struct wr_spmm_plan {
     /* HOST struct of DEVICE pointers: how rows with more than long_threshold non-zeros are cut into slices so
      * that no warp walks more than one slice (power-law graphs: a 10^6-edge item row would otherwise be the tail

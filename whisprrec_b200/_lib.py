@@ -47,6 +47,8 @@ SIGNATURES = {
     'wr_bprmf_ctx_destroy': (_int, [_p]),
     'wr_csr_build_scratch_bytes': (_sz, [_i64]),
     'wr_csr_build': (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p, _p]),
+    'wr_subgraph_csr_scratch_bytes': (_sz, [_i64]),
+    'wr_subgraph_csr': (_int, [_p, _p, _i64, _p, _i64, _int, _p, _p, _p, _p, _sz, _p, _p]),
     'wr_csr_norm_weights': (_int, [_p, _p, _p, _i64, _p, _p]),
     'wr_csr_spmm': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p]),
     'wr_eval_rank_topk': (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _int, _int, _p, _p, _p, _p, _p, _p,
@@ -336,6 +338,22 @@ def csr_build(users, items, n_users, n_items, ws):
     n = int(nnz.item())
     del scratch
     return rowptr, col[:n]
+
+
+def subgraph_csr(rowptr, col, keep, ws, transpose=False):
+    """wr_subgraph_csr: (rowptr int64 [N + 1], col int32 [kept]) of the sub-graph keeping edges `keep` (int64 device tensor
+    of edge numbers in CSR order) of the square CSR matrix (rowptr, col), or of its transpose."""
+    K, N = keep.numel(), rowptr.numel() - 1
+    dev = keep.device
+    lib = load()
+    out_ptr = torch.empty(N + 1, dtype=I64, device=dev)
+    out_col = torch.empty(K, dtype=I32, device=dev)
+    nnz = torch.zeros(1, dtype=I64, device=dev)
+    nbytes = lib.wr_subgraph_csr_scratch_bytes(K)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.wr_subgraph_csr(ptr(rowptr, I64), ptr(col, I32), N, ptr(keep, I64), K, int(transpose), ptr(out_ptr, I64),
+                              ptr(out_col, I32), ptr(nnz, I64), scratch.data_ptr(), nbytes, ws.ptr, stream_ptr()))
+    return out_ptr, out_col[:int(nnz.item())]
 
 
 def csr_norm_weights(rowptr, col, dinv, val):

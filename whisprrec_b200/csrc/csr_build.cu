@@ -237,6 +237,29 @@ __global__ void set_count_kernel(const uint32_t *tile_off_last, const uint32_t *
 }
 __global__ void set_scalar_kernel(int64_t *p, int64_t v) { *p = v; }
 __global__ void save_u32_kernel(const uint32_t *src, uint32_t *dst) { *dst = *src; }
+__global__ void save_i64_kernel(const int64_t *src, int64_t *dst) { *dst = *src; }
+
+// keys of the kept edges of a CSR matrix: edge e of the main graph sits in row upper_bound(rowptr, e) - 1
+__global__ void __launch_bounds__(256) subgraph_keys_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                             int64_t n_rows, const int64_t *__restrict__ keep, int64_t K,
+                                                             int transpose, uint64_t *keys, WrWorkspace *ws) {
+    const int64_t nnz = rowptr[n_rows];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = keep[k];
+        if ((uint64_t)e >= (uint64_t)nnz) {
+            atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+            keys[k] = KEY_INVALID;
+            continue;
+        }
+        int64_t lo = 0, hi = n_rows;                 // first row whose rowptr[row + 1] > e
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid + 1] > e) hi = mid; else lo = mid + 1;
+        }
+        const uint64_t r = (uint64_t)lo, c = (uint64_t)(uint32_t)col[e];
+        keys[k] = transpose ? (c << 32) | r : (r << 32) | c;
+    }
+}
 
 // ---- CSR rows from sorted distinct keys (hi = row inside the block of rows, lo = column inside the other block) ----
 // rowptr[row_base + r] = edge_base + (first key whose hi >= r); col[edge_base + k] = col_base + lo_k.
@@ -381,6 +404,48 @@ extern "C" int wr_csr_build(const int64_t *edge_u, const int64_t *edge_i, int64_
     rows_from_keys_kernel<<<g, 256, 0, st>>>(cur, s.n_dev, n_items, n_users, 0, 1, rowptr, col, 1);
     WR_CHECK_LAUNCH();
     finish_nnz_kernel<<<1, 1, 0, st>>>(s.n_dev, nnz_out);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+// wr_subgraph_csr: CSR structure (or the structure of the transpose) of the sub-graph that keeps edges keep[0..K) of a
+// square CSR matrix -- SGL's edge-dropout views (utils/augmentor.py:77-111; the kept edge numbers come from Python's
+// random stream, wr_pyrandom_sample).  Same machinery as wr_csr_build: packed keys, radix sort, row pointers.
+extern "C" size_t wr_subgraph_csr_scratch_bytes(int64_t K) { return wr_csr_build_scratch_bytes(K); }
+
+extern "C" int wr_subgraph_csr(const int64_t *rowptr, const int32_t *col, int64_t n_rows, const int64_t *keep, int64_t K,
+                               int transpose, int64_t *out_rowptr, int32_t *out_col, int64_t *nnz_out, void *scratch,
+                               size_t scratch_bytes, void *ws, void *stream) {
+    if (!rowptr || !col || !keep || !out_rowptr || !out_col || !nnz_out || !scratch || !ws) return WR_E_NULL;
+    if (K <= 0 || K >= ((int64_t)1 << 32) - RS_TILE || n_rows <= 0 || n_rows >= INT32_MAX) return WR_E_SIZE;
+    if (scratch_bytes < wr_csr_build_scratch_bytes(K)) return WR_E_SIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    BuildScratch s;
+    char *base = (char *)(((uintptr_t)scratch + 255) & ~(uintptr_t)255);
+    carve(&s, base, K);
+    const int bits = bits_for(n_rows);
+    const int g = (int)((K + 255) / 256 < 16 * (int64_t)kSMs ? (K + 255) / 256 : 16 * (int64_t)kSMs);
+    set_scalar_kernel<<<1, 1, 0, st>>>(s.n_dev, K);
+    WR_CHECK_LAUNCH();
+    subgraph_keys_kernel<<<g, 256, 0, st>>>(rowptr, col, n_rows, keep, K, transpose, s.keysA, (WrWorkspace *)ws);
+    WR_CHECK_LAUNCH();
+    uint64_t *cur = s.keysA, *alt = s.keysB;
+    int rc = radix_sort(s, &cur, &alt, bits, bits, st);
+    if (rc) return rc;
+    // the kept edge numbers are distinct, but a repeated one must not become a repeated entry
+    unique_count_kernel<<<s.n_tiles, 256, 0, st>>>(cur, s.n_dev, s.tile_cnt);
+    WR_CHECK_LAUNCH();
+    save_u32_kernel<<<1, 1, 0, st>>>(s.tile_cnt + s.n_tiles - 1, s.last_cnt);
+    WR_CHECK_LAUNCH();
+    rc = exclusive_scan_u32(s.tile_cnt, s.n_tiles, s.scan_tmp, st);
+    if (rc) return rc;
+    unique_compact_kernel<<<s.n_tiles, 256, 0, st>>>(cur, s.n_dev, s.tile_cnt, alt);
+    WR_CHECK_LAUNCH();
+    set_count_kernel<<<1, 1, 0, st>>>(s.tile_cnt + s.n_tiles - 1, s.last_cnt, s.n_dev);
+    WR_CHECK_LAUNCH();
+    rows_from_keys_kernel<<<g, 256, 0, st>>>(alt, s.n_dev, n_rows, 0, 0, 0, out_rowptr, out_col, 1);
+    WR_CHECK_LAUNCH();
+    save_i64_kernel<<<1, 1, 0, st>>>(s.n_dev, nnz_out);
     WR_CHECK_LAUNCH();
     return WR_OK;
 }

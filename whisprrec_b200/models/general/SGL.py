@@ -11,7 +11,8 @@ One training step (SGL.py:233-246 and its backward) is, on the device:
   are not symmetric: their transposed CSRs are built with them), EmbLoss on the ego rows (wr_embloss_fwd_bwd); the
   gradient lands in tables.G and the optimiser is the fused Adam sweep, as for LightGCN.
 The views are redrawn every epoch from Python's global `random` stream exactly as utils/augmentor.py:77-111 does
-(utils/graph_views.py on wr_pyrandom_sample), so they are bit-identical to the reference's.
+(wr_pyrandom_sample) and assembled on the device (wr_subgraph_csr: radix sort of the kept edges into CSR order, and
+into the transposed order), so they are bit-identical to the reference's.
 """
 import torch
 import torch.nn as nn
@@ -27,11 +28,10 @@ from ...utils import graph_views
 class _Graph(object):
     """A normalised adjacency on the device: CSR, its long-row plan, and (views only) the CSR of its transpose."""
 
-    def __init__(self, rowptr, col, val, D, dev, transpose=None):
-        to = lambda a: torch.from_numpy(a).to(dev)
-        self.rowptr, self.col, self.val = to(rowptr), to(col), to(val)
-        self.plan = _lib.SpmmPlan(rowptr, D, dev)
-        self.T = self if transpose is None else _Graph(*transpose, D=D, dev=dev)      # symmetric: its own transpose
+    def __init__(self, rowptr, col, val, D, transpose=None):
+        self.rowptr, self.col, self.val = rowptr, col, val
+        self.plan = _lib.SpmmPlan(rowptr.cpu().numpy(), D, rowptr.device)
+        self.T = self if transpose is None else _Graph(*transpose, D=D)      # symmetric: its own transpose
 
 
 class SGL(GeneralModel):
@@ -76,10 +76,10 @@ class SGL(GeneralModel):
         t = self.tables
         dev = t.P.device
         rowptr, col, dinv = self._adj_host
+        d_rowptr, d_col = torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev)
         val = torch.empty(len(col), dtype=torch.float32, device=dev)
-        _lib.csr_norm_weights(torch.from_numpy(rowptr).to(dev), torch.from_numpy(col).to(dev),
-                              torch.from_numpy(dinv).to(dev), val)
-        self.train_graph = _Graph(rowptr, col, val.cpu().numpy(), t.D, dev)
+        _lib.csr_norm_weights(d_rowptr, d_col, torch.from_numpy(dinv).to(dev), val)
+        self.train_graph = _Graph(d_rowptr, d_col, val, t.D)
         self.pool = [torch.empty_like(t.P) for _ in range(3)]           # pooled tables: main graph, view 1, view 2
         self.pool_grad = [torch.zeros_like(t.P) for _ in range(3)]
         self.layer = [torch.empty_like(t.P), torch.empty_like(t.P)]
@@ -89,11 +89,11 @@ class SGL(GeneralModel):
     def graph_construction(self):
         """SGL.py:67-79: the two augmented views of this epoch (edge dropout on Python's global random stream)."""
         t = self.fuse()
-        rowptr, col, _ = self._adj_host
+        g = self.train_graph
         views = []
         for _ in range(2):
-            fwd, tr = graph_views.edge_dropout_view(rowptr, col, self.drop_ratio, transpose=True)
-            views.append(_Graph(*fwd, D=t.D, dev=t.P.device, transpose=tr))
+            fwd, tr = graph_views.edge_dropout_view_device(g.rowptr, g.col, self.drop_ratio, t.ws)
+            views.append(_Graph(*fwd, D=t.D, transpose=tr))
         self.sub_graphs = views
 
     # ---- propagation -----------------------------------------------------------------------------------------------

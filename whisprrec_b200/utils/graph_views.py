@@ -39,3 +39,27 @@ def edge_dropout_view(rowptr, col, drop_ratio, transpose=False):
         return fwd
     t_ptr, t_col, t_val = csr(cols, rows)
     return fwd, (t_ptr, t_col, t_val)
+
+
+def edge_dropout_view_device(rowptr_d, col_d, drop_ratio, ws):
+    """The same view built on the device (SGL.graph_construction): the kept edge numbers are drawn on the host exactly as
+    above (Python's stream cannot move), everything else -- row / column of every kept edge, the sort into CSR order,
+    the transposed structure, the fp32 weights -- is wr_subgraph_csr + wr_csr_norm_weights; only the node degrees visit
+    the host, for the reference's own NumPy `power` call.  rowptr_d / col_d: device CSR of the full adjacency.
+    Returns ((rowptr, col, val), (rowptr_T, col_T, val_T)) as device tensors."""
+    import torch
+    nnz = int(col_d.numel())
+    keep = torch.from_numpy(_lib.py_random_sample(nnz, int(nnz * (1 - drop_ratio)))).to(col_d.device)
+    out = []
+    dinv_d = None
+    for transpose in (False, True):
+        ptr, col = _lib.subgraph_csr(rowptr_d, col_d, keep, ws, transpose=transpose)
+        if dinv_d is None:
+            deg = (ptr[1:] - ptr[:-1]).to(torch.int32).cpu().numpy().astype(np.float32)
+            dinv = np.power(deg + 1e-10, -0.5).astype(np.float32)              # SGL.py:113-117, row sums of the VIEW
+            dinv[np.isinf(dinv)] = 0.
+            dinv_d = torch.from_numpy(dinv).to(col_d.device)
+        val = torch.empty(col.numel(), dtype=torch.float32, device=col_d.device)
+        _lib.csr_norm_weights(ptr, col, dinv_d, val)                            # a * b == b * a: the transpose gets the same bits
+        out.append((ptr, col, val))
+    return out[0], out[1]
