@@ -23,7 +23,7 @@ GOLD=$ROOT/tests/golden/ml1m_shaped_reference_log.txt
 [ "$MODEL" = LightGCN ] && GOLD=$ROOT/tests/golden/ml1m_shaped_reference_log_lightgcn.txt
 if [ "$EPOCHS" = 3 ] && [ -f "$GOLD" ]; then
   if diff -q <(grep -v '^#' "$GOLD" | tr -s ' ' | sed 's/ *$//') <(tr -s ' ' < /tmp/wr_cli/one.txt | sed 's/ *$//') > /dev/null; then
-    echo "cli_check ok: equals the reference's log"; else echo "cli_check: differs from the reference's log"; fi
+    echo "cli_check ok: equals the reference's log"; else echo "cli_check: differs from the reference's log"; RC=1; fi
 fi
 if [ "$NGPU" -gt 1 ]; then
   PYTHONPATH=$ROOT python -m torch.distributed.run --nnodes=1 --nproc-per-node $NGPU --master-addr 127.0.0.1 --master-port 29577 \
@@ -32,7 +32,8 @@ if [ "$NGPU" -gt 1 ]; then
   sort -u /tmp/wr_cli/one.txt > /tmp/wr_cli/one_sorted.txt
   echo "--- one GPU";  cat /tmp/wr_cli/one.txt
   echo "--- $NGPU GPUs"; cat /tmp/wr_cli/multi.txt
-  if diff -q /tmp/wr_cli/one_sorted.txt /tmp/wr_cli/multi.txt > /dev/null; then echo "cli_check ok: identical log lines"; else echo "cli_check: logs differ"; diff /tmp/wr_cli/one_sorted.txt /tmp/wr_cli/multi.txt | head; fi
+  if diff -q /tmp/wr_cli/one_sorted.txt /tmp/wr_cli/multi.txt > /dev/null; then echo "cli_check ok: identical log lines"; else echo "cli_check: logs differ"; diff /tmp/wr_cli/one_sorted.txt /tmp/wr_cli/multi.txt | head; RC=1; fi
 else
   cat /tmp/wr_cli/one.txt; echo "cli_check ok (one GPU)"
 fi
+exit ${RC:-0}

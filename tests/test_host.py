@@ -285,11 +285,106 @@ def test_sgl_edge_dropout_views_match_reference(tag):
     np.cumsum(np.bincount(tr[:, 0], minlength=nU), out=ptr[1:])
     rowptr, col, _ = build_norm_adj_csr(nU, nI, ptr, tr[:, 1].astype(np.int32))
     random.seed(1234)
+    def dense_of(vp, vc, vv):
+        d = np.zeros((N, N), dtype=np.float32)
+        d[np.repeat(np.arange(N), np.diff(vp)), vc] = vv
+        return d
     for name in ('sub1', 'sub2'):
-        vp, vc, vv = edge_dropout_view(rowptr, col, drop)
-        dense = np.zeros((N, N), dtype=np.float32)
-        dense[np.repeat(np.arange(N), np.diff(vp)), vc] = vv
-        assert (dense == s[name]).all(), name
+        fwd, tr_ = edge_dropout_view(rowptr, col, drop, transpose=True)
+        assert (dense_of(*fwd) == s[name]).all(), name
+        assert (dense_of(*tr_) == s[name].T).all(), name + ' transposed'        # what the adjoint propagation multiplies by
+
+
+def test_sgl_model_keeps_the_reference_flags():
+    """`--model_name SGL` resolves, and its flags / defaults / log arguments are the reference's (SGL.py:20-42)."""
+    from whisprrec_b200.main import resolve
+    cls = resolve('model', 'SGL')
+    a = model_args(cls)
+    assert (a.embedding_size, a.gcn_layers, a.type, a.reg_weight, a.ssl_tau, a.ssl_weight, a.drop_ratio) == \
+        (64, 2, 'ED', 1e-4, 0.1, 0.05, 0.1)
+    assert cls.extra_log_args == ['embedding_size', 'gcn_layers', 'reg_weight', 'type', 'ssl_tau', 'ssl_weight', 'drop_ratio']
+    assert cls.reader == 'BaseReader' and cls.runner == 'BaseRunner'
+
+
+def test_checkpoints_have_the_reference_state_dict_layout(tmp_path):
+    """SURVEY.md section 8 f-4 without the reference checkout: the state_dict a `.pt` of ours holds has exactly the keys,
+    shapes and dtypes of the unmodified reference's models (tests/golden/reference_state_dicts.json, written by
+    tests/golden/make_golden_keys.py from the reference classes), and survives save / load (BaseModel.py:48-59)."""
+    import json
+    from tests.helpers import GOLDEN
+    from whisprrec_b200.main import resolve
+    want = json.load(open(os.path.join(GOLDEN, 'reference_state_dicts.json')))
+    corpus = ml100k_corpus()
+    for name, layout in want.items():
+        cls = resolve('model', name)
+        m = cls(model_args(cls), corpus)
+        got = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+        assert got == layout, name
+        path = str(tmp_path / (name + '.pt'))
+        torch.save(m.state_dict(), path)
+        back = torch.load(path)
+        assert list(back.keys()) == list(m.state_dict().keys())
+        for k in back:
+            assert torch.equal(back[k], m.state_dict()[k])
+
+
+def test_corpus_cache_is_written_under_the_reference_class_path(tmp_path):
+    """SURVEY.md section 8 f-4, both directions: the cache main.py writes names `helpers.BaseReader.BaseReader` (what the
+    reference's `pickle.load` resolves to ITS reader class, main.py:54-63) and no module of this package; it loads back
+    here as our reader with every attribute intact.  (The run against the real reference is the next test.)"""
+    import pickle
+    from whisprrec_b200 import main as wr_main
+    from whisprrec_b200.helpers.BaseReader import BaseReader
+    corpus = ml100k_corpus()
+    pkl = str(tmp_path / 'BaseReader.pkl')
+    wr_main.save_corpus(corpus, pkl)
+    raw = open(pkl, 'rb').read()
+    assert b'helpers.BaseReader' in raw and b'whisprrec_b200' not in raw
+    assert 'helpers' not in __import__('sys').modules or not hasattr(__import__('sys').modules['helpers'], '__wr_alias__')
+    back = wr_main.load_corpus(pkl)
+    assert type(back) is BaseReader and (back.n_users, back.n_items) == (corpus.n_users, corpus.n_items)
+    assert back.train_clicked_set == corpus.train_clicked_set and back.residual_clicked_set == corpus.residual_clicked_set
+    for ph in ('train', 'dev', 'test'):
+        assert back.data_df[ph].equals(corpus.data_df[ph])
+
+    class Theirs(object):                     # what the reference does: its own class, object.__new__ + __dict__
+        pass
+
+    class U(pickle.Unpickler):
+        def find_class(self, module, name):
+            if (module, name) == ('helpers.BaseReader', 'BaseReader'):
+                return Theirs
+            return super().find_class(module, name)
+    with open(pkl, 'rb') as f:
+        theirs = U(f).load()
+    assert type(theirs) is Theirs and theirs.n_items == corpus.n_items and len(theirs.data_df['train']) == len(corpus.data_df['train'])
+
+
+@pytest.mark.skipif(not os.path.exists('/root/reference/src/models/general/BPRMF.py'),
+                    reason='needs the reference checkout (authoring container only)')
+def test_our_corpus_cache_loads_in_the_reference(tmp_path):
+    """The same file through the reference's own code path: `pickle.load` in a process that has the reference's `src/` on
+    its path (main.py:57-59) yields the reference's BaseReader with our ids and splits."""
+    import subprocess
+    import sys
+    from whisprrec_b200 import main as wr_main
+    corpus = ml100k_corpus()
+    pkl = str(tmp_path / 'BaseReader.pkl')
+    wr_main.save_corpus(corpus, pkl)
+    code = f"""
+import sys, pickle, numpy as np
+np.float_ = np.float64
+sys.path.insert(0, '/root/reference/src')
+from helpers.BaseReader import BaseReader
+with open("{pkl}", "rb") as f:
+    c = pickle.load(f)
+assert type(c) is BaseReader, type(c)
+print(c.n_users, c.n_items, len(c.data_df['train']), len(c.train_clicked_set))
+"""
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split() == [str(corpus.n_users), str(corpus.n_items), str(len(corpus.data_df['train'])),
+                                str(len(corpus.train_clicked_set))]
 
 
 @pytest.mark.skipif(not os.path.exists('/root/reference/src/models/general/BPRMF.py'),

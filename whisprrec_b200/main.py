@@ -57,6 +57,38 @@ def load_corpus(path):
         return _CorpusUnpickler(f).load()
 
 
+def save_corpus(corpus, path):
+    """Write the corpus cache so that BOTH programs can load it (reference main.py:54-63): the reader object is pickled
+    under the reference's class path (`helpers.<Reader>.<Reader>`, plain attributes: `n_users`, `n_items`, `data_df`,
+    `train_clicked_set`, `residual_clicked_set`, ...), which `load_corpus` maps back to this package's class.  Written to a
+    temporary file and renamed, so that a concurrent reader never sees half a pickle."""
+    import types
+    cls = type(corpus)
+    mod_name = 'helpers.' + cls.__name__
+    stand_in = type(cls.__name__, (object,), {})
+    stand_in.__module__ = mod_name
+    alias_pkg, alias_mod = types.ModuleType('helpers'), types.ModuleType(mod_name)
+    setattr(alias_mod, cls.__name__, stand_in)
+    setattr(alias_pkg, cls.__name__, alias_mod)
+    saved = {k: sys.modules.get(k) for k in ('helpers', mod_name)}
+    obj = stand_in.__new__(stand_in)
+    obj.__dict__.update(corpus.__dict__)
+    tmp = '{}.tmp.{}'.format(path, os.getpid())
+    try:
+        sys.modules['helpers'], sys.modules[mod_name] = alias_pkg, alias_mod
+        with open(tmp, 'wb') as f:
+            pickle.dump(obj, f)
+        os.replace(tmp, path)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        if os.path.exists(tmp):
+            os.remove(tmp)
+
+
 def parse_global_args(parser):
     parser.add_argument('--gpu', type=str, default='0', help='Set CUDA_VISIBLE_DEVICES, default for CPU only')
     parser.add_argument('--verbose', type=int, default=logging.INFO, help='Logging Level, 0, 10, ..., 50')
@@ -154,12 +186,14 @@ def run(args, model_class, reader_class, runner_class, reader_name):
         corpus = load_corpus(corpus_path)
     else:
         corpus = reader_class(args)
-        logging.info('Save corpus to {}'.format(corpus_path))
-        try:
-            with open(corpus_path, 'wb') as f:
-                pickle.dump(corpus, f)
-        except OSError as e:                     # read-only data dir: the cache is an optimisation only
-            logging.info('corpus not cached: {}'.format(e))
+        if peers is None or peers.rank == 0:     # one writer (every rank builds the same corpus from the same file)
+            logging.info('Save corpus to {}'.format(corpus_path))
+            try:
+                save_corpus(corpus, corpus_path)
+            except OSError as e:                 # read-only data dir: the cache is an optimisation only
+                logging.info('corpus not cached: {}'.format(e))
+        if peers is not None:
+            peers.host_sync()
 
     model = model_class(args, corpus).to(args.device)
     logging.info('#params: {}'.format(model.count_variables()))
