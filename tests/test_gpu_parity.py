@@ -151,6 +151,38 @@ def test_bprmf_host_fed_step_matches_device_step(ws):
     assert models[0].tables.ws.status() == 0
 
 
+@pytest.mark.parametrize('cls', [BPRMF, LightGCN])
+def test_a_foreign_torch_optimizer_can_drive_the_fused_models(cls):
+    """SURVEY.md section 8b, level L1: the reference's runner builds `torch.optim.Adam(model.parameters(), lr,
+    weight_decay=l2)` and loops `zero_grad(); loss = predict(batch); loss.backward(); step()` (BaseRunner.py:120-124,
+    196-199).  Our predict leaves its gradient in `.grad` views of the gradient table; zero_grad() drops them
+    (set_to_none), predict re-attaches them: four steps equal the fused-optimizer path."""
+    corpus = ml100k_corpus()
+    models = []
+    for _ in range(2):
+        args = model_args(cls, lr=1e-3, l2=1e-6)
+        utils.init_seed(3407)
+        m = cls(args, corpus).to(DEV)
+        m.fuse()
+        models.append(m)
+    models[0].optimizer = torch.optim.Adam(models[0].parameters(), lr=1e-3, weight_decay=1e-6)
+    models[1].optimizer = BaseRunner(model_args(cls, lr=1e-3, l2=1e-6))._build_optimizer(models[1])
+    rng = np.random.RandomState(4)
+    for step in range(4):
+        B = 2048 if step < 3 else 300
+        batch = {'user_id': dv(rng.randint(0, corpus.n_users, B)), 'pos_item': dv(rng.randint(1, corpus.n_items, B)),
+                 'neg_items': dv(rng.randint(1, corpus.n_items, B))}
+        losses = []
+        for m in models:
+            m.optimizer.zero_grad()
+            loss = m.predict(batch)
+            loss.backward()
+            m.optimizer.step()
+            losses.append(float(loss))
+        assert losses[0] == pytest.approx(losses[1], rel=2e-6)
+        assert_close(host(models[0].tables.P), host(models[1].tables.P), f'P step {step}', rtol=1e-5, atol_scale=2e-6)
+
+
 def test_host_fed_context_on_tables_too_large_for_the_single_launch(ws):
     """wr_bprmf_ctx_step beyond the single-launch size (> 8 Mi elements): the two kernels read the ids straight from
     the mapped pinned buffer and the loss comes back by copy; same numbers as the device-fed step."""

@@ -211,6 +211,19 @@ class GeneralModel(BaseModel):
     def _on_fused(self):
         pass
 
+    def _prepare_grads(self):
+        """Integration level L1: when something other than FusedAdam drives the step -- the
+        reference's own BaseRunner builds `torch.optim.Adam(model.parameters())` and calls `zero_grad()`, which since
+        torch 2.0 sets `.grad = None` -- the gradient table is cleared here (no fused sweep re-zeroes it) and the two
+        `.grad` views into it are re-attached, so `loss.backward(); optimizer.step()` sees the kernel's gradient."""
+        t = self.tables
+        ue, ie = self._embedding_pair()
+        if not isinstance(self.optimizer, FusedAdam):
+            t.G.zero_()
+        if ue.weight.grad is None or ue.weight.grad.data_ptr() != t.G.data_ptr():
+            ue.weight.grad = t.users(t.G)
+            ie.weight.grad = t.items(t.G)
+
     # ---- one box, several GPUs: row-sharded tables over NVLink peer memory (whisprrec_b200/sharded.py) ----
     sharded = None
 

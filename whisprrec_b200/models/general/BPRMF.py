@@ -56,6 +56,7 @@ class BPRMF(GeneralModel):
         """BPRMF.py:69-80 + the backward of BaseRunner.py:198 in one launch; gradient lands in tables.G."""
         self.quiesce()
         t = self.fuse()
+        self._prepare_grads()
         out = t.loss if loss_out is None else loss_out
         _lib.bpr_fwd_bwd(t.users(t.P), t.items(t.P), feed_dict['user_id'], feed_dict['pos_item'],
                          feed_dict['neg_items'], t.users(t.G), t.items(t.G), out, t.ws)

@@ -188,6 +188,7 @@ class LightGCN(GeneralModel):
     def predict(self, feed_dict, loss_out=None):
         """LightGCN.py:150-175 and its backward (PropagationEngine.fwd_bwd)."""
         t = self.fuse()
+        self._prepare_grads()
         out = t.loss if loss_out is None else loss_out
         self.engine.fwd_bwd(feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items'], out)
         return out[0].detach().as_subclass(_base.FusedLoss)

@@ -136,6 +136,7 @@ class SGL(GeneralModel):
         t = self.fuse()
         if self.sub_graphs is None:
             self.graph_construction()
+        self._prepare_grads()
         out = t.loss if loss_out is None else loss_out
         user, pos, neg = feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items']
         L = self.gcn_layers
