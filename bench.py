@@ -800,6 +800,29 @@ def extras(corpus, dev, model, runner, data, hbm_peak):
             n_tr, n_dev = len(d100['train']), len(d100['dev'])
             res[name] = {'epoch_s': float(np.median(ep)), 'train_interactions_per_s': n_tr / float(np.median(ep)),
                          'dev_eval_s': float(np.median(ev)), 'eval_rows_per_s': n_dev / float(np.median(ev))}
+        try:    # SGL: whole epochs incl. the two edge-dropout views per epoch
+            from whisprrec_b200.main import default_args as _da
+            from whisprrec_b200.models.general.SGL import SGL
+            from whisprrec_b200.helpers.BaseRunner import BaseRunner as _BR
+            from whisprrec_b200.utils import utils as _u
+            sa = _da(SGL, lr=1e-3, l2=0.0, batch_size=B, embedding_size=D)
+            _u.init_seed(3407)
+            sm = SGL(sa, c100).to(dev)
+            sm.fuse()
+            sr = _BR(sa)
+            sm.optimizer = sr._build_optimizer(sm)
+            sd = {ph: SGL.Dataset(sm, c100, ph) for ph in ('train', 'dev')}
+            sr.fit(sd['train'])
+            ep = []
+            for _ in range(3):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                sr.fit(sd['train'])
+                torch.cuda.synchronize(); ep.append(time.perf_counter() - t0)
+            res['SGL'] = {'epoch_s': float(np.median(ep)), 'train_interactions_per_s': len(sd['train']) / float(np.median(ep)),
+                          'note': 'views redrawn every epoch (Python random stream on the host, CSR + transposed CSR on the device); '
+                                  'the unmodified reference needs 10.3 s for its first ml-100k epoch on the CPU (DESIGN.md r1 probe)'}
+        except Exception as e:  # noqa: BLE001
+            res['SGL'] = {'error': repr(e)}
         res['reference_cpu'] = {'note': 'unmodified reference on an 8-core host (BASELINE.md section 2): BPRMF epoch 1.4 s '
                                         '(47k interactions/s), LightGCN 1.7 s (39k/s), dev eval 1.3 s (6.3k rows/s)'}
         out['ml100k'] = res
