@@ -310,16 +310,27 @@ constexpr int TC_THREADS = (4 + TC_EPI_WARPS) * 32;
 // B travels through a ring of stages of SKB 64-element K blocks (32 KB each) of one 256-item tile: a whole tile per
 // stage for precision 1 (one barrier round per tile: 5 % faster at D = 128 than block-wise staging), one K block per
 // stage for precision 2, whose tiles (96 / 192 KB) would not fit twice.
-constexpr int TC_KBLOCK_BYTES = TC_BN * 128;
 constexpr int TC_CAND_BUF = 64;                        // candidate entries buffered per epilogue warp (precision 2)
-template <int K, int EXACT>
+// MT = 128-row A tiles per CTA.  MT = 1 (default): 128 rows x 256-item tiles; MT = 2 (WR_TC_VARIANT=12): 256 rows x
+// 128-item tiles -- the same 32,768 scores and the same 512 TMEM columns per tile, but every B byte that leaves L2 feeds
+// twice the rows.  Built to test whether the 6 TB/s of L2 reads (the item table is streamed once per 128 rows) is what
+// holds the kernel at 36 % tensor-pipe activity at D = 64: it is not -- 43.3 ms against 43.2 ms at D = 64, 60.2 against
+// 59.6 at D = 128 (profiles/r02_eval_variants.txt).  ncu: 0.745 instructions issued per cycle per SM sub-partition, ALU
+// pipe 65 % busy: the epilogue's ~4.5 issue slots per score (2 for the count, the rest mask / cursor / loop overhead per
+// 32-column chunk) are the limiter at D = 64.
+template <int K, int EXACT, int MT>
 struct TcCfg {
+    static constexpr int BM = TC_BM * MT;                  // rows per CTA
+    static constexpr int BN = MT == 2 ? 128 : TC_BN;       // items per tile
     static constexpr int KB = K / 64;                      // 64-element (128 B) K blocks
     static constexpr int SKB = EXACT ? 1 : KB;             // K blocks per stage
-    static constexpr int STAGE_BYTES = SKB * TC_KBLOCK_BYTES;
-    static constexpr int A_BYTES = TC_BM * K * 2;
-    static constexpr int STAGES = EXACT ? (K <= 192 ? 5 : 3) : (K == 64 ? 4 : 2);
+    static constexpr int KBLOCK_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = SKB * KBLOCK_BYTES;
+    static constexpr int A_BYTES = BM * K * 2;
     static constexpr int TAIL = 256 /*barriers*/ + 4 * TC_BM * 4 /*counts*/ + (EXACT ? TC_EPI_WARPS * TC_CAND_BUF * 8 : 0);
+    static constexpr int ROOM = 227 * 1024 - 1024 - A_BYTES - TAIL - (MT == 1 && !EXACT ? 19 * 1024 : 0) /*top-k drain state*/;
+    static constexpr int STAGES = ROOM / STAGE_BYTES > 6 ? 6 : ROOM / STAGE_BYTES;
+    static_assert(STAGES >= 2, "the B ring needs two stages");
     static constexpr int SMEM = 1024 /*align slack*/ + A_BYTES + STAGES * STAGE_BYTES + TAIL;
 };
 
@@ -416,10 +427,11 @@ __device__ __forceinline__ void ring_push(const TopRings &rg, int row, float x, 
     }
 }
 
-template <int K, int VARIANT, int TOPK, int EXACT>
+template <int K, int VARIANT, int TOPK, int EXACT, int MT>
 __global__ void __launch_bounds__(TOPK == 2 ? TC_THREADS_DRAIN : TC_THREADS, 1)
 eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
-    using C = TcCfg<K, EXACT>;
+    using C = TcCfg<K, EXACT, MT>;
+    static_assert(MT == 1 || TOPK == 0, "the top-k lists are laid out for 128 rows per CTA");
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
@@ -439,7 +451,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     rg.epi_done = reinterpret_cast<int *>(rg.tau + TC_BM);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
+    const int64_t row0 = (int64_t)blockIdx.x * C::BM;
     const int t0 = blockIdx.y * p.tiles_per_split;
     const int t1 = min(p.n_tiles, t0 + p.tiles_per_split);
 
@@ -480,7 +492,8 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             mbar_expect_tx(a_full, C::A_BYTES);
 #pragma unroll
             for (int kb = 0; kb < C::KB; ++kb)
-                tma_load_2d(&tmA, a_full, sA + kb * (TC_BM * 128), kb * 64, (int)row0);
+                for (int mh = 0; mh < MT; ++mh)
+                    tma_load_2d(&tmA, a_full, sA + (mh * C::KB + kb) * (TC_BM * 128), kb * 64, (int)row0 + mh * TC_BM);
             int it = 0;
             for (int t = t0; t < t1; ++t) {
 #pragma unroll 1
@@ -491,15 +504,15 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_expect_tx(&full[stage], C::STAGE_BYTES);
 #pragma unroll
                     for (int kb = 0; kb < C::SKB; ++kb)
-                        tma_load_2d(&tmB, &full[stage], sB + stage * C::STAGE_BYTES + kb * TC_KBLOCK_BYTES, (kb0 + kb) * 64,
-                                    t * TC_BN);
+                        tma_load_2d(&tmB, &full[stage], sB + stage * C::STAGE_BYTES + kb * C::KBLOCK_BYTES, (kb0 + kb) * 64,
+                                    t * C::BN);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ---------------- MMA issuer ----------------
-            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, TC_BN);
+            constexpr uint32_t idesc = umma_idesc_bf16(TC_BM, C::BN);
             mbar_wait(a_full, 0);
             tc_fence_after();
             int it = 0;
@@ -507,7 +520,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int acc = ti & 1;
                 const uint32_t aph = (ti >> 1) & 1;
                 mbar_wait(&tm_empty[acc], aph ^ 1);          // epilogue has drained this accumulator
-                const uint32_t d_tmem = tmem_base + acc * TC_BN;
+                const uint32_t d_tmem = tmem_base + acc * MT * C::BN;      // MT accumulators of BN columns per buffer
 #pragma unroll 1
                 for (int kb0 = 0; kb0 < C::KB; kb0 += C::SKB, ++it) {
                     const int stage = it % C::STAGES;
@@ -516,11 +529,14 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tc_fence_after();
 #pragma unroll
                     for (int kb = 0; kb < C::SKB; ++kb) {
-                        const uint64_t a0 = umma_desc_sw128(sA + (kb0 + kb) * (TC_BM * 128));
-                        const uint64_t b0 = umma_desc_sw128(sB + stage * C::STAGE_BYTES + kb * TC_KBLOCK_BYTES);
+                        const uint64_t b0 = umma_desc_sw128(sB + stage * C::STAGE_BYTES + kb * C::KBLOCK_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)         // K = 16 bf16 = 32 B per instruction: +2 in the >>4 address field
-                            umma_bf16(d_tmem, a0 + 2 * k, b0 + 2 * k, idesc, (kb0 | kb | k) != 0);
+                        for (int mh = 0; mh < MT; ++mh) {   // the two row halves share the B tile
+                            const uint64_t a0 = umma_desc_sw128(sA + (mh * C::KB + kb0 + kb) * (TC_BM * 128));
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)     // K = 16 bf16 = 32 B per instruction: +2 in the >>4 address field
+                                umma_bf16(d_tmem + mh * C::BN, a0 + 2 * k, b0 + 2 * k, idesc, (kb0 | kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty[stage]);              // frees the smem stage when the MMAs retire
                 }
@@ -529,8 +545,10 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
         // ---------------- epilogue: 16 warps, TMEM lane quarter = warp % 4, column group = (warp - 4) / 4 ----------------
-        const int quarter = warp & 3, grp = (warp - 4) >> 2;
-        const int rl = quarter * 32 + lane;
+        const int quarter = warp & 3, widx = (warp - 4) >> 2;
+        const int mh = MT == 2 ? widx >> 1 : 0;             // which 128-row half this warp reads
+        const int grp = MT == 2 ? (widx & 1) : widx;        // which 64-column stripe of the tile
+        const int rl = mh * TC_BM + quarter * 32 + lane;
         const int64_t r = row0 + rl;
         bool live = false;
         float st = 0.f;
@@ -545,7 +563,7 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             posj = (int32_t)p.pos[r];
             cur = p.hist_ptr[u];
             hend = p.hist_ptr[u + 1];
-            const int32_t first = (int32_t)min((int64_t)t0 * TC_BN, (int64_t)INT32_MAX);
+            const int32_t first = (int32_t)min((int64_t)t0 * C::BN, (int64_t)INT32_MAX);
             int64_t lo = cur, hi = hend;
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
@@ -584,8 +602,8 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int c = 0; c < 2; ++c) {
                 const int col0 = grp * 64 + c * 32;
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * TC_BN + col0), v);
-                const int32_t j0 = t * TC_BN + col0;
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * MT + mh) * C::BN + col0), v);
+                const int32_t j0 = t * C::BN + col0;
                 // columns of this chunk that must not count: history, past the table, the target itself
                 uint32_t m = 0, m_top = 0;      // m_top: not a candidate (history, past the table); the target is one
                 if (!live) {
@@ -814,10 +832,11 @@ eval_tc_rank_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 atomicAdd(rg.epi_done, 1);
             }
         }
-        cnt_s[grp * TC_BM + rl] = cnt;
+        cnt_s[grp * C::BM + rl] = cnt;
         asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");      // the epilogue warps only
         if (grp == 0 && r < p.R) {
-            const int total = cnt_s[rl] + cnt_s[TC_BM + rl] + cnt_s[2 * TC_BM + rl] + cnt_s[3 * TC_BM + rl];
+            const int total = MT == 2 ? cnt_s[rl] + cnt_s[C::BM + rl]
+                                      : cnt_s[rl] + cnt_s[TC_BM + rl] + cnt_s[2 * TC_BM + rl] + cnt_s[3 * TC_BM + rl];
             if (p.splits == 1) p.rank[r] = 1 + total;
             else atomicAdd(&p.rank[r], total);
             if (TOPK == 1) {
@@ -948,38 +967,44 @@ static int make_map(CUtensorMap *map, const void *base, int64_t rows, int D /* b
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
 
-template <int K, int VARIANT, int TOPK, int EXACT>
+template <int K, int VARIANT, int TOPK, int EXACT, int MT>
 static int launch_tc_v(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
-    constexpr int smem = TcCfg<K, EXACT>::SMEM + (TOPK == 2 ? TC_SMEM_DRAIN : 0);
+    constexpr int smem = TcCfg<K, EXACT, MT>::SMEM + (TOPK == 2 ? TC_SMEM_DRAIN : 0);
     constexpr int threads = TOPK == 2 ? TC_THREADS_DRAIN : TC_THREADS;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<K, VARIANT, TOPK, EXACT>,
+    cudaError_t e = cudaFuncSetAttribute(eval_tc_rank_kernel<K, VARIANT, TOPK, EXACT, MT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    eval_tc_rank_kernel<K, VARIANT, TOPK, EXACT><<<dim3(row_tiles, p.splits), threads, smem, st>>>(ma, mb, p);
+    eval_tc_rank_kernel<K, VARIANT, TOPK, EXACT, MT><<<dim3(row_tiles, p.splits), threads, smem, st>>>(ma, mb, p);
     return (int)cudaGetLastError();
+}
+
+static int tc_variant() {
+    static int variant = -1;
+    if (variant < 0) {
+        const char *e = getenv("WR_TC_VARIANT");        // tuning knob: the epilogue's counting form; 12 = 256 rows per CTA
+        variant = e ? atoi(e) : 1;
+    }
+    return variant;
 }
 
 template <int D>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, TcParams &p, int row_tiles, cudaStream_t st) {
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("WR_TC_VARIANT");        // tuning knob for the epilogue's counting form
-        variant = e ? atoi(e) : 1;
-    }
+    const int variant = tc_variant();
     if (p.topk_idx) {
         static int mode = -1;
         if (mode < 0) {
             const char *e = getenv("WR_TC_TOPK_MODE");      // 1: per-thread lists in the epilogue; 2: drain warps
             mode = e ? atoi(e) : 2;
         }
-        return mode == 1 ? launch_tc_v<D, 1, 1, 0>(ma, mb, p, row_tiles, st) : launch_tc_v<D, 1, 2, 0>(ma, mb, p, row_tiles, st);
+        return mode == 1 ? launch_tc_v<D, 1, 1, 0, 1>(ma, mb, p, row_tiles, st) : launch_tc_v<D, 1, 2, 0, 1>(ma, mb, p, row_tiles, st);
     }
     switch (variant) {
-        case 1: return launch_tc_v<D, 1, 0, 0>(ma, mb, p, row_tiles, st);
-        case 2: return launch_tc_v<D, 2, 0, 0>(ma, mb, p, row_tiles, st);
-        case 3: return launch_tc_v<D, 3, 0, 0>(ma, mb, p, row_tiles, st);
-        default: return launch_tc_v<D, 0, 0, 0>(ma, mb, p, row_tiles, st);
+        case 1: return launch_tc_v<D, 1, 0, 0, 1>(ma, mb, p, row_tiles, st);
+        case 2: return launch_tc_v<D, 2, 0, 0, 1>(ma, mb, p, row_tiles, st);
+        case 3: return launch_tc_v<D, 3, 0, 0, 1>(ma, mb, p, row_tiles, st);
+        case 12: return launch_tc_v<D, 1, 0, 0, 2>(ma, mb, p, row_tiles, st);      // 256 rows per CTA (see TcCfg)
+        default: return launch_tc_v<D, 0, 0, 0, 1>(ma, mb, p, row_tiles, st);
     }
 }
 
@@ -993,9 +1018,9 @@ using namespace wr;
 // ~0.1 % of the pairs; sized for 0.8 %) stays below 1 GB
 static void exact_blocking(int64_t R, int64_t n_items, int64_t *rows_per_block, unsigned long long *cand_cap) {
     int64_t rb = (int64_t)(16e9 / (double)n_items);
-    rb = rb / TC_BM * TC_BM;
-    if (rb < TC_BM) rb = TC_BM;
-    if (rb > R) rb = (R + TC_BM - 1) / TC_BM * TC_BM;
+    rb = rb / (2 * TC_BM) * (2 * TC_BM);
+    if (rb < 2 * TC_BM) rb = 2 * TC_BM;
+    if (rb > R) rb = (R + 2 * TC_BM - 1) / (2 * TC_BM) * (2 * TC_BM);
     unsigned long long cap = (unsigned long long)((double)rb * (double)n_items / 128.0);
     if (cap < (1ull << 20)) cap = 1ull << 20;
     if (cap > (1ull << 27)) cap = 1ull << 27;
@@ -1034,8 +1059,11 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
     uint8_t *row_ok = base;
     base += align_up((size_t)R, 1024);
 
+    // rows per CTA / items per tile: 128 x 256; 256 x 128 is the measured alternative (WR_TC_VARIANT=12)
+    const int mt = (!exact && !topk_idx && tc_variant() == 12) ? 2 : 1;
+    const int BMc = TC_BM * mt, BNc = mt == 2 ? 128 : TC_BN;
     CUtensorMap ma, mb;
-    int rc = make_map(&mb, Bm, n_items, K, TC_BN);
+    int rc = make_map(&mb, Bm, n_items, K, BNc);
     if (rc) return rc;
     TcParams p{};
     p.user = user; p.pos = pos; p.R = R; p.n_users = n_users; p.n_items = n_items;
@@ -1043,7 +1071,7 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
     p.rank = rank; p.scores = scores_out; p.splits = 1; p.k = k; p.top_trigger = k <= 16 ? 4 : 16;    // small k: keep tau fresh
     p.topk_idx = topk_idx; p.topk_val = topk_val;
     if (const char *e = getenv("WR_TC_TOP_TRIGGER")) p.top_trigger = atoi(e);     // tuning knob, <= TC_TOPBUF - 32
-    p.n_tiles = (int)((n_items + TC_BN - 1) / TC_BN);
+    p.n_tiles = (int)((n_items + BNc - 1) / BNc);
 
     if (!exact) {
         const int64_t n4 = n_items * D / 4;
@@ -1057,7 +1085,7 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
         WR_CHECK_LAUNCH();
         rc = make_map(&ma, A, R, K, TC_BM);
         if (rc) return rc;
-        const int64_t row_tiles64 = (R + TC_BM - 1) / TC_BM;
+        const int64_t row_tiles64 = (R + BMc - 1) / BMc;
         if (row_tiles64 > INT32_MAX) return WR_E_SIZE;
         const int row_tiles = (int)row_tiles64;
         int splits = 1;
@@ -1106,7 +1134,7 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
         q.anorm = anorm + r0;
         rc = make_map(&ma, A + r0 * K, rn, K, TC_BM);
         if (rc) return rc;
-        const int row_tiles = (int)((rn + TC_BM - 1) / TC_BM);
+        const int row_tiles = (int)((rn + BMc - 1) / BMc);
         int splits = 1;
         if (row_tiles < kSMs) splits = (kSMs + row_tiles - 1) / row_tiles;
         if (splits > q.n_tiles) splits = q.n_tiles;
@@ -1119,7 +1147,7 @@ int wr_eval_rank_tc(const float *Uemb, const float *Iemb, const int64_t *user, c
         }
         e = cudaMemsetAsync(cand_cnt, 0, sizeof(unsigned long long), st);
         if (e != cudaSuccess) return (int)e;
-        rc = D == 64 ? launch_tc_v<192, 1, 0, 1>(ma, mb, q, row_tiles, st) : launch_tc_v<384, 1, 0, 1>(ma, mb, q, row_tiles, st);
+        rc = D == 64 ? launch_tc_v<192, 1, 0, 1, 1>(ma, mb, q, row_tiles, st) : launch_tc_v<384, 1, 0, 1, 1>(ma, mb, q, row_tiles, st);
         if (rc) return rc;
         eval_recheck_kernel<<<8 * kSMs, 256, 0, st>>>(cand, cand_cnt, cap, target_in ? Uemb + r0 * D : Uemb, q.user,
                                                        target_in ? 1 : 0, Iemb, D, q.target, q.rank);
