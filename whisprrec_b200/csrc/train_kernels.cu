@@ -524,6 +524,8 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
     }
     __syncthreads();
     // ---- phase 2: Adam + L2 over every element, gradient re-zeroed; two iterations of loads in flight ----
+    // div_nr / sqrt_nr (<= 1 ulp from the IEEE forms): with the IEEE sequences this phase is issue-bound on cache-sized tables
+    const float inv_bc2 = 1.0f / s.bc2_sqrt;
     const float4 z = f4_zero();
     for (int64_t i = i0; i < n4; i += 2 * stride) {
         const int64_t i2 = i + stride;
@@ -536,19 +538,19 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
             vb = V[i2];
             gb = __ldcg(G + i2);
         }
-        adam_elem(pa.x, ma.x, va.x, ga.x, s);
-        adam_elem(pa.y, ma.y, va.y, ga.y, s);
-        adam_elem(pa.z, ma.z, va.z, ga.z, s);
-        adam_elem(pa.w, ma.w, va.w, ga.w, s);
+        adam_elem_nr(pa.x, ma.x, va.x, ga.x, s, inv_bc2);
+        adam_elem_nr(pa.y, ma.y, va.y, ga.y, s, inv_bc2);
+        adam_elem_nr(pa.z, ma.z, va.z, ga.z, s, inv_bc2);
+        adam_elem_nr(pa.w, ma.w, va.w, ga.w, s, inv_bc2);
         P[i] = pa;
         M[i] = ma;
         V[i] = va;
         G[i] = z;
         if (two) {
-            adam_elem(pb.x, mb.x, vb.x, gb.x, s);
-            adam_elem(pb.y, mb.y, vb.y, gb.y, s);
-            adam_elem(pb.z, mb.z, vb.z, gb.z, s);
-            adam_elem(pb.w, mb.w, vb.w, gb.w, s);
+            adam_elem_nr(pb.x, mb.x, vb.x, gb.x, s, inv_bc2);
+            adam_elem_nr(pb.y, mb.y, vb.y, gb.y, s, inv_bc2);
+            adam_elem_nr(pb.z, mb.z, vb.z, gb.z, s, inv_bc2);
+            adam_elem_nr(pb.w, mb.w, vb.w, gb.w, s, inv_bc2);
             P[i2] = pb;
             M[i2] = mb;
             V[i2] = vb;
