@@ -99,6 +99,28 @@ int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64_t *user, c
                   double beta1, double beta2, float eps, float step_size, float bc2_sqrt, const float *dev_scalars,
                   float *loss_out, void *ws, void *stream);
 
+/* Row-marked variants for tables too large for the caches, where the sweep is HBM-bound.  BPRMF's gradient is zero
+ * outside the 3 B rows of the batch (models/general/BPRMF.py:41-53: only the gathered rows enter the loss), so `touched`
+ * -- ceil(n_rows / 32) uint32 words of DEVICE memory, bit r = row r of G is non-zero, ALL ZERO between steps -- lets
+ * the sweep skip the read and the re-zeroing of every other gradient row: 24 bytes of traffic per parameter instead
+ * of 32, results identical bit for bit.
+ *   wr_mark_rows             sets the bits of a batch (rows user[b], n_users + pos[b], n_users + neg[b])
+ *   wr_adam_l2_sweep_marked  wr_adam_l2_sweep over n_rows x D that reads G only where a bit is set; clears the map
+ *   wr_inbox_scatter_marked  wr_inbox_scatter that also sets the bit of every owner-local row it adds into
+ *   wr_bprmf_step_marked     wr_bprmf_step on the three above (cache-sized tables: the single launch, map untouched)
+ */
+int wr_mark_rows(const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B, int64_t n_users,
+                 int64_t n_items, uint32_t *touched, void *stream);
+int wr_adam_l2_sweep_marked(float *P, float *M, float *V, float *G, int64_t n_rows, int D, uint32_t *touched, float l2,
+                            double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
+                            const float *dev_scalars, void *stream);
+int wr_inbox_scatter_marked(float *G, const float *inbox_rows, int32_t *inbox_idx, int world, int64_t cap, int D,
+                            uint32_t *touched, void *stream);
+int wr_bprmf_step_marked(float *P, float *M, float *V, float *G, uint32_t *touched, const int64_t *user,
+                         const int64_t *pos, const int64_t *neg, int64_t B, int D, int64_t n_users, int64_t n_items,
+                         float gamma, float l2, double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
+                         const float *dev_scalars, float *loss_out, void *ws, void *stream);
+
 /* wr_bprmf_epoch: the step loop of BaseRunner.fit (BaseRunner.py:194-200) in one call: batch s is columns
  * [s * batch, min(N, (s + 1) * batch)) of ids[3][N] (DEVICE, rows user / pos / neg), Adam's t runs from adam_t0 + 1,
  * losses[s] (DEVICE, ceil(N / batch) floats) receives the loss of step s.  When the Adam state fits in the SMs' shared
@@ -242,6 +264,10 @@ typedef struct wr_spmm_plan {
     const uint32_t *hot_bits;     /* nullable: bitmap over the N columns; rows of X whose bit is set are loaded with an L2
                                      evict_last policy, the col / val streams with evict_first.  For tables far larger than
                                      L2: mark the highest-degree nodes, as many as fit in ~2/3 of L2 */
+    const uint32_t *x_rows;       /* nullable, per call: bitmap over the N columns; a row of X whose bit is CLEAR is taken as
+                                     zero and is not fetched (the first backward propagation: the pooled gradient of a
+                                     batch is zero outside the batch's 3 B rows, LightGCN.py:150-163).  Same result bit for
+                                     bit as reading the zeros.  Takes precedence over hot_bits. */
 } wr_spmm_plan;
 
 int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const float *val, int64_t N, int D, const float *X,
@@ -403,7 +429,9 @@ int wr_inbox_scatter(float *G, const float *inbox_rows, int32_t *inbox_idx, int 
  *       receive buffer (host_recv[r]: rank r's [world][cap][D] fp32; we write block [rank], in request order).
  *   -- wr_peer_barrier --
  *   wr_bpr_fwd_bwd_exchanged: wr_bpr_fwd_bwd_sharded_staged with the three rows of entry b read from
- *       recv[where[3 b + role]] (local memory); gradient rows go to the owners' inboxes as before.
+ *       recv[where[3 b + role]] (local memory); gradient rows go to the owners' inboxes as before.  touched
+ *       (nullable): the row map of wr_adam_l2_sweep_marked over this rank's rows -- rows the kernel reduces in place
+ *       (entries this rank owns itself) get their bit; wr_inbox_scatter_marked adds the rest.
  * cap >= 3 x the largest per-rank batch.  Ids outside their table raise WR_STATUS_INDEX_OUT_OF_RANGE (entry skipped).
  */
 int wr_xchg_request(const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B, int64_t n_users,
@@ -415,8 +443,19 @@ int wr_xchg_serve(const float *T_local, int D, int world, int rank, const int32_
 int wr_bpr_fwd_bwd_exchanged(const float *recv, const int32_t *where, const wr_shards *host_Gd,
                              float *const host_inbox_rows[WR_MAX_WORLD], int32_t *const host_inbox_idx[WR_MAX_WORLD],
                              int64_t cap, const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B,
-                             int64_t B_global, int D, float gamma, float grad_scale, float *loss_out, void *ws,
-                             void *stream);
+                             int64_t B_global, int D, float gamma, float grad_scale, uint32_t *touched, float *loss_out,
+                             void *ws, void *stream);
+
+/* wr_push_marked_rows: the all-gather of a row-sharded table that is zero outside a few rows -- the pooled gradient of
+ * a batch, input of the first adjoint propagation (LightGCN.py:150-163 backward).  node_bits: bitmap over the GLOBAL node
+ * ids [n_users + n_items] (wr_mark_rows on every rank's slice of the batch, OR-ed over the ranks); this rank stores each
+ * of ITS rows whose bit is set into host_push[g] + local_row * D for every peer g (host_push[g]: rank g's copy of this
+ * rank's shard; entry [rank] ignored).  The unmarked rows of the copies are left as they are: the SpMM that follows
+ * gets the same bitmap as wr_spmm_plan.x_rows and never fetches them.  host_X: the table's wr_shards (layout and
+ * base[rank] = the local shard).
+ */
+int wr_push_marked_rows(const wr_shards *host_X, int D, const uint32_t *node_bits, float *const host_push[WR_MAX_WORLD],
+                        void *stream);
 
 /* wr_embloss_owner_sumsq / wr_embloss_owner_scatter: EmbLoss (utils/loss.py:83-98, LightGCN.py:165-175) computed by the
  * OWNERS of the ego rows from the request lists of wr_xchg_request, which hold every occurrence of every row of the

@@ -127,9 +127,14 @@ def run(a, rank, world, dev, peers=None):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms = float(tt.item())
     # one SpMM pass P = nnz (4 + 4 + 4D) + N (4 + 4D); step = 2L P + 2 (L+2) N 4D + 32 D N + 48 B D + 12 B
+    # The first adjoint pass reads the pooled gradient of the batch, which is zero outside <= 3 B world rows: when the
+    # step skips those rows (12 B world <= N, wr_spmm_plan.x_rows) its row reads are counted for the marked share only.
+    sparse_first = L > 0 and 12 * B * world <= N
+    marked_share = min(1.0, 3.0 * B * world / N) if sparse_first else 1.0
     def step_bytes(n_rows, n_nnz):
         P = n_nnz * (8 + 4 * D) + n_rows * (4 + 4 * D)
-        return 2 * L * P + 2 * (L + 2) * n_rows * 4 * D + 32 * D * n_rows + 48 * B * D + 12 * B
+        P1 = n_nnz * (8 + 4 * D * marked_share) + n_rows * (4 + 4 * D)
+        return (2 * L - 1) * P + P1 + 2 * (L + 2) * n_rows * 4 * D + 32 * D * n_rows + 48 * B * D + 12 * B
     per_gpu = step_bytes(n_local, nnz_local)
     gbs = per_gpu / (ms * 1e-3) / 1e9
     return {
@@ -138,6 +143,8 @@ def run(a, rank, world, dev, peers=None):
         'interactions_per_s': world * B / (ms * 1e-3), 'steps_per_s': 1e3 / ms,
         'algorithmic_bytes_per_gpu_step': per_gpu, 'algorithmic_gbs_per_gpu': gbs,
         'frac_of_hbm_peak': gbs / peaks['hbm_gbs'], 'hbm_peak_gbs': peaks['hbm_gbs'],
+        'first_adjoint_pass': ('rows of the pooled gradient outside the batch are not fetched (marked share %.4f)' % marked_share)
+        if sparse_first else 'dense',
         'compulsory_bytes_per_pass': nnz_local * 8 + n_local * (4 + 8 * D),
         'compulsory_bytes_per_gpu_step': 2 * L * (nnz_local * 8 + n_local * (4 + 8 * D)) + 2 * (L + 2) * n_local * 4 * D + 32 * D * n_local,
         'graph_build_s': t_graph, 'mem_gb': torch.cuda.max_memory_allocated() / 1e9}

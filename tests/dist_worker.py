@@ -245,6 +245,36 @@ def run_gpu():
             assert tabs2.ws.status() == 0
             if B >= 8192 * world:
                 assert getattr(tabs2, '_xchg', None) is not None and int(tabs2._inbox['idx'].abs().max()) == 0
+        # ---------------- the sparse pooled-gradient exchange (marked rows pushed, masked first adjoint SpMM) ----------------
+        if D == 128:
+            nU2, nI2, B2, L, reg = 40000, 30000, 8192 * world, 3, 1e-5
+            rng2, U2, I2, pairs2 = problem(17, nU2, nI2, D, 4 * nU2)
+            lay2 = S.ShardLayout(nU2, nI2, world, rank)
+            rowptr, col, val = O.build_norm_adj_csr(nU2, nI2, pairs2[:, 0], pairs2[:, 1])
+            dinv = O.deg_inv_sqrt(np.diff(rowptr))
+            tabs4 = S.ShardedTables(peers, lay2, D)
+            tabs4.load_full(d(U2), d(I2))
+            lg = S.ShardedLightGCN(tabs4, rowptr, col, dinv, L, reg, gather_first=True)
+            lg.sparse_grad = True
+            A = O.csr_to_torch(rowptr, col, val, nU2 + nI2)
+            oU, oI = torch.from_numpy(U2.copy()), torch.from_numpy(I2.copy())
+            om = [torch.zeros_like(oU), torch.zeros_like(oU), torch.zeros_like(oI), torch.zeros_like(oI)]
+            for step in range(1, 3):
+                sel = rng2.randint(0, len(pairs2), B2)
+                user, pos = pairs2[sel, 0].astype(np.int64), pairs2[sel, 1].astype(np.int64)
+                neg = rng2.randint(1, nI2 // 4, B2).astype(np.int64)          # a quarter of the items: many rows stay unmarked
+                lo, hi = lay2.batch_slice(B2)
+                loss = lg.step(d(user[lo:hi]), d(pos[lo:hi]), d(neg[lo:hi]), B2, 1e-3, 0.0)
+                o_loss, ogU, ogI = O.lightgcn_fwd_bwd(A, oU, oI, user, pos, neg, L, reg)
+                O.adam_l2_step(oU, om[0], om[1], ogU, step, 1e-3, 0.0)
+                O.adam_l2_step(oI, om[2], om[3], ogI, step, 1e-3, 0.0)
+                assert abs(float(loss[0]) - float(o_loss)) <= 1e-5 * abs(float(o_loss)), (float(loss[0]), float(o_loss))
+                gu, gi = tabs4.gather_full()
+                assert_close(host(gu), oU.numpy(), f'sparse-exchange LightGCN U step {step}', rtol=1e-4, atol_scale=1e-4)
+                assert_close(host(gi), oI.numpy(), f'sparse-exchange LightGCN I step {step}', rtol=1e-4, atol_scale=1e-4)
+                peers.barrier()
+            assert int(lg._gm.ne(0).sum()) == 0 and tabs4.ws.status() == 0
+            del lg, tabs4
         peers.host_sync()
         if rank == 0:
             print(f'dist_worker gpu ok: world {world} nU {nU} nI {nI} D {D}')

@@ -414,6 +414,65 @@ def test_adam_l2_sweep_vs_oracle(n):
     assert torch.equal(P, P2) and torch.equal(M, M2) and torch.equal(V, V2)
 
 
+@pytest.mark.parametrize('rows,D', [(3000, 64), (70001, 128), (1237, 20)])
+def test_row_marked_adam_sweep_equals_the_dense_sweep(rows, D):
+    """wr_adam_l2_sweep_marked: G is read (and re-zeroed) only where the row map says so; with the map covering exactly
+    the non-zero rows every bit of P / M / V equals the dense sweep's, and the map comes back empty."""
+    rng = np.random.RandomState(rows % 97)
+    P0 = (rng.randn(rows, D) * 0.1).astype(np.float32)
+    Pa, Pb = dv(P0), dv(P0)
+    Ma, Va, Mb, Vb = (torch.zeros_like(Pa) for _ in range(4))
+    touched = _lib.row_map(rows, DEV)
+    for step in range(1, 4):
+        hot = np.unique(rng.randint(0, rows, size=max(1, rows // 50)))
+        g = np.zeros((rows, D), dtype=np.float32)
+        g[hot] = (rng.randn(len(hot), D) * 1e-2).astype(np.float32)
+        Ga, Gb = dv(g), dv(g)
+        bits = np.zeros((rows + 31) // 32, dtype=np.uint32)
+        np.bitwise_or.at(bits, hot >> 5, (np.uint32(1) << (hot & 31).astype(np.uint32)))
+        touched.copy_(torch.from_numpy(bits.view(np.int32)))
+        _lib.adam_l2_sweep_marked(Pa, Ma, Va, Ga, touched, step, 1e-3, 1e-4)
+        _lib.adam_l2_sweep(Pb, Mb, Vb, Gb, step, 1e-3, 1e-4)
+        assert torch.equal(Pa, Pb) and torch.equal(Ma, Mb) and torch.equal(Va, Vb)
+        assert float(Ga.abs().max()) == 0.0 and int(touched.ne(0).sum()) == 0
+    # a row whose bit is clear is not read at all: garbage there must not reach the parameters
+    Ga = torch.full_like(Pa, float('nan'))
+    Gb = torch.zeros_like(Pb)
+    _lib.adam_l2_sweep_marked(Pa, Ma, Va, Ga, touched, 4, 1e-3, 1e-4)
+    _lib.adam_l2_sweep(Pb, Mb, Vb, Gb, 4, 1e-3, 1e-4)
+    assert torch.equal(Pa, Pb)
+
+
+def test_row_marked_bprmf_step_equals_the_unmarked_step(ws):
+    """wr_bprmf_step_marked on tables beyond the single-launch size: same loss and, up to the order of the float
+    reductions into a repeated row, the same tables as wr_bprmf_step; the gradient and the map end the step at zero."""
+    rng = np.random.RandomState(21)
+    nU, nI, D, B = 50000, 30000, 128, 8192            # 10.2 M elements
+    P0 = (rng.randn(nU + nI, D) * 0.05).astype(np.float32)
+    Pa, Pb = dv(P0), dv(P0)
+    Ma, Va, Ga = (torch.zeros_like(Pa) for _ in range(3))
+    Mb, Vb, Gb = (torch.zeros_like(Pb) for _ in range(3))
+    touched = _lib.row_map(nU + nI, DEV)
+    never = torch.ones(nU + nI, dtype=torch.bool, device=DEV)
+    la, lb = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    for step in range(1, 4):
+        ids = dv(np.stack([rng.randint(0, nU, B), rng.randint(0, nI, B), rng.randint(1, nI, B)]).astype(np.int64))
+        _lib.bprmf_step(Pa, Ma, Va, Ga, ids[0], ids[1], ids[2], nU, step, 1e-3, 1e-6, la, ws, touched=touched)
+        _lib.bprmf_step(Pb, Mb, Vb, Gb, ids[0], ids[1], ids[2], nU, step, 1e-3, 1e-6, lb, ws)
+        assert float(la[0]) == float(lb[0])
+        assert float(Ga.abs().max()) == 0.0 and int(touched.ne(0).sum()) == 0
+        assert float((Pa - Pb).abs().max()) <= 2e-6 * float(Pb.abs().max()) + 1e-9
+        never[ids[0]] = False                     # rows no batch has touched so far: bit-identical (no float reductions)
+        never[nU + ids[1]] = False
+        never[nU + ids[2]] = False
+        assert torch.equal(Pa[never], Pb[never]) and torch.equal(Va[never], Vb[never])
+    # out-of-range ids: reported, skipped, and never marked
+    bad = dv(np.array([[0, nU], [1, 2], [3, 4]], dtype=np.int64))
+    _lib.bprmf_step(Pa, Ma, Va, Ga, bad[0], bad[1], bad[2], nU, 4, 1e-3, 1e-6, la, ws, touched=touched)
+    assert ws.status() & 1                                    # WR_STATUS_INDEX_OUT_OF_RANGE, read-and-clear
+    assert int(touched.ne(0).sum()) == 0
+
+
 def test_adam_zero_gradient_no_decay_is_identity():
     P = torch.randn(1000, 64, device=DEV)
     P0 = P.clone()
@@ -643,6 +702,44 @@ def test_csr_spmm_hot_row_cache_policy_changes_nothing_but_the_cache(ws):
     short = torch.from_numpy(np.diff(h_rowptr) <= 128).to(DEV)
     assert torch.equal(ya[short], yb[short]) and torch.equal(pa[short], pb[short])
     assert_close(host(yb), host(ya), 'sliced rows', rtol=1e-5, atol_scale=2e-6)
+
+
+@pytest.mark.parametrize('D', [128, 64, 20])
+def test_csr_spmm_row_map_skips_zero_rows_and_changes_no_bit(ws, D):
+    """wr_spmm_plan.x_rows (the first adjoint propagation: X is the pooled gradient of a batch, zero outside a few rows):
+    rows whose bit is clear are not fetched; with the map covering the non-zero rows the result is the unmasked one,
+    and garbage in an unmarked row never reaches the output."""
+    from whisprrec_b200.models.general.LightGCN import build_norm_adj_device
+    from whisprrec_b200.utils import synthetic
+    nU, nI = 30_000, 4_000
+    uu, ii = synthetic.power_law_pairs(nU, nI, 300_000, seed=11)
+    rowptr, col, val, _ = build_norm_adj_device(nU, nI, uu.to(DEV), ii.to(DEV), ws)
+    h_rowptr = host(rowptr)
+    N = nU + nI
+    rng = np.random.RandomState(D)
+    hot = np.unique(np.concatenate([rng.randint(0, N, 2000), np.arange(nU, nU + 40)]))     # incl. the popular items
+    X = torch.zeros((N, D), device=DEV)
+    X[dv(hot)] = torch.randn((len(hot), D), device=DEV) * 0.1
+    bits = np.zeros((N + 31) // 32, dtype=np.uint32)
+    np.bitwise_or.at(bits, hot >> 5, (np.uint32(1) << (hot & 31).astype(np.uint32)))
+    x_rows = dv(bits.view(np.int32))
+    plan = _lib.SpmmPlan(h_rowptr, D, DEV)
+    add = torch.randn((N, D), device=DEV)
+    ya, yb = torch.empty_like(X), torch.empty_like(X)
+    _lib.csr_spmm(rowptr, col, val, X, Y=ya, add=add, plan=plan)
+    _lib.csr_spmm(rowptr, col, val, X, Y=yb, add=add, plan=plan, x_rows=x_rows)
+    short = torch.from_numpy(np.diff(h_rowptr) <= 128).to(DEV) if plan.n_chunks else torch.ones(N, dtype=torch.bool, device=DEV)
+    assert torch.equal(ya[short], yb[short])
+    assert_close(host(yb), host(ya), 'sliced rows', rtol=1e-5, atol_scale=2e-6)
+    cold = torch.ones(N, dtype=torch.bool, device=DEV)
+    cold[dv(hot)] = False
+    X[cold] = float('nan')
+    yc = torch.empty_like(X)
+    _lib.csr_spmm(rowptr, col, val, X, Y=yc, add=add, x_rows=x_rows)                       # and without a plan
+    assert bool(torch.isfinite(yc).all())
+    assert_close(host(yc), host(ya), 'no plan', rtol=1e-5, atol_scale=2e-6)
+    with pytest.raises(_lib.WhisprError):
+        _lib.csr_spmm(rowptr, col, val, X, Y=yc, x_rows=x_rows[:10])
 
 
 def test_csr_norm_weights_bit_exact():

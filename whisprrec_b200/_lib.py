@@ -71,10 +71,17 @@ SIGNATURES = {
     'wr_bpr_fwd_bwd_sharded_staged': (_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
     'wr_xchg_request': (_int, [_p, _p, _p, _i64, _i64, _i64, _int, _int, _p, _p, _i64, _p, _p, _p, _p]),
     'wr_xchg_serve': (_int, [_p, _int, _int, _int, _p, _p, _i64, _p, _p]),
-    'wr_bpr_fwd_bwd_exchanged': (_int, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p]),
+    'wr_bpr_fwd_bwd_exchanged': (_int, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _p, _p, _p,
+                                        _p]),
     'wr_embloss_owner_sumsq': (_int, [_p, _int, _int, _p, _p, _i64, _p, _p, _p]),
     'wr_embloss_owner_scatter': (_int, [_p, _p, _int, _int, _p, _p, _i64, _f32, _i64, _p, _p, _p]),
     'wr_inbox_scatter': (_int, [_p, _p, _p, _int, _i64, _int, _p]),
+    'wr_push_marked_rows': (_int, [_p, _int, _p, _p, _p]),
+    'wr_inbox_scatter_marked': (_int, [_p, _p, _p, _int, _i64, _int, _p, _p]),
+    'wr_mark_rows': (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p]),
+    'wr_adam_l2_sweep_marked': (_int, [_p, _p, _p, _p, _i64, _int, _p, _f32, _f64, _f64, _f32, _f32, _f32, _p, _p]),
+    'wr_bprmf_step_marked': (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _int, _i64, _i64, _f32, _f32, _f64, _f64, _f32,
+                                    _f32, _f32, _p, _p, _p, _p]),
     'wr_bprmf_step_sharded_supported': (_int, [_i64, _int]),
     'wr_bprmf_step_sharded': (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _int, _f32, _f32, _f64, _f64, _f32, _f32,
                                      _f32, _c.c_uint32, _p, _p, _p, _p, _p]),
@@ -227,10 +234,44 @@ def adam_l2_sweep(P, M, V, G, step, lr, l2, beta1=0.9, beta2=0.999, eps=1e-8, de
                                   eps, ss, bc2s, ptr(dev_scalars, F32), stream_ptr()))
 
 
-def bprmf_step(P, M, V, G, user, pos, neg, n_users, step, lr, l2, loss_out, ws, beta1=0.9, beta2=0.999, eps=1e-8,
-               gamma=1e-10, dev_scalars=None):
-    """One BPRMF iteration (zero_grad + predict + backward + Adam.step) on the fused tables."""
+FUSED_STEP_MAX_ELEMS = 8 << 20      # WR_FUSED_STEP_MAX_ELEMS of csrc/train_kernels.cu: beyond it steps stream from HBM
+
+
+def row_map(n_rows, device):
+    """The `touched` bitmap of the row-marked entry points: one bit per table row, all zero between steps."""
+    return torch.zeros((n_rows + 31) // 32, dtype=I32, device=device)
+
+
+def adam_l2_sweep_marked(P, M, V, G, touched, step, lr, l2, beta1=0.9, beta2=0.999, eps=1e-8, dev_scalars=None):
+    """adam_l2_sweep for a gradient that is zero outside the rows whose bit is set in `touched` (cleared on return)."""
+    if touched.numel() < (P.shape[0] + 31) // 32:
+        raise WhisprError('row map too small for the table')
     ss, bc2s = adam_scalars(step, lr, beta1, beta2)
+    check(load().wr_adam_l2_sweep_marked(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), P.shape[0], P.shape[1],
+                                         ptr(touched, I32), l2, beta1, beta2, eps, ss, bc2s, ptr(dev_scalars, F32),
+                                         stream_ptr()))
+
+
+def mark_rows(user, pos, neg, n_users, n_items, touched):
+    if touched.numel() < (n_users + n_items + 31) // 32:
+        raise WhisprError('row map too small for the table')
+    check(load().wr_mark_rows(ptr(user, I64), ptr(pos, I64), ptr(neg, I64), user.numel(), n_users, n_items,
+                              ptr(touched, I32), stream_ptr()))
+
+
+def bprmf_step(P, M, V, G, user, pos, neg, n_users, step, lr, l2, loss_out, ws, beta1=0.9, beta2=0.999, eps=1e-8,
+               gamma=1e-10, dev_scalars=None, touched=None):
+    """One BPRMF iteration (zero_grad + predict + backward + Adam.step) on the fused tables.  With a row map
+    (`touched`, see row_map) tables beyond the caches skip the gradient rows the batch did not touch."""
+    ss, bc2s = adam_scalars(step, lr, beta1, beta2)
+    if touched is not None:
+        if touched.numel() < (P.shape[0] + 31) // 32:
+            raise WhisprError('row map too small for the table')
+        check(load().wr_bprmf_step_marked(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), ptr(touched, I32),
+                                          ptr(user, I64), ptr(pos, I64), ptr(neg, I64), user.numel(), P.shape[1], n_users,
+                                          P.shape[0] - n_users, gamma, l2, beta1, beta2, eps, ss, bc2s,
+                                          ptr(dev_scalars, F32), ptr(loss_out, F32), ws.ptr, stream_ptr()))
+        return
     check(load().wr_bprmf_step(ptr(P, F32), ptr(M, F32), ptr(V, F32), ptr(G, F32), ptr(user, I64), ptr(pos, I64),
                                ptr(neg, I64), user.numel(), P.shape[1], n_users, P.shape[0] - n_users, gamma, l2,
                                beta1, beta2, eps, ss, bc2s, ptr(dev_scalars, F32), ptr(loss_out, F32), ws.ptr,
@@ -365,7 +406,22 @@ class _PlanStruct(ctypes.Structure):
     """Mirror of `wr_spmm_plan` (include/whisprrec_b200.h)."""
     _fields_ = [('long_threshold', _i64), ('n_chunks', _i64), ('n_long', _i64),
                 ('chunk_row', _p), ('chunk_beg', _p), ('chunk_len', _p), ('chunk_slot', _p), ('slot_chunks', _p),
-                ('slot_arrivals', _p), ('slot_partial', _p), ('hot_bits', _p)]
+                ('slot_arrivals', _p), ('slot_partial', _p), ('hot_bits', _p), ('x_rows', _p)]
+
+
+def _plan_ref(plan, x_rows, keep):
+    """Pointer to the wr_spmm_plan of a call: the plan's own struct, or a copy of it carrying the per-call x_rows map."""
+    base = None if plan is None else plan.struct
+    if x_rows is None:
+        return None if base is None else ctypes.addressof(base)
+    st = _PlanStruct()
+    if base is not None:
+        ctypes.memmove(ctypes.addressof(st), ctypes.addressof(base), ctypes.sizeof(st))
+    else:
+        st.long_threshold = (1 << 63) - 1
+    st.x_rows = ptr(x_rows, I32)
+    keep.append(st)
+    return ctypes.addressof(st)
 
 
 class SpmmPlan:
@@ -431,11 +487,15 @@ class SpmmPlan:
 
 
 def csr_spmm(rowptr, col, val, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None, acc_div=1.0,
-             plan=None):
+             plan=None, x_rows=None):
+    """x_rows: optional bitmap over the rows of X (row_map): rows whose bit is clear are zero and are not fetched."""
     N, D = X.shape
+    if x_rows is not None and x_rows.numel() < (N + 31) // 32:
+        raise WhisprError('row map too small for X')
+    keep = []
     check(load().wr_csr_spmm(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), N, D, ptr(X, F32), ptr(Y, F32),
                              ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32), acc_div,
-                             None if plan is None else plan.ref(), stream_ptr()))
+                             _plan_ref(plan, x_rows, keep), stream_ptr()))
 
 
 def exact_tc_supported(D, k=0, scores=False):
@@ -662,13 +722,13 @@ def xchg_serve(T_local, world, rank, req_local, cnt_local, cap, recv_ptrs):
 
 
 def bpr_fwd_bwd_exchanged(recv, where, Gd, inbox_row_ptrs, inbox_idx_ptrs, cap, user, pos, neg, B_global, D, loss_out, ws,
-                          gamma=1e-10, grad_scale=1.0):
+                          gamma=1e-10, grad_scale=1.0, touched=None):
     world = Gd.world
     ra, ia = _ptr_array(inbox_row_ptrs, world), _ptr_array(inbox_idx_ptrs, world)
     check(load().wr_bpr_fwd_bwd_exchanged(ptr(recv, F32), ptr(where, I32), ctypes.addressof(Gd), ctypes.addressof(ra),
                                           ctypes.addressof(ia), cap, ptr(user, I64), ptr(pos, I64), ptr(neg, I64),
-                                          user.numel(), B_global, D, gamma, grad_scale, ptr(loss_out, F32), ws.ptr,
-                                          stream_ptr()))
+                                          user.numel(), B_global, D, gamma, grad_scale, ptr(touched, I32),
+                                          ptr(loss_out, F32), ws.ptr, stream_ptr()))
 
 
 def embloss_owner_sumsq(T_local, world, req_local, cnt_local, cap, sumsq_out, ws):
@@ -682,9 +742,15 @@ def embloss_owner_scatter(T_local, G_local, world, req_local, cnt_local, cap, re
                                           ptr(loss_out, F32), stream_ptr()))
 
 
-def inbox_scatter(G, inbox_rows, inbox_idx, world, cap):
-    check(load().wr_inbox_scatter(ptr(G, F32), ptr(inbox_rows, F32), ptr(inbox_idx, I32), world, cap, G.shape[1],
-                                  stream_ptr()))
+def inbox_scatter(G, inbox_rows, inbox_idx, world, cap, touched=None):
+    check(load().wr_inbox_scatter_marked(ptr(G, F32), ptr(inbox_rows, F32), ptr(inbox_idx, I32), world, cap, G.shape[1],
+                                         ptr(touched, I32), stream_ptr()))
+
+
+def push_marked_rows(X, D, node_bits, push_ptrs):
+    """Store this rank's rows of the sharded table X whose GLOBAL node bit is set into every peer's copy of the shard."""
+    pa = _ptr_array(push_ptrs, X.world)
+    check(load().wr_push_marked_rows(ctypes.addressof(X), D, ptr(node_bits, I32), ctypes.addressof(pa), stream_ptr()))
 
 
 def bprmf_step_sharded_supported(n_local_rows, D):
@@ -731,16 +797,17 @@ def allgather_shards(src, dst, D):
 
 
 def csr_spmm_sharded(rowptr, col, val, n_local, D, X, Y=None, add=None, zero_add=False, acc_in=None, acc_out=None,
-                     acc_div=1.0, plan=None, push_ptrs=None):
+                     acc_div=1.0, plan=None, push_ptrs=None, x_rows=None):
     """push_ptrs: list of `world` raw pointers (entry [rank] ignored / None): every peer's copy of this rank's shard of Y,
-    written from the SpMM epilogue (the fused all-gather)."""
+    written from the SpMM epilogue (the fused all-gather).  x_rows: bitmap over the GLOBAL node ids (the column ids)."""
     pa = None
+    keep = []
     if push_ptrs is not None:
         FA = _p * MAX_WORLD
         pa = FA(*(list(push_ptrs) + [None] * (MAX_WORLD - len(push_ptrs))))
     check(load().wr_csr_spmm_sharded(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), n_local, D, ctypes.addressof(X),
                                      ptr(Y, F32), ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32),
-                                     acc_div, None if plan is None else plan.ref(),
+                                     acc_div, _plan_ref(plan, x_rows, keep),
                                      None if pa is None else ctypes.addressof(pa), stream_ptr()))
 
 

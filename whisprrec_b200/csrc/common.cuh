@@ -279,6 +279,7 @@ struct StageTabs {
     // rows already delivered by their owners (wr_xchg_*): batch entry b's row in role `which` is recv[where[3 b + which]]
     const float *recv;
     const int32_t *where;
+    uint32_t *touched;                   // nullable: bitmap over this rank's rows, set for rows reduced in place
     __device__ __forceinline__ const float *urow(int64_t u, int D) const { return shard_user_row(t, u, D); }
     __device__ __forceinline__ const float *irow(int64_t i, int D) const { return shard_item_row(t, i, D); }
     __device__ __forceinline__ const float *row(int64_t b, int which, int64_t id, int D) const {
@@ -291,6 +292,7 @@ struct StageTabs {
                                         int which) const {
         if ((int)owner == g.rank) {
             red_add_v4(g.base[owner] + local_row * D + off, v);
+            if (touched && off == 0) atomicOr(touched + (local_row >> 5), 1u << (local_row & 31));
             return;
         }
         const int64_t slot = (int64_t)g.rank * cap + 3 * b + which;

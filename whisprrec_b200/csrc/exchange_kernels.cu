@@ -167,6 +167,46 @@ __global__ void __launch_bounds__(256) embloss_owner_scatter_kernel(const float 
     }
 }
 
+// Sparse all-gather of a row-sharded table that is zero outside the rows of `node_bits` (bitmap over the GLOBAL node
+// ids; the pooled gradient of a batch): each owner stores just its marked rows into every peer's copy of its shard.
+// A warp looks at 32 local rows at a time; posted NVLink stores only.
+__global__ void __launch_bounds__(256) push_marked_rows_kernel(const float *__restrict__ X, wr_shards lay, int D,
+                                                                const uint32_t *__restrict__ node_bits, RecvPtrs dst,
+                                                                int n_dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t n_local = lay.rows_u_local + lay.rows_i_local;
+    const int D4 = D >> 2;
+    for (int64_t base = warp * 32; base < n_local; base += nwarps * 32) {
+        const int64_t lr = base + lane;
+        bool set = false;
+        if (lr < n_local) {
+            int64_t node;
+            bool valid;
+            if (lr < lay.rows_u_local) {
+                node = lr * lay.world + lay.rank;
+                valid = node < lay.n_users;
+            } else {
+                const int64_t it = (lr - lay.rows_u_local) * lay.world + lay.rank;
+                node = lay.n_users + it;
+                valid = it < lay.n_items;
+            }
+            set = valid && ((__ldg(node_bits + (node >> 5)) >> (node & 31)) & 1u);
+        }
+        uint32_t live = __ballot_sync(0xffffffffu, set);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            const int64_t off = (base + src) * D;
+            for (int v = lane; v < D4; v += 32) {
+                const float4 x = ldg4(X + off + 4 * v);
+                for (int g = 0; g < n_dst; ++g) *reinterpret_cast<float4 *>(dst.recv[g] + off + 4 * v) = x;
+            }
+        }
+    }
+}
+
 }  // namespace wr
 
 using namespace wr;
@@ -235,6 +275,29 @@ extern "C" int wr_embloss_owner_scatter(const float *T_local, float *G_local, in
     embloss_owner_scatter_kernel<<<8 * kSMs, 256, 0, (cudaStream_t)stream>>>(T_local, G_local, D, world, req_local, req_cnt_local,
                                                                             cap, reg_weight, 1.0f / (float)B_global,
                                                                             sumsq_global, loss_out);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_push_marked_rows(const wr_shards *host_X, int D, const uint32_t *node_bits,
+                                   float *const host_push[WR_MAX_WORLD], void *stream) {
+    if (!host_X || !node_bits || !host_push) return WR_E_NULL;
+    const int rc = wr_check_shards(host_X);
+    if (rc) return rc;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    RecvPtrs pr{};
+    int n = 0;
+    for (int g = 0; g < host_X->world; ++g) {
+        if (g == host_X->rank || !host_push[g]) continue;
+        if (!wr_aligned16(host_push[g])) return WR_E_ALIGN;
+        pr.recv[n++] = host_push[g];
+    }
+    if (n == 0) return WR_OK;
+    const int64_t n_local = host_X->rows_u_local + host_X->rows_i_local;
+    int64_t grid = (n_local + 255) / 256;
+    if (grid > 16 * kSMs) grid = 16 * kSMs;
+    if (grid < 1) grid = 1;
+    push_marked_rows_kernel<<<(int)grid, 256, 0, (cudaStream_t)stream>>>(host_X->base[host_X->rank], *host_X, D, node_bits, pr, n);
     WR_CHECK_LAUNCH();
     return WR_OK;
 }

@@ -47,7 +47,8 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParamsT<XACC> &p, int6
     // Tables far larger than L2 (power-law graphs at scale): the rows of the highest-degree nodes are re-read thousands
     // of times per pass, the rest a few dozen times with reuse distances of gigabytes.  plan.hot_bits marks the former;
     // they are loaded with an L2 evict_last policy (they stay), the index / weight streams with evict_first.
-    const uint32_t *hot_bits = p.plan.hot_bits;
+    const uint32_t *x_rows = p.plan.x_rows;
+    const uint32_t *hot_bits = x_rows ? nullptr : p.plan.hot_bits;
     uint64_t pol_keep = 0, pol_stream = 0;
     if (hot_bits) {
         asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
@@ -65,8 +66,11 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParamsT<XACC> &p, int6
             } else {
                 c = __ldg(p.col + base + lane);
                 w = __ldg(p.val + base + lane);
+                // sparse X (the pooled gradient of a batch): a row whose bit is clear is zero -- it is not fetched
+                if (x_rows && !((__ldg(x_rows + (c >> 5)) >> (c & 31)) & 1u)) c = -1;
             }
         }
+        if (x_rows && !__any_sync(0xffffffffu, lane < cnt && c >= 0)) continue;
         for (int j = 0; j < cnt; j += EPS * UNROLL) {
             float4 x[UNROLL][VPL];
             float ww[UNROLL];
@@ -89,8 +93,10 @@ __device__ __forceinline__ void spmm_accumulate(const SpmmParamsT<XACC> &p, int6
                         } else {
                             RG::load(row, sub, x[u]);
                         }
-                    } else {
+                    } else if (cc >= 0) {
                         RG::load(p.X.row(cc, D), sub, x[u]);
+                    } else {
+                        RG::zero(x[u]);
                     }
                 } else {
                     RG::zero(x[u]);
@@ -209,8 +215,11 @@ __global__ void __launch_bounds__(256) csr_spmm_generic_kernel(SpmmParamsT<XACC>
         const int64_t beg = p.rowptr[row], end = p.rowptr[row + 1];
         for (int v = lane; v < D4; v += 32) {
             float4 acc = f4_zero();
-            for (int64_t e = beg; e < end; ++e)
-                acc = fma4(__ldg(p.val + e), ldg4(p.X.row(__ldg(p.col + e), D) + 4 * v), acc);
+            for (int64_t e = beg; e < end; ++e) {
+                const int c = __ldg(p.col + e);
+                if (p.plan.x_rows && !((__ldg(p.plan.x_rows + (c >> 5)) >> (c & 31)) & 1u)) continue;
+                acc = fma4(__ldg(p.val + e), ldg4(p.X.row(c, D) + 4 * v), acc);
+            }
             spmm_row_epilogue(p, row * D + 4 * v, acc);
         }
     }
@@ -249,6 +258,7 @@ static int spmm_launch(SpmmParamsT<XACC> &p, int D, const wr_spmm_plan *host_pla
         p.plan = q;
     }
     if (host_plan && fast) p.plan.hot_bits = host_plan->hot_bits;
+    if (host_plan) p.plan.x_rows = host_plan->x_rows;
     int64_t g = (p.N + 7) / 8;
     if (g > 16 * kSMs) g = 16 * kSMs;
     p.row_blocks = (int)g;

@@ -306,6 +306,70 @@ __global__ void adam_tail_kernel(float *P, float *M, float *V, float *G, int64_t
     }
 }
 
+// The same sweep for a gradient that is zero outside a few rows (BPRMF: the 3 B rows of the batch): bit r of `touched`
+// says row r of G holds something.  Rows whose bit is clear are updated with g = 0 and their G row is neither read nor
+// rewritten: 24 B of traffic per parameter instead of 32.  `shift` = log2(D/4) when D/4 is a power of two, else -1.
+template <int UNROLL>
+__global__ void __launch_bounds__(256) adam_sweep_marked_kernel(float4 *__restrict__ P, float4 *__restrict__ M,
+                                                                 float4 *__restrict__ V, float4 *__restrict__ G,
+                                                                 int64_t n4, int D4, int shift,
+                                                                 const uint32_t *__restrict__ touched, AdamScalars s,
+                                                                 const float *dev_scalars) {
+    if (dev_scalars) {
+        s.step_size = __ldg(dev_scalars);
+        s.bc2_sqrt = __ldg(dev_scalars + 1);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 z = f4_zero();
+    for (; i < n4; i += UNROLL * stride) {
+        float4 p[UNROLL], m[UNROLL], v[UNROLL], g[UNROLL];
+        bool hit[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t e = i + u * stride;
+            hit[u] = false;
+            if (e < n4) {
+                const int64_t row = shift >= 0 ? (e >> shift) : (e / D4);
+                hit[u] = (__ldg(touched + (row >> 5)) >> (row & 31)) & 1u;
+                p[u] = P[e];
+                m[u] = M[e];
+                v[u] = V[e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) g[u] = hit[u] ? G[i + u * stride] : z;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t e = i + u * stride;
+            if (e < n4) {
+                adam_elem(p[u].x, m[u].x, v[u].x, g[u].x, s);
+                adam_elem(p[u].y, m[u].y, v[u].y, g[u].y, s);
+                adam_elem(p[u].z, m[u].z, v[u].z, g[u].z, s);
+                adam_elem(p[u].w, m[u].w, v[u].w, g[u].w, s);
+                P[e] = p[u];
+                M[e] = m[u];
+                V[e] = v[u];
+                if (hit[u]) G[e] = z;
+            }
+        }
+    }
+}
+
+// Bits of the rows a batch touches, in the concatenated [users; items] numbering (out-of-range ids are the gradient
+// kernel's to report).
+__global__ void __launch_bounds__(256) mark_rows_kernel(const int64_t *user, const int64_t *pos, const int64_t *neg,
+                                                         int64_t B, int64_t n_users, int64_t n_items, uint32_t *touched) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int64_t u = user[b], i = pos[b], j = neg[b];
+    if ((uint64_t)u >= (uint64_t)n_users || (uint64_t)i >= (uint64_t)n_items || (uint64_t)j >= (uint64_t)n_items) return;
+    const int64_t r1 = n_users + i, r2 = n_users + j;
+    atomicOr(touched + (u >> 5), 1u << (u & 31));
+    atomicOr(touched + (r1 >> 5), 1u << (r1 & 31));
+    atomicOr(touched + (r2 >> 5), 1u << (r2 & 31));
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Row movement for row-sharded tables.
 // ------------------------------------------------------------------------------------------------------
@@ -689,7 +753,7 @@ extern "C" int wr_embloss_fwd_bwd(const float *U0, const float *I0, const int64_
 // Reduce this rank's inbox into its gradient shard: for every sender s and slot j, idx = inbox_idx[s][j] (0 = empty),
 // G[idx - 1] += inbox_rows[s][j]; the slot is cleared for the next step.  One warp per slot, lanes over the row.
 __global__ void __launch_bounds__(256) inbox_scatter_kernel(float *G, const float *__restrict__ rows, int32_t *idx,
-                                                             int64_t n_slots, int D) {
+                                                             int64_t n_slots, int D, uint32_t *touched) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -705,6 +769,7 @@ __global__ void __launch_bounds__(256) inbox_scatter_kernel(float *G, const floa
             live &= live - 1;
             const int64_t row = (int64_t)__shfl_sync(0xffffffffu, mine, src) - 1;
             const float *r = rows + (base + src) * D;
+            if (touched && lane == 0) atomicOr(touched + (row >> 5), 1u << (row & 31));
             for (int v = lane; v < D4; v += 32) red_add_v4(G + row * D + 4 * v, ldg4(r + 4 * v));
         }
     }
@@ -724,7 +789,7 @@ extern "C" int wr_bpr_fwd_bwd_sharded_staged(const wr_shards *host_T, const wr_s
     if (rc) return rc;
     if (B <= 0 || B_global < B || cap < 3 * B) return WR_E_SIZE;
     if (!(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return WR_E_DIM;
-    BprParamsT<StageTabs> p{{*host_T, *host_Gd, {}, {}, cap, nullptr, nullptr}, user, pos, neg, B, host_T->n_users, host_T->n_items,
+    BprParamsT<StageTabs> p{{*host_T, *host_Gd, {}, {}, cap, nullptr, nullptr, nullptr}, user, pos, neg, B, host_T->n_users, host_T->n_items,
                             gamma, grad_scale / (float)B_global, (float)B_global, loss_out, 0, (WrWorkspace *)ws};
     for (int g = 0; g < host_T->world; ++g) {
         if (!host_inbox_rows[g] || !host_inbox_idx[g]) return WR_E_NULL;
@@ -741,7 +806,8 @@ extern "C" int wr_bpr_fwd_bwd_exchanged(const float *recv, const int32_t *where,
                                         float *const host_inbox_rows[WR_MAX_WORLD],
                                         int32_t *const host_inbox_idx[WR_MAX_WORLD], int64_t cap, const int64_t *user,
                                         const int64_t *pos, const int64_t *neg, int64_t B, int64_t B_global, int D,
-                                        float gamma, float grad_scale, float *loss_out, void *ws, void *stream) {
+                                        float gamma, float grad_scale, uint32_t *touched, float *loss_out, void *ws,
+                                        void *stream) {
     if (!recv || !where || !host_Gd || !host_inbox_rows || !host_inbox_idx || !user || !pos || !neg || !loss_out || !ws)
         return WR_E_NULL;
     const int rc = wr_check_shards(host_Gd);
@@ -749,7 +815,7 @@ extern "C" int wr_bpr_fwd_bwd_exchanged(const float *recv, const int32_t *where,
     if (B <= 0 || B_global < B || cap < 3 * B) return WR_E_SIZE;
     if (!(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return WR_E_DIM;
     if (!wr_aligned16(recv)) return WR_E_ALIGN;
-    BprParamsT<StageTabs> p{{*host_Gd, *host_Gd, {}, {}, cap, recv, where}, user, pos, neg, B, host_Gd->n_users,
+    BprParamsT<StageTabs> p{{*host_Gd, *host_Gd, {}, {}, cap, recv, where, touched}, user, pos, neg, B, host_Gd->n_users,
                             host_Gd->n_items, gamma, grad_scale / (float)B_global, (float)B_global, loss_out, 0,
                             (WrWorkspace *)ws};
     for (int g = 0; g < host_Gd->world; ++g) {
@@ -763,6 +829,11 @@ extern "C" int wr_bpr_fwd_bwd_exchanged(const float *recv, const int32_t *where,
 
 extern "C" int wr_inbox_scatter(float *G, const float *inbox_rows, int32_t *inbox_idx, int world, int64_t cap, int D,
                                 void *stream) {
+    return wr_inbox_scatter_marked(G, inbox_rows, inbox_idx, world, cap, D, nullptr, stream);
+}
+
+extern "C" int wr_inbox_scatter_marked(float *G, const float *inbox_rows, int32_t *inbox_idx, int world, int64_t cap,
+                                       int D, uint32_t *touched, void *stream) {
     if (!G || !inbox_rows || !inbox_idx) return WR_E_NULL;
     if (world < 1 || world > WR_MAX_WORLD || cap <= 0) return WR_E_SIZE;
     if (D <= 0 || (D & 3)) return WR_E_DIM;
@@ -770,7 +841,7 @@ extern "C" int wr_inbox_scatter(float *G, const float *inbox_rows, int32_t *inbo
     const int64_t n_slots = (int64_t)world * cap;
     int64_t g = (n_slots + 255) / 256;
     if (g > 16 * kSMs) g = 16 * kSMs;
-    inbox_scatter_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(G, inbox_rows, inbox_idx, n_slots, D);
+    inbox_scatter_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(G, inbox_rows, inbox_idx, n_slots, D, touched);
     WR_CHECK_LAUNCH();
     return WR_OK;
 }
@@ -840,6 +911,46 @@ extern "C" int wr_adam_l2_sweep(float *P, float *M, float *V, float *G, int64_t 
     return WR_OK;
 }
 
+extern "C" int wr_mark_rows(const int64_t *user, const int64_t *pos, const int64_t *neg, int64_t B, int64_t n_users,
+                            int64_t n_items, uint32_t *touched, void *stream) {
+    if (!user || !pos || !neg || !touched) return WR_E_NULL;
+    if (B <= 0 || n_users <= 0 || n_items <= 0) return WR_E_SIZE;
+    mark_rows_kernel<<<(int)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(user, pos, neg, B, n_users, n_items, touched);
+    WR_CHECK_LAUNCH();
+    return WR_OK;
+}
+
+extern "C" int wr_adam_l2_sweep_marked(float *P, float *M, float *V, float *G, int64_t n_rows, int D, uint32_t *touched,
+                                       float l2, double beta1, double beta2, float eps, float step_size, float bc2_sqrt,
+                                       const float *dev_scalars, void *stream) {
+    if (!P || !M || !V || !G || !touched) return WR_E_NULL;
+    if (n_rows <= 0) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
+    AdamScalars s{l2, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), eps, step_size, bc2_sqrt};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D4 = D >> 2;
+    int shift = -1;
+    if ((D4 & (D4 - 1)) == 0) {
+        shift = 0;
+        while ((1 << shift) < D4) ++shift;
+    }
+    const int64_t n4 = n_rows * D4;
+    if (n4 >= (int64_t)8 * kSMs * 256 * 4) {
+        const int grid = grid_for(n4, 256 * 4, 8 * kSMs);
+        adam_sweep_marked_kernel<4><<<grid, 256, 0, st>>>((float4 *)P, (float4 *)M, (float4 *)V, (float4 *)G, n4, D4, shift,
+                                                           touched, s, dev_scalars);
+    } else {
+        const int grid = grid_for(n4, 256, 8 * kSMs);
+        adam_sweep_marked_kernel<1><<<grid, 256, 0, st>>>((float4 *)P, (float4 *)M, (float4 *)V, (float4 *)G, n4, D4, shift,
+                                                           touched, s, dev_scalars);
+    }
+    WR_CHECK_LAUNCH();
+    // every bit goes back to zero behind the sweep (stream order): the next step's markers start from a clean map
+    const cudaError_t e = cudaMemsetAsync(touched, 0, (size_t)((n_rows + 31) / 32) * sizeof(uint32_t), st);
+    return e == cudaSuccess ? WR_OK : (int)e;
+}
+
 // Largest grid of bprmf_step_kernel<...> that is resident at once on the current device (cached per instantiation).
 template <int LPR, int VPL, class TABS>
 static int step_max_grid(int *out) {
@@ -902,6 +1013,32 @@ extern "C" int wr_bprmf_step(float *P, float *M, float *V, float *G, const int64
     if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
     return wr_bprmf_step_impl(P, M, V, G, user, pos, neg, B, D, n_users, n_items, gamma, l2, beta1, beta2, eps, step_size,
                               bc2_sqrt, dev_scalars, loss_out, ws, stream);
+}
+
+// wr_bprmf_step with a row map for the streaming (two-kernel) path: the batch's rows are marked, the gradient kernel
+// accumulates into them and the sweep reads G only where a bit is set.  Cache-sized tables take the single launch and
+// leave the map alone.  Results are those of wr_bprmf_step bit for bit (a skipped G row held zeros).
+extern "C" int wr_bprmf_step_marked(float *P, float *M, float *V, float *G, uint32_t *touched, const int64_t *user,
+                                    const int64_t *pos, const int64_t *neg, int64_t B, int D, int64_t n_users,
+                                    int64_t n_items, float gamma, float l2, double beta1, double beta2, float eps,
+                                    float step_size, float bc2_sqrt, const float *dev_scalars, float *loss_out, void *ws,
+                                    void *stream) {
+    if (!P || !M || !V || !G || !touched || !user || !pos || !neg || !loss_out || !ws) return WR_E_NULL;
+    if (B <= 0 || n_users <= 0 || n_items <= 0 || n_users >= INT32_MAX || n_items >= INT32_MAX) return WR_E_SIZE;
+    if (D <= 0 || (D & 3)) return WR_E_DIM;
+    if (!wr_aligned16(P) || !wr_aligned16(M) || !wr_aligned16(V) || !wr_aligned16(G)) return WR_E_ALIGN;
+    const int64_t n_elems = (n_users + n_items) * D;
+    const bool fused_shape = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
+    if (fused_shape && n_elems <= WR_FUSED_STEP_MAX_ELEMS)
+        return wr_bprmf_step_impl(P, M, V, G, user, pos, neg, B, D, n_users, n_items, gamma, l2, beta1, beta2, eps,
+                                  step_size, bc2_sqrt, dev_scalars, loss_out, ws, stream);
+    int rc = wr_mark_rows(user, pos, neg, B, n_users, n_items, touched, stream);
+    if (rc) return rc;
+    rc = wr_bpr_fwd_bwd(P, P + n_users * D, user, pos, neg, B, D, n_users, n_items, gamma, 1.0f, G, G + n_users * D,
+                        loss_out, 0, ws, stream);
+    if (rc) return rc;
+    return wr_adam_l2_sweep_marked(P, M, V, G, n_users + n_items, D, touched, l2, beta1, beta2, eps, step_size, bc2_sqrt,
+                                   dev_scalars, stream);
 }
 
 // The per-step launches: one cooperative launch (parameter loads first, BPR, grid barrier, Adam) for tables of up to

@@ -70,9 +70,11 @@ class BPRMF(GeneralModel):
         opt = self.optimizer
         out = t.loss if loss_out is None else loss_out
         opt.step_count += 1
+        if t.P.numel() > _lib.FUSED_STEP_MAX_ELEMS and getattr(t, 'touched', None) is None:
+            t.touched = _lib.row_map(t.P.shape[0], t.P.device)      # streaming path: skip untouched gradient rows
         _lib.bprmf_step(t.P, t.M, t.V, t.G, feed_dict['user_id'], feed_dict['pos_item'], feed_dict['neg_items'],
                         t.n_users, opt.step_count, opt.lr, opt.weight_decay, out, t.ws, beta1=opt.betas[0],
-                        beta2=opt.betas[1], eps=opt.eps)
+                        beta2=opt.betas[1], eps=opt.eps, touched=getattr(t, 'touched', None))
         return out[0].detach().as_subclass(_base.FusedLoss)
 
     def train_epoch(self, ids, batch_size, losses):

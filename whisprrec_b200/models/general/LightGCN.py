@@ -78,6 +78,7 @@ class PropagationEngine(object):
         self.pool = torch.empty_like(t.P)            # mean_k E^k
         self.layer = [torch.empty_like(t.P), torch.empty_like(t.P)]
         self.pool_grad = torch.zeros_like(t.P)       # dL/d(pool); re-zeroed by the last backward SpMM
+        self.x_rows = _lib.row_map(t.P.shape[0], t.P.device)        # rows of pool_grad a batch touches (large graphs)
 
     def propagate(self):
         """LightGCN.py:134-148: L SpMMs with the running layer sum (and the final /(L+1)) in their epilogue."""
@@ -106,13 +107,20 @@ class PropagationEngine(object):
                              t.ws, grad_scale=1.0 / (L + 1))
             # pool = 1/(L+1) sum_k A^k E0 with A symmetric  =>  dE0 = H_0,  H_L = g,  H_{k-1} = g + A H_k
             h = g
+            # g is zero outside the batch's <= 3 B rows: when those are a small part of the table the first adjoint
+            # propagation fetches only them (wr_spmm_plan.x_rows) -- on a graph far beyond L2 that is most of its traffic
+            sparse = 12 * user.numel() <= t.P.shape[0]
+            if sparse:
+                _lib.mark_rows(user, pos, neg, t.n_users, t.P.shape[0] - t.n_users, self.x_rows)
             for k in range(1, L + 1):
                 last = k == L
                 y = t.G if last else self.layer[(k - 1) & 1]
                 # the fused re-zeroing of g is only safe when g is not also the SpMM input (L >= 2)
                 _lib.csr_spmm(self.rowptr, self.col, self.val, h, Y=y, add=g, zero_add=last and L > 1,
-                              plan=self.plan)
+                              plan=self.plan, x_rows=self.x_rows if sparse and k == 1 else None)
                 h = y
+            if sparse:
+                self.x_rows.zero_()
             if L == 1:
                 g.zero_()
         _lib.embloss_fwd_bwd(t.users(t.P), t.items(t.P), user, pos, neg, t.users(t.G), t.items(t.G), out, t.ws,

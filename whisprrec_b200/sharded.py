@@ -281,9 +281,19 @@ class ShardedTables(object):
         lay = self.layout
         return t[lay.rows_u_local:lay.rows_u_local + len(lay.local_items())]
 
-    def adam(self, lr, l2, betas=(0.9, 0.999), eps=1e-8):
+    def adam(self, lr, l2, betas=(0.9, 0.999), eps=1e-8, touched=None):
         self.step_count += 1
+        if touched is not None:
+            _lib.adam_l2_sweep_marked(self.P, self.M, self.V, self.G, touched, self.step_count, lr, l2, betas[0],
+                                      betas[1], eps)
+            return
         _lib.adam_l2_sweep(self.P, self.M, self.V, self.G, self.step_count, lr, l2, betas[0], betas[1], eps)
+
+    def row_map(self):
+        """Bitmap over this rank's rows for the row-marked sweep (wr_inbox_scatter_marked sets, the sweep clears)."""
+        if getattr(self, '_row_map', None) is None:
+            self._row_map = _lib.row_map(self.layout.n_local, self.peers.device)
+        return self._row_map
 
 
 def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
@@ -314,11 +324,14 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
         inbox = tabs.inbox(B_global)
         x = tabs.exchange(B_global)
         tabs.fetch_rows(x, tabs.P, user, pos, neg)
+        # rows reduced in place (entries this rank owns) and rows that arrive through the inbox both mark the row map:
+        # those are the only rows of G the sweep has to read and re-zero
+        touched = tabs.row_map()
         _lib.bpr_fwd_bwd_exchanged(x['recv'], x['where'], tabs.Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'],
-                                   user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
+                                   user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws, touched=touched)
         loss = tabs.peers.barrier(tabs.loss_part[:1])
-        _lib.inbox_scatter(tabs.G, inbox['rows'], inbox['idx'], tabs.layout.world, inbox['cap'])
-        tabs.adam(lr, l2)
+        _lib.inbox_scatter(tabs.G, inbox['rows'], inbox['idx'], tabs.layout.world, inbox['cap'], touched)
+        tabs.adam(lr, l2, touched=touched)
         tabs.peers.barrier()
         return loss
     _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
@@ -371,6 +384,7 @@ class ShardedLightGCN(object):
                 buf, ptrs = tabs.peers.alloc((lay.world, lay.n_local, tabs.D))
                 self.gathered.append(buf)
                 self.gathered_ptrs.append(ptrs)
+        self.sparse_grad = None       # None: the batch decides (_step_exchanged); True / False force it
         self._cur = 0                 # which copy holds (or receives by all-gather) the next SpMM's input
         self._pushed = None           # base pointer of the shard whose rows the last SpMM pushed into gathered[_cur]
         self._local_views = {}
@@ -462,8 +476,22 @@ def _step_exchanged(self, user, pos, neg, B_global, lr, l2):
     """The rest of ShardedLightGCN.step for large batches (after propagate): pooled rows delivered by their owners,
     EmbLoss computed by the owners of the ego rows from the request lists -- no loads from peer memory, no remote REDs."""
     t, L = self.tabs, self.L
-    world = t.layout.world
+    lay = t.layout
+    world = lay.world
     x, inbox = t.exchange(B_global), t.inbox(B_global)
+    # The pooled gradient is zero outside the batch's <= 3 B_global rows.  When those are a small part of the table the
+    # first adjoint propagation needs neither the other rows (its SpMM skips them: wr_spmm_plan.x_rows) nor their
+    # all-gather: the owners push just the marked rows.  The map is over GLOBAL node ids: every rank marks its slice,
+    # the maps are OR-ed (1 bit per node: 1.5 MB for 12 M nodes).
+    sparse = self.gather_first and (12 * int(B_global) <= lay.n_users + lay.n_items if self.sparse_grad is None
+                                    else bool(self.sparse_grad))
+    if sparse:
+        gm = self._node_map()
+        _lib.mark_rows(user, pos, neg, lay.n_users, lay.n_items, gm)
+        t.peers.dist.all_gather_into_tensor(self._node_maps, gm, group=t.peers.group)
+        for g in range(world):
+            if g != lay.rank:
+                gm.bitwise_or_(self._node_maps[g])
     t.fetch_rows(x, self.pool, user, pos, neg)
     _lib.bpr_fwd_bwd_exchanged(x['recv'], x['where'], self.pool_Gd, inbox['row_ptrs'], inbox['idx_ptrs'], inbox['cap'],
                                user, pos, neg, B_global, t.D, t.loss_part, t.ws, grad_scale=1.0 / (L + 1))
@@ -472,13 +500,22 @@ def _step_exchanged(self, user, pos, neg, B_global, lr, l2):
     t.loss.copy_(sums[:1])
     self.sumsq[:3].copy_(sums[1:4])
     _lib.inbox_scatter(self.pool_grad, inbox['rows'], inbox['idx'], world, inbox['cap'])
-    t.peers.barrier()                            # every rank's pooled gradient is complete before its peers pull it
+    if sparse:
+        step = self.gathered[0][0].numel() * 4
+        cur = self._cur
+        _lib.push_marked_rows(self.pool_Gd, t.D, gm, [None if g == lay.rank else self.gathered_ptrs[cur][g] + lay.rank * step
+                                                       for g in range(world)])
+        self._pushed = self.pool_Gd.base[lay.rank]       # the SpMM below finds its input delivered
+    t.peers.barrier()                            # every rank's pooled gradient is complete (and, pushed, has landed)
     h = self.pool_Gd
     for k in range(1, L + 1):
         last = k == L
         y, ys = (t.G, t.Gd) if last else self.layer[(k - 1) & 1]
-        self._spmm(h, push=not last, Y=y, add=self.pool_grad, zero_add=last and L > 1)
+        self._spmm(h, push=not last, Y=y, add=self.pool_grad, zero_add=last and L > 1,
+                   x_rows=gm if sparse and k == 1 else None)
         h = ys
+    if sparse:
+        gm.zero_()
     if L == 1:
         self.pool_grad.zero_()
     _lib.embloss_owner_scatter(t.P, t.G, world, x['req'], x['cnt'], x['cap'], self.reg_weight, B_global, self.sumsq, t.loss)
@@ -487,6 +524,15 @@ def _step_exchanged(self, user, pos, neg, B_global, lr, l2):
     return t.loss
 
 
+def _node_map(self):
+    if getattr(self, '_gm', None) is None:
+        lay = self.tabs.layout
+        self._gm = _lib.row_map(lay.n_users + lay.n_items, self.tabs.peers.device)
+        self._node_maps = torch.zeros((lay.world, self._gm.numel()), dtype=torch.int32, device=self.tabs.peers.device)
+    return self._gm
+
+
+ShardedLightGCN._node_map = _node_map
 ShardedLightGCN._step_exchanged = _step_exchanged
 
 
