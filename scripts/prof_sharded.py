@@ -85,7 +85,8 @@ if what in ('both', 'bprmf'):
         return w
     WRAPPED = ('allgather_shards', 'csr_spmm_sharded', 'bpr_fwd_bwd_sharded', 'bpr_fwd_bwd_sharded_staged', 'inbox_scatter',
                'embloss_sumsq_sharded', 'embloss_scatter_sharded', 'adam_l2_sweep', 'peer_barrier', 'xchg_request', 'xchg_serve',
-               'bpr_fwd_bwd_exchanged', 'embloss_owner_sumsq', 'embloss_owner_scatter')
+               'bpr_fwd_bwd_exchanged', 'embloss_owner_sumsq', 'embloss_owner_scatter', 'csr_spmm_sharded_dma', 'push_shard_dma',
+               'push_marked_rows', 'adam_l2_sweep_marked', 'mark_rows')
     for name in WRAPPED:
         setattr(_lib, name, timed(name, getattr(_lib, name)))
 
@@ -171,7 +172,8 @@ if what in ('both', 'lightgcn'):
             return w
         for name in ('allgather_shards', 'csr_spmm_sharded', 'bpr_fwd_bwd_sharded', 'bpr_fwd_bwd_sharded_staged', 'inbox_scatter',
                      'embloss_sumsq_sharded', 'embloss_scatter_sharded', 'adam_l2_sweep', 'peer_barrier', 'xchg_request',
-                     'xchg_serve', 'bpr_fwd_bwd_exchanged', 'embloss_owner_sumsq', 'embloss_owner_scatter'):
+                     'xchg_serve', 'bpr_fwd_bwd_exchanged', 'embloss_owner_sumsq', 'embloss_owner_scatter', 'csr_spmm_sharded_dma',
+                     'push_shard_dma', 'push_marked_rows', 'adam_l2_sweep_marked', 'mark_rows'):
             setattr(_lib, name, timed(name, getattr(_lib, name)))
 
     def lg_phases():

@@ -76,6 +76,9 @@ SIGNATURES = {
     'wr_embloss_owner_sumsq': (_int, [_p, _int, _int, _p, _p, _i64, _p, _p, _p]),
     'wr_embloss_owner_scatter': (_int, [_p, _p, _int, _int, _p, _p, _i64, _f32, _i64, _p, _p, _p]),
     'wr_inbox_scatter': (_int, [_p, _p, _p, _int, _i64, _int, _p]),
+    'wr_csr_spmm_sharded_dma': (_int, [_p, _p, _p, _i64, _int, _p, _p, _p, _int, _p, _p, _f32, _p, _p, _p, _i64, _i64,
+                                       _c.c_uint32, _i64, _p, _p]),
+    'wr_push_shard_dma': (_int, [_p, _i64, _int, _int, _p, _p]),
     'wr_push_marked_rows': (_int, [_p, _int, _p, _p, _p]),
     'wr_inbox_scatter_marked': (_int, [_p, _p, _p, _int, _i64, _int, _p, _p]),
     'wr_mark_rows': (_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p]),
@@ -809,6 +812,22 @@ def csr_spmm_sharded(rowptr, col, val, n_local, D, X, Y=None, add=None, zero_add
                                      ptr(Y, F32), ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32),
                                      acc_div, _plan_ref(plan, x_rows, keep),
                                      None if pa is None else ctypes.addressof(pa), stream_ptr()))
+
+
+def csr_spmm_sharded_dma(rowptr, col, val, n_local, D, X, Y, push_ptrs, progress, block_rows, epoch, side_stream, nnz=0,
+                         add=None, zero_add=False, acc_in=None, acc_out=None, acc_div=1.0, plan=None, x_rows=None):
+    """csr_spmm_sharded with the all-gather of Y done by the copy engines on `side_stream` while the kernel runs."""
+    pa = _ptr_array(push_ptrs, X.world)
+    keep = []
+    check(load().wr_csr_spmm_sharded_dma(ptr(rowptr, I64), ptr(col, I32), ptr(val, F32), n_local, D, ctypes.addressof(X),
+                                         ptr(Y, F32), ptr(add, F32), int(zero_add), ptr(acc_in, F32), ptr(acc_out, F32),
+                                         acc_div, _plan_ref(plan, x_rows, keep), ctypes.addressof(pa), ptr(progress, I32),
+                                         progress.numel(), block_rows, epoch, nnz, side_stream.cuda_stream, stream_ptr()))
+
+
+def push_shard_dma(src, world, rank, push_ptrs):
+    pa = _ptr_array(push_ptrs, world)
+    check(load().wr_push_shard_dma(ptr(src, F32), src.numel(), world, rank, ctypes.addressof(pa), stream_ptr()))
 
 
 def rowdot(A, B, round_bf16=False):

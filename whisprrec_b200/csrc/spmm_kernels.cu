@@ -29,11 +29,24 @@ struct SpmmParamsT {
     float *acc_out;
     float acc_div;
     wr_spmm_plan plan;       // by value; long_threshold = INT64_MAX when there is no plan
-    int row_blocks;          // CTAs [0, row_blocks) walk rows, the rest walk the chunks of split rows
+    int row_blocks;          // CTAs [0, row_blocks) walk rows, the next chunk_blocks walk the chunks of split rows
+    int chunk_blocks;
+    // copy-engine push (wr_csr_spmm_sharded_dma): blocks of rows have to complete in a steady stream from the start of the
+    // kernel, so the two kinds of CTA are interleaved in launch order in proportion to their work (both then sweep the
+    // row range for the whole duration) and the row walk starts at row_rot (the item rows: their split rows are the last
+    // the chunk walk reaches, so their short rows go first)
+    int interleave;
+    int64_t row_rot;
     // fused all-gather of the output (multi-GPU): every finished row of Y is also stored into each peer's copy of this
     // rank's shard (posted NVLink writes behind the arithmetic), so the next layer starts without a gather pass
     float *push[WR_MAX_WORLD];
     int n_push;
+    // progress words for a copy-engine push beside the kernel (wr_csr_spmm_sharded_dma): rows are counted per block of
+    // 2^prog_shift rows; whoever finishes a block's last row publishes prog_flag[block] = prog_epoch
+    int32_t *prog_count;
+    uint32_t *prog_flag;
+    int prog_shift;
+    uint32_t prog_epoch;
 };
 using SpmmParams = SpmmParamsT<LocalX>;
 
@@ -141,6 +154,20 @@ __device__ __forceinline__ void spmm_row_epilogue(const SpmmParamsT<XACC> &p, in
     }
 }
 
+// Lane 0, after __syncwarp(): row `row` of Y is complete (all lanes' stores happen-before through the warp barrier).
+template <class XACC>
+__device__ __forceinline__ void spmm_row_done(const SpmmParamsT<XACC> &p, int64_t row) {
+    const int64_t k = row >> p.prog_shift;
+    const int64_t first = k << p.prog_shift;
+    const int rows_here = (int)min((int64_t)1 << p.prog_shift, p.N - first);
+    __threadfence();
+    if (atomicAdd(p.prog_count + k, 1) == rows_here - 1) {
+        p.prog_count[k] = 0;                   // ready for the next call
+        __threadfence_system();                // the block's rows, observed through the counter, before the flag
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.prog_flag + k), "r"(p.prog_epoch) : "memory");
+    }
+}
+
 // A warp owns a row (or, for rows longer than plan.long_threshold, one <= chunk-sized slice of it).  The row of
 // D = 4*LPR*VPL floats is covered by LPR lanes, so 32/LPR neighbour rows are fetched per step (one 128-bit load per
 // lane each), UNROLL steps in flight.  Column ids / weights are read 32 at a time, coalesced, and handed round
@@ -151,10 +178,21 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParamsT<XACC> p) {
     using RG = RowGroup<LPR, VPL>;
     constexpr int D = RG::D;
     const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-    if ((int)blockIdx.x < p.row_blocks) {
-        const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    bool is_chunk = (int)blockIdx.x >= p.row_blocks;
+    int kind_idx = is_chunk ? (int)blockIdx.x - p.row_blocks : (int)blockIdx.x;
+    if (p.interleave) {
+        const int64_t total = p.row_blocks + p.chunk_blocks;
+        const int c0 = (int)((int64_t)blockIdx.x * p.chunk_blocks / total);
+        const int c1 = (int)(((int64_t)blockIdx.x + 1) * p.chunk_blocks / total);
+        is_chunk = c1 > c0;
+        kind_idx = is_chunk ? c0 : (int)blockIdx.x - c0;
+    }
+    if (!is_chunk) {
+        const int64_t warp = (int64_t)kind_idx * (blockDim.x >> 5) + (threadIdx.x >> 5);
         const int64_t nwarps = (int64_t)p.row_blocks * (blockDim.x >> 5);
-        for (int64_t row = warp; row < p.N; row += nwarps) {
+        for (int64_t it = warp; it < p.N; it += nwarps) {
+            int64_t row = it + p.row_rot;
+            if (row >= p.N) row -= p.N;
             const int64_t beg = __ldg(p.rowptr + row), end = __ldg(p.rowptr + row + 1);
             if (end - beg > p.plan.long_threshold) continue;      // split rows are handled below
             float4 acc[VPL];
@@ -164,10 +202,14 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParamsT<XACC> p) {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) spmm_row_epilogue(p, row * D + 4 * (sub + v * LPR), acc[v]);
             }
+            if (p.prog_count) {
+                __syncwarp();
+                if (lane == 0) spmm_row_done(p, row);
+            }
         }
     } else {
-        const int64_t warp = (int64_t)(blockIdx.x - p.row_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-        const int64_t nwarps = (int64_t)(gridDim.x - p.row_blocks) * (blockDim.x >> 5);
+        const int64_t warp = (int64_t)kind_idx * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        const int64_t nwarps = (int64_t)p.chunk_blocks * (blockDim.x >> 5);
         for (int64_t ch = warp; ch < p.plan.n_chunks; ch += nwarps) {
             const int64_t beg = __ldg(p.plan.chunk_beg + ch);
             const int64_t end = beg + __ldg(p.plan.chunk_len + ch);
@@ -199,6 +241,10 @@ __global__ void __launch_bounds__(256) csr_spmm_kernel(SpmmParamsT<XACC> p) {
                     }
                 }
                 if (lane == 0) p.plan.slot_arrivals[slot] = 0;
+                if (p.prog_count) {
+                    __syncwarp();
+                    if (lane == 0) spmm_row_done(p, row);
+                }
             }
         }
     }
@@ -244,8 +290,33 @@ __global__ void __launch_bounds__(256) csr_norm_weights_kernel(const int64_t *__
 
 using namespace wr;
 
+// CTAs of csr_spmm_kernel<...> that are resident at once on the current device (cached per instantiation).
+template <int LPR, int VPL, int UNROLL, class XACC>
+static int spmm_resident_ctas() {
+    static int cached = 0;
+    if (!cached) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_kernel<LPR, VPL, UNROLL, XACC>, 256, 0) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 4;
+        cached = per_sm * kSMs;
+    }
+    return cached;
+}
+
 template <class XACC>
-static int spmm_launch(SpmmParamsT<XACC> &p, int D, const wr_spmm_plan *host_plan, cudaStream_t st) {
+static int spmm_resident_for(int D) {
+    switch (D) {
+        case 16: return spmm_resident_ctas<4, 1, 2, XACC>();
+        case 32: return spmm_resident_ctas<8, 1, 2, XACC>();
+        case 64: return spmm_resident_ctas<16, 1, 8, XACC>();
+        case 128: return spmm_resident_ctas<32, 1, 4, XACC>();
+        default: return spmm_resident_ctas<32, 2, 2, XACC>();
+    }
+}
+
+template <class XACC>
+static int spmm_launch(SpmmParamsT<XACC> &p, int D, const wr_spmm_plan *host_plan, cudaStream_t st, int64_t nnz_hint = 0) {
     p.plan = wr_spmm_plan{};
     p.plan.long_threshold = INT64_MAX;
     const bool fast = D == 16 || D == 32 || D == 64 || D == 128 || D == 256;
@@ -264,6 +335,24 @@ static int spmm_launch(SpmmParamsT<XACC> &p, int D, const wr_spmm_plan *host_pla
     p.row_blocks = (int)g;
     int64_t gc = (p.plan.n_chunks + 7) / 8;
     if (gc > 16 * kSMs) gc = 16 * kSMs;
+    if (p.interleave) {
+        // Exactly the CTAs that are resident at once (a second wave would sweep the row range again after the first has
+        // finished it: no block of rows would be complete before the end), split in proportion to the edges each kind
+        // walks (slices average ~7/8 of the 128-edge limit)
+        const int64_t total = spmm_resident_for<XACC>(D);
+        double share = p.plan.n_chunks > 0 ? (nnz_hint > 0 ? (double)p.plan.n_chunks * 112.0 / (double)nnz_hint : 0.5) : 0.0;
+        share = share < 0.02 ? 0.02 : (share > 0.9 ? 0.9 : share);
+        int64_t c = (int64_t)(share * total + 0.5);
+        if (c > (p.plan.n_chunks + 7) / 8) c = (p.plan.n_chunks + 7) / 8;
+        if (c < 1 && p.plan.n_chunks > 0) c = 1;
+        int64_t r = total - c;
+        if (r > (p.N + 7) / 8) r = (p.N + 7) / 8;
+        if (r < 1) r = 1;
+        g = r;
+        gc = c;
+    }
+    p.row_blocks = (int)g;
+    p.chunk_blocks = (int)gc;
     const int grid = (int)(g + gc);
     switch (D) {
         case 16: csr_spmm_kernel<4, 1, 2, XACC><<<grid, 256, 0, st>>>(p); break;
@@ -298,7 +387,7 @@ extern "C" int wr_csr_spmm(const int64_t *rowptr, const int32_t *col, const floa
     if (rc) return rc;
     if (!wr_aligned16(X)) return WR_E_ALIGN;
     if (X == Y || X == acc_out) return WR_E_SIZE;
-    SpmmParams p{rowptr, col, val, N, {X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, {}, 0};
+    SpmmParams p{rowptr, col, val, N, {X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, 0, 0, 0, {}, 0, nullptr, nullptr, 0, 0};
     return spmm_launch(p, D, host_plan, (cudaStream_t)stream);
 }
 
@@ -313,7 +402,8 @@ extern "C" int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, co
     if (rc) return rc;
     if (n_local != host_X->rows_u_local + host_X->rows_i_local) return WR_E_SIZE;
     if (host_X->base[host_X->rank] == Y || host_X->base[host_X->rank] == acc_out) return WR_E_SIZE;
-    SpmmParamsT<ShardX> p{rowptr, col, val, n_local, {*host_X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, {}, 0};
+    SpmmParamsT<ShardX> p{rowptr, col, val, n_local, {*host_X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, 0, 0, 0, {}, 0,
+                          nullptr, nullptr, 0, 0};
     if (host_push) {
         if (!Y) return WR_E_NULL;
         for (int g = 0; g < host_X->world; ++g) {
@@ -323,6 +413,84 @@ extern "C" int wr_csr_spmm_sharded(const int64_t *rowptr, const int32_t *col, co
         }
     }
     return spmm_launch(p, D, host_plan, (cudaStream_t)stream);
+}
+
+// cuStreamWaitValue32 through the runtime's driver entry point table (the library does not link libcuda).
+typedef int (*wr_wait_value32_fn)(void *stream, unsigned long long addr, uint32_t value, unsigned int flags);
+static wr_wait_value32_fn wait_value32() {
+    static wr_wait_value32_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (wr_wait_value32_fn)sym;
+    }
+    return fn;
+}
+
+extern "C" int wr_csr_spmm_sharded_dma(const int64_t *rowptr, const int32_t *col, const float *val, int64_t n_local, int D,
+                                       const wr_shards *host_X, float *Y, float *add, int zero_add, const float *acc_in,
+                                       float *acc_out, float acc_div, const wr_spmm_plan *host_plan,
+                                       float *const host_push[WR_MAX_WORLD], int32_t *progress, int64_t progress_words,
+                                       int64_t block_rows, uint32_t epoch, int64_t nnz, void *side_stream, void *stream) {
+    if (!host_X || !host_push || !progress || !Y || !side_stream) return WR_E_NULL;
+    int rc = wr_check_shards(host_X);
+    if (rc) return rc;
+    rc = spmm_check(rowptr, col, val, n_local, D, Y, add, acc_in, acc_out);
+    if (rc) return rc;
+    if (!(D == 16 || D == 32 || D == 64 || D == 128 || D == 256)) return WR_E_DIM;
+    if (n_local != host_X->rows_u_local + host_X->rows_i_local) return WR_E_SIZE;
+    if (host_X->base[host_X->rank] == Y || host_X->base[host_X->rank] == acc_out) return WR_E_SIZE;
+    if (block_rows < 32 || (block_rows & (block_rows - 1)) || epoch == 0) return WR_E_SIZE;
+    const int64_t nblk = (n_local + block_rows - 1) / block_rows;
+    if (progress_words < 2 * nblk) return WR_E_SIZE;
+    wr_wait_value32_fn wait = wait_value32();
+    if (!wait) return (int)cudaErrorNotSupported;
+    SpmmParamsT<ShardX> p{rowptr, col, val, n_local, {*host_X}, Y, add, zero_add, acc_in, acc_out, acc_div, {}, 0, 0, 1, host_X->rows_u_local, {}, 0,
+                          progress, (uint32_t *)progress + nblk, 0, epoch};
+    while (((int64_t)1 << p.prog_shift) < block_rows) ++p.prog_shift;
+    cudaStream_t st = (cudaStream_t)stream, sd = (cudaStream_t)side_stream;
+    rc = spmm_launch(p, D, host_plan, st, nnz);
+    if (rc) return rc;
+    const int world = host_X->world, rank = host_X->rank;
+    for (int64_t k = 0; k < nblk; ++k) {
+        // CU_STREAM_WAIT_VALUE_GEQ = 0: (int32_t)(*addr - value) >= 0
+        const int wrc = wait(sd, (unsigned long long)(uintptr_t)(p.prog_flag + k), epoch, 0u);
+        if (wrc) return wrc;
+        const int64_t first = k * block_rows;
+        const size_t bytes = (size_t)(min(block_rows, n_local - first) * D) * sizeof(float);
+        for (int r0 = 1; r0 < world; ++r0) {
+            const int g = (rank + r0) % world;               // peers in a rotated order: links evenly loaded
+            if (!host_push[g]) continue;
+            const cudaError_t e = cudaMemcpyAsync(host_push[g] + first * D, Y + first * D, bytes, cudaMemcpyDefault, sd);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    cudaEvent_t ev;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, sd);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, ev, 0);
+    cudaEventDestroy(ev);
+    return e == cudaSuccess ? WR_OK : (int)e;
+}
+
+// All-gather of one shard by the copy engines: this rank's rows -> every peer's copy (no SM work, ~20 % faster than the
+// pull kernel on 8 B200s).  The caller's barrier after it makes the copies visible to their readers.
+extern "C" int wr_push_shard_dma(const float *src, int64_t n_floats, int world, int rank,
+                                 float *const host_push[WR_MAX_WORLD], void *stream) {
+    if (!src || !host_push) return WR_E_NULL;
+    if (world < 1 || world > WR_MAX_WORLD || rank < 0 || rank >= world || n_floats <= 0) return WR_E_SIZE;
+    for (int r0 = 1; r0 < world; ++r0) {
+        const int g = (rank + r0) % world;
+        if (!host_push[g]) continue;
+        const cudaError_t e = cudaMemcpyAsync(host_push[g], src, (size_t)n_floats * sizeof(float), cudaMemcpyDefault,
+                                              (cudaStream_t)stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return WR_OK;
 }
 
 extern "C" int wr_csr_norm_weights(const int64_t *rowptr, const int32_t *col, const float *dinv, int64_t N,

@@ -10,6 +10,7 @@ themselves, meeting at wr_peer_barrier.
 `ShardedTables` and the step / evaluation drivers need one GPU per rank.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -289,6 +290,12 @@ class ShardedTables(object):
             return
         _lib.adam_l2_sweep(self.P, self.M, self.V, self.G, self.step_count, lr, l2, betas[0], betas[1], eps)
 
+    def settle(self):
+        """Meet the other ranks if the last step left without a closing barrier (the exchange protocol does)."""
+        if getattr(self, '_unsettled', False):
+            self._unsettled = False
+            self.peers.barrier()
+
     def row_map(self):
         """Bitmap over this rank's rows for the row-marked sweep (wr_inbox_scatter_marked sets, the sweep clears)."""
         if getattr(self, '_row_map', None) is None:
@@ -305,6 +312,7 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
     Returns the batch loss (device scalar view, identical on every rank)."""
     if tabs.single_launch:
         # cache-sized shards: one cooperative launch, both cross-GPU meeting points inside the kernel
+        tabs.settle()
         tabs.step_count += 1
         tabs._sync_epoch += 1
         _lib.bprmf_step_sharded(tabs.T, tabs.Gd, tabs.M, tabs.V, user, pos, neg, B_global, tabs.D, tabs.step_count,
@@ -332,8 +340,13 @@ def bprmf_step(tabs, user, pos, neg, B_global, lr, l2):
         loss = tabs.peers.barrier(tabs.loss_part[:1])
         _lib.inbox_scatter(tabs.G, inbox['rows'], inbox['idx'], tabs.layout.world, inbox['cap'], touched)
         tabs.adam(lr, l2, touched=touched)
-        tabs.peers.barrier()
+        # No meeting point after the sweep: in this protocol a rank's rows are only ever read by the rank itself (it
+        # serves them after its own sweep, in stream order), and every buffer a peer writes next -- request lists, receive
+        # blocks, inboxes -- is written behind a barrier of the NEXT step that this rank reaches only after the kernels
+        # above.  Paths that do read peers' rows meet first (settle()).
+        tabs._unsettled = True
         return loss
+    tabs.settle()
     _lib.bpr_fwd_bwd_sharded(tabs.T, tabs.Gd, user, pos, neg, B_global, tabs.D, tabs.loss_part, tabs.ws)
     loss = tabs.peers.barrier(tabs.loss_part[:1])
     tabs.adam(lr, l2)
@@ -367,6 +380,7 @@ class ShardedLightGCN(object):
             torch.zeros(1, dtype=torch.float32, device=dev)
         del rows, src
         self.plan = _lib.SpmmPlan(lptr.cpu().numpy(), tabs.D, dev)
+        self.nnz = total
         self.pool, self.pool_T = tabs.symmetric()
         self.pool_grad, self.pool_Gd = tabs.symmetric()
         self.layer = [tabs.symmetric(), tabs.symmetric()]
@@ -384,6 +398,20 @@ class ShardedLightGCN(object):
                 buf, ptrs = tabs.peers.alloc((lay.world, lay.n_local, tabs.D))
                 self.gathered.append(buf)
                 self.gathered_ptrs.append(ptrs)
+        # all-gathers by the copy engines beside the SpMM (wr_csr_spmm_sharded_dma) where the kernel has the fast row form
+        self.dma = self.gather_first and tabs.D in (16, 32, 64, 128, 256)
+        # layer outputs: pushed by the SpMM's own epilogue stores.  WR_SPMM_PUSH=dma selects the copy-engine push beside the
+        # kernel (wr_csr_spmm_sharded_dma) -- measured slower at 8 GPUs (16.4 vs 14.0 ms per pass, step 99 vs 88 ms,
+        # profiles/r02_prof_sharded_n8_v8_*.json), kept as an option
+        self.dma_spmm = os.environ.get('WR_SPMM_PUSH', 'store') == 'dma'
+        if self.dma:
+            self._block_rows = 32
+            while self._block_rows * 32 < lay.n_local:
+                self._block_rows *= 2
+            nblk = (lay.n_local + self._block_rows - 1) // self._block_rows
+            self._progress = torch.zeros(2 * nblk, dtype=torch.int32, device=dev)
+            self._epoch = 0
+            self._side = torch.cuda.Stream(device=dev)
         self.sparse_grad = None       # None: the batch decides (_step_exchanged); True / False force it
         self._cur = 0                 # which copy holds (or receives by all-gather) the next SpMM's input
         self._pushed = None           # base pointer of the shard whose rows the last SpMM pushed into gathered[_cur]
@@ -405,29 +433,53 @@ class ShardedLightGCN(object):
         return v
 
     def _spmm(self, X, push=False, **kw):
-        """One propagation.  push=True: the output Y is the next SpMM's input -- its rows are stored into every peer's
-        other gathered copy from the epilogue, and that SpMM skips its all-gather."""
+        """One propagation.  push=True: the output Y is the next SpMM's input -- its rows go into every peer's other
+        gathered copy while the kernel runs (copy engines; store-push epilogue where that is not available), and that
+        SpMM skips its all-gather."""
         t = self.tabs
+        lay = t.layout
         push_ptrs = None
         if self.gather_first:
             cur = self._cur
-            if self._pushed != X.base[X.rank]:            # input not delivered by the previous SpMM: pull it
-                _lib.allgather_shards(X, self.gathered[cur], t.D)
+            step = self.gathered[0][0].numel() * 4
+            if self._pushed != X.base[X.rank]:            # input not delivered by the previous SpMM
+                if self.dma:                              # push it (copy engines), then meet
+                    src = self._shard_tensor(X)
+                    _lib.push_shard_dma(src, lay.world, lay.rank,
+                                        [None if g == lay.rank else self.gathered_ptrs[cur][g] + lay.rank * step
+                                         for g in range(lay.world)])
+                    t.peers.barrier()
+                else:                                     # pull it
+                    _lib.allgather_shards(X, self.gathered[cur], t.D)
             X = self._local_view(X, cur)
             self._pushed = None
             if push:
-                step = self.gathered[0][0].numel() * 4
-                push_ptrs = [None if g == t.layout.rank else self.gathered_ptrs[1 - cur][g] + t.layout.rank * step
-                             for g in range(t.layout.world)]
+                push_ptrs = [None if g == lay.rank else self.gathered_ptrs[1 - cur][g] + lay.rank * step
+                             for g in range(lay.world)]
                 self._pushed = kw['Y'].data_ptr()
                 self._cur = 1 - cur
-        _lib.csr_spmm_sharded(self.rowptr, self.col, self.val, t.layout.n_local, t.D, X, plan=self.plan,
-                              push_ptrs=push_ptrs, **kw)
+        if push_ptrs is not None and self.dma and self.dma_spmm:
+            self._epoch += 1
+            _lib.csr_spmm_sharded_dma(self.rowptr, self.col, self.val, lay.n_local, t.D, X, kw.pop('Y'), push_ptrs,
+                                      self._progress, self._block_rows, self._epoch, self._side, nnz=self.nnz,
+                                      plan=self.plan, **kw)
+        else:
+            _lib.csr_spmm_sharded(self.rowptr, self.col, self.val, lay.n_local, t.D, X, plan=self.plan,
+                                  push_ptrs=push_ptrs, **kw)
         t.peers.barrier()          # every rank's rows of the output exist (everywhere) before anyone reads them
+
+    def _shard_tensor(self, X):
+        """The local tensor behind a wr_shards struct of this object (P, the pooled gradient or a layer buffer)."""
+        base = X.base[X.rank]
+        for cand in (self.tabs.P, self.pool_grad, self.pool, self.layer[0][0], self.layer[1][0], self.tabs.G):
+            if cand.data_ptr() == base:
+                return cand
+        raise _lib.WhisprError('unknown shard')
 
     def propagate(self):
         """LightGCN.py:134-148 on row shards: layer k+1 reads its neighbours' layer-k rows from their owners."""
         t, L = self.tabs, self.L
+        t.settle()
         if L == 0:
             self.pool.copy_(t.P)
             t.peers.barrier()
