@@ -168,7 +168,8 @@ def roofline_block(step_bytes, step_avg_s, hbm_peak, peak_src, ep_us_per_step):
            'note': 'one launch per step with a cold L2: a latency chain (ids -> rows -> REDs -> grid barrier -> Adam) on 23 MB, '
                    'of which ~8 us is the launch/event floor (scripts/prof_resident.py); the same arithmetic where HBM is '
                    'the bound: extra.bprmf_10Mx2M_d128_b65536',
-           'resident_epoch': {'kernel': 'bprmf_epoch_kernel<16,1>', 'us_per_step': ep_us_per_step,
+           'resident_epoch': {'kernel': 'bprmf_epoch_owner_kernel<8,2> (one grid barrier per step; WR_EPOCH_KERNEL=two_barrier: '
+                                        'bprmf_epoch_kernel<16,1>)', 'us_per_step': ep_us_per_step,
                               'achieved': step_bytes / (ep_us_per_step * 1e-6) / 1e9,
                               'frac': step_bytes / (ep_us_per_step * 1e-6) / 1e9 / hbm_peak,
                               'note': 'ALGORITHMIC bytes over the per-step time of the one-launch epoch; the tables stay in '

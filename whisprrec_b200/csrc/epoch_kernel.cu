@@ -18,6 +18,7 @@
 // Single steps (wr_bprmf_step) stay on the L2-streamed cooperative kernel of train_kernels.cu: with a cold L2 and one
 // step per launch there is nothing for the shared-memory state to amortise (measured: 18.5 vs 14.3 us, scripts/prof_resident.py).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -69,6 +70,8 @@ struct EpochParams {
     uint64_t idle_ns;
     int64_t *dev_ids;                  // device ring [host_ring][3 * dev_ids_cap]: the helpers' copy of each step's ids
     int64_t dev_ids_cap;
+    // owner-computes form (bprmf_epoch_owner_kernel): rows per CTA, ids per staged step, staged steps
+    int32_t rows_per_cta, bcap, depth;
     uint64_t *trace;                   // profiling (wr_debug_epoch_trace): [step - first_step][8] globaltimer stamps
     uint64_t *cta_trace;               // profiling: [step - first_step][grid][4] arrival / passage of both barriers, every CTA
 };
@@ -116,9 +119,9 @@ __device__ __forceinline__ uint4 ld_relaxed_sys_v4(const void *p) {
 // (nullable) is one more word thread 0 waits for while it spins anyway: *extra >= extra_min.  Returns false when the
 // wait was abandoned (timeout / another CTA gave up).
 __device__ __forceinline__ bool grid_barrier(WrWorkspace *ws, uint32_t value, uint32_t *s_abort, const uint32_t *extra,
-                                             uint32_t extra_min) {
+                                             uint32_t extra_min, bool arrive = true) {
     const int tid = threadIdx.x;
-    if (tid == 0) st_release_gpu(&ws->ep_flag[32 * blockIdx.x], value);
+    if (arrive && tid == 0) st_release_gpu(&ws->ep_flag[32 * blockIdx.x], value);
     if (tid < (int)gridDim.x) {
         const uint32_t *f = &ws->ep_flag[32 * tid];
         uint64_t t0 = 0;
@@ -152,8 +155,16 @@ __device__ __forceinline__ bool all_arrived(const WrWorkspace *ws, uint32_t valu
 }
 
 // ---- the helper warp: stages ids ahead of the workers, reduces the loss of the steps it is on duty for ----
+struct StageHdr {            // owner-computes form: the ids themselves live in dynamic shared memory, [depth][3][bcap] int64
+    int32_t B;
+    float step_size, bc2_sqrt;
+};
+
+template <bool OWNER>
 __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_ready, uint32_t *s_consumed,
-                             uint32_t *s_exit_at, uint32_t *s_abort, int32_t *s_B) {
+                             uint32_t *s_exit_at, uint32_t *s_abort, int32_t *s_B, StageHdr *hdr = nullptr,
+                             int64_t *stage_ids = nullptr) {
+    const uint32_t stage_depth = OWNER ? (uint32_t)p.depth : (uint32_t)EP_STAGE_DEPTH;
     const int lane = threadIdx.x & 31, cta = blockIdx.x, grid = gridDim.x;
     const bool streaming = p.host_desc != nullptr;
     WrWorkspace *ws = p.ws;
@@ -188,7 +199,7 @@ __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_rea
         if (duty < n) {
             const uint32_t rel = duty - p.first_step;
             if (duty_state == 0) {
-                if (all_arrived(ws, 2u * rel + 1u)) {
+                if (all_arrived(ws, OWNER ? rel + 1u : 2u * rel + 1u)) {
                     float t = 0.f;
                     for (int i = lane; i < grid; i += 32) t += __ldcg(&ws->ep_partial[(duty % EP_PD) * WR_EP_MAX_GRID + i]);
                     t = warp_sum(t);
@@ -205,7 +216,7 @@ __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_rea
                 }
             }
             if (duty_state == 1) {      // streaming: the step is complete once every CTA is through its second barrier
-                if (all_arrived(ws, 2u * rel + 2u)) {
+                if (all_arrived(ws, OWNER ? rel + 1u : 2u * rel + 2u)) {
                     if (lane == 0) {
                         // every CTA's P stores were released at gpu scope before its arrival, which this warp has acquired
                         asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.host_done + duty % p.host_ring), "r"(duty + 1u) : "memory");
@@ -223,7 +234,7 @@ __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_rea
         // ---- streaming: copy this helper's piece of step nf's ids out of pinned host memory into the device ring
         //      (16-byte loads, every helper a contiguous 128-byte-aligned piece: a few hundred PCIe reads per step
         //      instead of one per id) ----
-        if (streaming && nf < count && nf - lds_acquire(s_consumed) < (uint32_t)EP_STAGE_DEPTH + 2u) {
+        if (streaming && nf < count && nf - lds_acquire(s_consumed) < stage_depth + 2u) {
             StepDesc d = fresh;
             if (!have_fresh) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(p.desc + nf % p.desc_ring);
@@ -258,7 +269,7 @@ __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_rea
         }
         if (can_stage) {
             const uint32_t cons = lds_acquire(s_consumed);
-            if (n - cons < (uint32_t)EP_STAGE_DEPTH) {
+            if (n - cons < stage_depth) {
                 StepDesc d;
                 {
                     const uint4 *src = reinterpret_cast<const uint4 *>(p.desc + n % p.desc_ring);
@@ -270,7 +281,43 @@ __device__ void epoch_helper(const EpochParams &p, Stage *stage, uint32_t *s_rea
                     d.ids = p.dev_ids + (size_t)(n % p.host_ring) * 3 * p.dev_ids_cap;
                     d.stride = d.B;
                 }
-                const int B = d.B, per = (B + grid - 1) / grid;
+                const int B = d.B;
+                if (OWNER) {
+                    // every id of the step goes into shared memory as it is (8-byte async copies, all in flight at once:
+                    // a converting loop on one warp is a chain of L2 round trips -- measured 13 us per step)
+                    int64_t *su = stage_ids + (size_t)(n % stage_depth) * 3 * p.bcap;
+                    if (streaming) {
+                        // the device ring is rewritten while the kernel runs: L2 only (.cg, 16 bytes), the packed [3 B] block
+                        const int total16 = (3 * B + 1) >> 1;
+                        const uint4 *src = reinterpret_cast<const uint4 *>(d.ids);
+                        uint4 *dst = reinterpret_cast<uint4 *>(su);
+                        for (int k = lane; k < total16; k += 32) cp_async16(dst + k, src + k);
+                    } else {
+                        for (int r = 0; r < 3; ++r) {      // ids that exist before the launch; any 8-byte alignment
+                            const int64_t *src = d.ids + r * d.stride;
+                            int64_t *dst = su + (size_t)r * B;
+                            for (int b = lane; b < B; b += 32)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + b)),
+                                             "l"(src + b) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    if (lane == 0) {
+                        StageHdr &h = hdr[n % stage_depth];
+                        h.B = B;
+                        h.step_size = d.step_size;
+                        h.bc2_sqrt = d.bc2_sqrt;
+                        s_B[n % EP_PD] = B;
+                    }
+                    __syncwarp();
+                    if (lane == 0 && cta == 0) trace_stamp(p, n, 6);
+                    if (lane == 0) sts_release(s_ready, n + 1u);
+                    ++n;
+                    progress = true;
+                    continue;
+                }
+                const int per = (B + grid - 1) / grid;
                 int mine = B - cta * per;
                 mine = mine < 0 ? 0 : (mine > per ? per : mine);
                 Stage &st = stage[n % EP_STAGE_DEPTH];
@@ -398,7 +445,7 @@ __global__ void __maxnreg__(64) bprmf_epoch_kernel(const EpochParams p) {
     if (tid >= EP_THREADS) {
         const bool helper = tid < EP_THREADS + 32;
         if (helper) {
-            epoch_helper(p, stage, &s_ready, &s_consumed, &s_exit_at, &s_abort, s_B);
+            epoch_helper<false>(p, stage, &s_ready, &s_consumed, &s_exit_at, &s_abort, s_B);
             if ((tid & 31) == 0) epoch_depart(p);
         } else if (cta == 0 && p.host_desc) {
             epoch_poller(p);
@@ -564,12 +611,277 @@ __global__ void __maxnreg__(64) bprmf_epoch_kernel(const EpochParams p) {
     if (tid == 0) epoch_depart(p);
 }
 
+// ---- the owner-computes form: ONE grid barrier per step ---------------------------------------------------------------
+// The two-barrier kernel above scatters gradient rows with REDs through L2, so Adam has to wait for every CTA's REDs
+// (barrier 1) and the next step's gathers for every CTA's Adam (barrier 2).  Here the CTA that OWNS a row computes that
+// row's gradient itself: every CTA scans the whole batch (ids staged in shared memory by its helper), keeps the
+// (entry, role) pairs whose row it owns, evaluates those entries -- its own rows come from shared memory, the others
+// from L2 -- and accumulates into a gradient slice that also lives in shared memory.  Nothing is exchanged between the
+// BPR and the Adam phase any more.  What remains is the write-after-read hazard on P (a fast CTA's Adam must not
+// overwrite rows a slow CTA is still gathering for the same step): the published copy of P is double-buffered in global
+// memory -- step k reads buffer k & 1 and writes the other; the second buffer is G, which this kernel does not use
+// otherwise and hands back zeroed -- so the only meeting point of a step is "the new P is complete".
+//   * ownership is cyclic (row r belongs to CTA r % grid, local row r / grid): users, items and hot rows spread evenly;
+//   * each batch entry is evaluated by up to three CTAs (the arithmetic is ~1 % of a step);
+//   * the next step's ownership scan runs between a CTA's arrival at the barrier and its wait (ids and ownership only).
+__device__ __forceinline__ void grid_arrive(WrWorkspace *ws, uint32_t value) {
+    if (threadIdx.x == 0) st_release_gpu(&ws->ep_flag[32 * blockIdx.x], value);
+}
+
+template <int LPR, int VPL>
+__global__ void __maxnreg__(64) bprmf_epoch_owner_kernel(const EpochParams p) {
+    using RG = RowGroup<LPR, VPL>;
+    constexpr int D = RG::D, D4 = D / 4, GROUPS = RG::GROUPS, NG = EP_WARPS * GROUPS;
+    extern __shared__ float4 smem4[];
+    __shared__ StageHdr hdr[EP_STAGE_DEPTH];
+    __shared__ uint32_t s_ready, s_consumed, s_exit_at, s_abort, s_run, s_next_ok;
+    __shared__ uint32_t s_cnt[2];
+    __shared__ int32_t s_B[EP_PD];
+    __shared__ float s_red[EP_WARPS];
+    const int tid = threadIdx.x, cta = blockIdx.x, grid = gridDim.x;
+    WrWorkspace *ws = p.ws;
+    const int n_rows = (int)(p.n_users + p.n_items);
+    const int my_rows = n_rows > cta ? (n_rows - cta + grid - 1) / grid : 0;       // rows cta, cta + grid, ...
+    const int cnt = my_rows * D4;
+    // r / grid for r < 2^24 by one 64-bit multiply (exact: the error term r / 2^40 stays below 1 / grid)
+    const uint64_t magic = ((1ull << 40) + (uint64_t)grid - 1) / (uint64_t)grid;
+    auto local_of = [&](int r, int &q) -> bool {         // does this CTA own row r?  q = its local row
+        q = (int)(((uint64_t)(uint32_t)r * magic) >> 40);
+        return r - q * grid == cta;
+    };
+    float4 *sP = smem4, *sM = sP + p.chunk, *sV = sM + p.chunk, *sG = sV + p.chunk;
+    int64_t *stage_ids = reinterpret_cast<int64_t *>(sG + p.chunk);                 // [depth][3 bcap], a step's [3][B] packed
+    int32_t *lists = reinterpret_cast<int32_t *>(stage_ids + (size_t)p.depth * 3 * p.bcap);   // [2][3 bcap]
+    if (tid == 0) {
+        s_ready = p.first_step;
+        s_consumed = p.first_step;
+        s_exit_at = 0xffffffffu;
+        s_abort = 0;
+        s_run = 0;
+        s_next_ok = 0;
+        s_cnt[0] = 0;
+        s_cnt[1] = 0;
+    }
+    __syncthreads();
+    if (tid >= EP_THREADS) {
+        const bool helper = tid < EP_THREADS + 32;
+        if (helper) {
+            epoch_helper<true>(p, nullptr, &s_ready, &s_consumed, &s_exit_at, &s_abort, s_B, hdr, stage_ids);
+            if ((tid & 31) == 0) epoch_depart(p);
+        } else if (cta == 0 && p.host_desc) {
+            epoch_poller(p);
+            if ((tid & 31) == 0) epoch_depart(p);
+        }
+        return;
+    }
+    // =========================== workers ===========================
+    // global float4 index of element k of the slice: local row k / D4 is global row (k / D4) * grid + cta
+    auto gidx = [&](int k) -> int64_t { return ((int64_t)(k / D4) * grid + cta) * D4 + (k % D4); };
+    for (int k = tid; k < cnt; k += EP_THREADS) {
+        const int64_t g = gidx(k);
+        cp_async16(sP + k, p.P + g);
+        cp_async16(sM + k, p.M + g);
+        cp_async16(sV + k, p.V + g);
+        sG[k] = f4_zero();
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int lane = tid & 31, sub = lane % LPR, grp = lane / LPR, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    float *sGf = reinterpret_cast<float *>(sG);
+    const int n_users = (int)p.n_users;
+
+    // Which (entry, role) pairs of step `step` touch a row this CTA owns -> lists[step & 1], s_cnt[step & 1].
+    // Ids outside their table drop the whole entry (CTA 0 reports them).
+    // Warps [w0, EP_WARPS) take part (the look-ahead scan leaves the first warps to poll the barrier flags meanwhile).
+    auto scan = [&](uint32_t step, int w0) {
+        if (warp < w0) return;
+        const int B = hdr[step % (uint32_t)p.depth].B;
+        const int64_t *su = stage_ids + (size_t)(step % (uint32_t)p.depth) * 3 * p.bcap, *si = su + B, *sj = si + B;
+        int32_t *list = lists + (size_t)(step & 1u) * 3 * p.bcap;
+        uint32_t *count = &s_cnt[step & 1u];
+        // no warp-collective compaction: a lane that finds one of its rows here takes a slot with a shared-memory atomic
+        // (a CTA owns 1 / grid of the rows: ~3 B / grid hits per step, and most warps see none in an iteration)
+#pragma unroll 2
+        for (int b = (warp - w0) * 32 + lane; b < B; b += (EP_WARPS - w0) * 32) {
+            const int64_t u = su[b], i = si[b], j = sj[b];
+            const bool valid = (uint64_t)u < (uint64_t)p.n_users && (uint64_t)i < (uint64_t)p.n_items &&
+                               (uint64_t)j < (uint64_t)p.n_items;
+            if (!valid) {
+                if (cta == 0) atomicOr(&ws->status, WR_STATUS_INDEX_OUT_OF_RANGE);
+                continue;
+            }
+            int q;
+            if (local_of((int)u, q)) list[atomicAdd(count, 1u)] = (b << 2) | 0;
+            if (local_of(n_users + (int)i, q)) list[atomicAdd(count, 1u)] = (b << 2) | 1;
+            if (local_of(n_users + (int)j, q)) list[atomicAdd(count, 1u)] = (b << 2) | 2;
+        }
+    };
+
+    bool loaded = false, aborted = false, scanned = false;
+    uint32_t s = p.first_step;
+    for (;; ++s) {
+        if (tid == 0) {
+            uint32_t run = 1;
+            for (uint32_t spins = 0;; ++spins) {
+                if ((int32_t)(lds_acquire(&s_ready) - (s + 1u)) >= 0) break;
+                if (lds_acquire(&s_exit_at) <= s) { run = 0; break; }
+                if ((spins & 1023u) == 1023u && (ld_acquire_u32(&ws->ep_abort) | *(volatile uint32_t *)&s_abort)) { run = 0; s_abort = 1; break; }
+            }
+            s_run = run;
+        }
+        if (!loaded) asm volatile("cp.async.wait_all;" ::: "memory");
+        workers_sync();
+        loaded = true;
+        if (!*(volatile uint32_t *)&s_run) break;
+        const uint32_t rel = s - p.first_step;
+        if (p.trace && cta == 0 && tid == 0) trace_stamp(p, s, 0);
+        if (p.cta_trace && tid == 0) p.cta_trace[((size_t)rel * grid + cta) * 4 + 0] = global_timer_ns() | (scanned ? 0ull : 1ull);
+        if (!scanned) {              // the previous step could not look ahead (first step / ids not staged in time)
+            scan(s, 0);
+            workers_sync();
+        }
+        const StageHdr h = hdr[s % (uint32_t)p.depth];
+        const int64_t *su = stage_ids + (size_t)(s % (uint32_t)p.depth) * 3 * p.bcap, *si = su + h.B, *sj = si + h.B;
+        const int32_t *list = lists + (size_t)(s & 1u) * 3 * p.bcap;
+        const int L = (int)*(volatile uint32_t *)&s_cnt[s & 1u];
+        const float coef = 1.0f / (float)h.B;
+        AdamScalars sc{p.l2, p.w1, p.beta2, p.w2, p.eps, h.step_size, h.bc2_sqrt};
+        const float inv_bc2 = 1.0f / h.bc2_sqrt;
+        // the published copy of P this step gathers from, and the one its Adam writes
+        const float4 *Rd = (rel & 1u) ? p.G : p.P;
+        float4 *Wr = (rel & 1u) ? p.P : p.G;
+        // ---- BPR forward + backward for those entries; the gradient of OUR row goes into the shared-memory slice ----
+        float local = 0.f;
+        for (int e0 = warp * GROUPS; e0 < L; e0 += NG) {
+            const int e = e0 + grp;
+            const bool ok = e < L;
+            int role = 0, ru = 0, rp = 0, rn = 0;
+            if (ok) {
+                const int ent = list[e];
+                const int b = ent >> 2;
+                role = ent & 3;
+                ru = (int)su[b];
+                rp = n_users + (int)si[b];
+                rn = n_users + (int)sj[b];
+            }
+            float4 ue[VPL], pe[VPL], ne[VPL];
+            int mine_local = 0;
+            if (ok) {
+                int qu, qp, qn;
+                const bool lu = local_of(ru, qu), lp = local_of(rp, qp), ln = local_of(rn, qn);
+                mine_local = role == 0 ? qu : (role == 1 ? qp : qn);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const int o = sub + v * LPR;
+                    ue[v] = lu ? sP[qu * D4 + o] : __ldcg(Rd + (int64_t)ru * D4 + o);
+                    pe[v] = lp ? sP[qp * D4 + o] : __ldcg(Rd + (int64_t)rp * D4 + o);
+                    ne[v] = ln ? sP[qn * D4 + o] : __ldcg(Rd + (int64_t)rn * D4 + o);
+                }
+            } else {
+                RG::zero(ue);
+                RG::zero(pe);
+                RG::zero(ne);
+            }
+            float sp = 0.f, sn = 0.f;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                sp += dot4(ue[v], pe[v]);
+                sn += dot4(ue[v], ne[v]);
+            }
+            sp = group_sum<LPR>(sp);
+            sn = group_sum<LPR>(sn);
+            if (ok) {
+                float l, c;
+                bpr_pointwise(sp, sn, p.gamma, coef, l, c);
+                if (role == 0 && sub == 0) local += l;
+                float *g = sGf + (size_t)mine_local * D;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) {
+                    const float4 x = role == 0 ? scale4(sub4(pe[v], ne[v]), c) : scale4(ue[v], role == 1 ? c : -c);
+                    float *gv = g + 4 * (sub + v * LPR);
+                    atomicAdd(gv + 0, x.x);
+                    atomicAdd(gv + 1, x.y);
+                    atomicAdd(gv + 2, x.z);
+                    atomicAdd(gv + 3, x.w);
+                }
+            }
+        }
+        local = warp_sum(local);
+        if (lane == 0) s_red[warp] = local;
+        workers_sync();
+        if (tid == 0) {
+            if (p.cta_trace) p.cta_trace[((size_t)rel * grid + cta) * 4 + 1] = global_timer_ns();
+            if (p.trace && cta == 0) {
+                trace_stamp(p, s, 1);
+                trace_stamp(p, s, 2);          // (no barrier between the phases: slot 2 = slot 1)
+            }
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < EP_WARPS; ++w) t += s_red[w];
+            __stcg(&ws->ep_partial[(s % EP_PD) * WR_EP_MAX_GRID + cta], t);
+            s_cnt[s & 1u] = 0;
+            sts_release(&s_consumed, s + 1u);          // the ids of this step are no longer needed: the slot may be refilled
+            // can the next step's scan run behind this step's arrival?  (its ids must be staged already)
+            s_next_ok = (int32_t)(lds_acquire(&s_ready) - (s + 2u)) >= 0 ? 1u : 0u;
+        }
+        // ---- Adam + L2 on the slice: everything in shared memory; the new P goes to the OTHER published copy ----
+        const float4 z = f4_zero();
+        for (int k = tid; k < cnt; k += EP_THREADS) {
+            float4 ga = sG[k], pa = sP[k], ma = sM[k], va = sV[k];
+            adam_elem_nr(pa.x, ma.x, va.x, ga.x, sc, inv_bc2);
+            adam_elem_nr(pa.y, ma.y, va.y, ga.y, sc, inv_bc2);
+            adam_elem_nr(pa.z, ma.z, va.z, ga.z, sc, inv_bc2);
+            adam_elem_nr(pa.w, ma.w, va.w, ga.w, sc, inv_bc2);
+            Wr[gidx(k)] = pa;
+            sP[k] = pa;
+            sM[k] = ma;
+            sV[k] = va;
+            sG[k] = z;
+        }
+        workers_sync();
+        if (p.trace && cta == 0 && tid == 0) trace_stamp(p, s, 3);
+        if (p.cta_trace && tid == 0) p.cta_trace[((size_t)rel * grid + cta) * 4 + 2] = global_timer_ns();
+        // ---- the step's only grid barrier: the new copy of P is complete (and the loss partials are out).  The arrival
+        //      is published first; while it travels, the workers already pick the next step's entries.  While thread 0
+        //      spins it also waits for the loss of step s + 1 - EP_PD to have left the partial slot step s + 1 writes.
+        //      (The last step of a launch waits too: the clean-up below rewrites both copies.) ----
+        grid_arrive(ws, rel + 1u);
+        scanned = *(volatile uint32_t *)&s_next_ok != 0;
+        const int poll_warps = (grid + 31) >> 5;        // the threads that watch the other CTAs' flags (grid_barrier)
+        if (scanned) scan(s + 1u, poll_warps <= EP_WARPS - 4 ? poll_warps : 0);
+        const uint32_t nxt = s + 1u;
+        const bool gate = nxt - p.first_step >= (uint32_t)EP_PD;
+        if (!grid_barrier(ws, rel + 1u, &s_abort, gate ? &ws->ep_loss_flag[nxt % EP_PD] : nullptr,
+                          nxt - (uint32_t)EP_PD + 1u, false)) { aborted = true; break; }
+        if (p.trace && cta == 0 && tid == 0) trace_stamp(p, s, 4);
+        if (p.cta_trace && tid == 0) p.cta_trace[((size_t)rel * grid + cta) * 4 + 3] = global_timer_ns();
+    }
+    // ---- leave (every CTA is past the last step's barrier: nobody gathers any more): P, M and V of the slice go back to
+    //      their tables, the slice of G -- the second published copy of P -- goes back to zero ----
+    if (loaded && !aborted) {
+        const float4 z = f4_zero();
+        for (int k = tid; k < cnt; k += EP_THREADS) {
+            const int64_t g = gidx(k);
+            p.P[g] = sP[k];
+            p.M[g] = sM[k];
+            p.V[g] = sV[k];
+            p.G[g] = z;
+        }
+    } else if (!loaded) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    workers_sync();
+    if (tid == 0) epoch_depart(p);
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------
 struct EpochConfig {
     int grid;
     int64_t chunk;
     size_t smem;
     const void *fn;
+    int owner;                 // the one-barrier (owner-computes) kernel
+    int rows_per_cta, bcap, depth;
 };
 
 template <int LPR, int VPL>
@@ -601,9 +913,76 @@ static int epoch_config_for(int64_t n4, EpochConfig *out) {
     return 0;
 }
 
+// The owner-computes kernel: slices are whole rows; shared memory holds P / M / V / G of the slice (64 B per float4), the
+// int32 ids of `depth` staged steps and the CTA's work list (3 bcap entries at worst).
+template <int LPR, int VPL>
+static int epoch_owner_config_for(int64_t n_rows, int D, int64_t max_batch, EpochConfig *out) {
+    static int sms = 0, max_smem = 0, attr_set = 0;
+    const void *fn = (const void *)bprmf_epoch_owner_kernel<LPR, VPL>;
+    if (!sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) { sms = 0; return (int)e; }
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) { sms = 0; return (int)e; }
+        max_smem -= (int)fa.sharedSizeBytes + 1024;
+        if (sms > WR_EP_MAX_GRID) sms = WR_EP_MAX_GRID;
+    }
+    if (max_batch > (1 << 20)) return -1000;
+    out->grid = sms;
+    out->owner = 1;
+    out->rows_per_cta = (int)((n_rows + sms - 1) / sms);
+    out->chunk = (int64_t)out->rows_per_cta * (D / 4);
+    out->bcap = (int)((max_batch + 31) & ~(int64_t)31);
+    out->fn = fn;
+    const int64_t state = out->chunk * 64, per_stage = (int64_t)out->bcap * 24;      // int64 ids [3][bcap]; two int32 lists = one more
+    int depth = EP_STAGE_DEPTH;
+    while (depth >= 2 && state + (depth + 1) * per_stage > (int64_t)max_smem) --depth;
+    if (depth < 2) return -1000;
+    out->depth = depth;
+    out->smem = (size_t)(state + (depth + 1) * per_stage);
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = 1;
+    }
+    return 0;
+}
+
+static int epoch_owner_config(int64_t n_elems, int D, int64_t max_batch, EpochConfig *cfg) {
+    const int64_t n_rows = n_elems / D;
+    switch (D) {     // more float4 per lane than the two-barrier kernel: more entries in flight per CTA
+        case 16: return epoch_owner_config_for<2, 2>(n_rows, D, max_batch, cfg);
+        case 32: return epoch_owner_config_for<4, 2>(n_rows, D, max_batch, cfg);
+        case 64: return epoch_owner_config_for<8, 2>(n_rows, D, max_batch, cfg);
+        case 128: return epoch_owner_config_for<16, 2>(n_rows, D, max_batch, cfg);
+        case 256: return epoch_owner_config_for<32, 2>(n_rows, D, max_batch, cfg);
+        default: return -1000;
+    }
+}
+
+// WR_EPOCH_KERNEL=two_barrier keeps the first resident kernel (profiling / comparison)
+static bool epoch_owner_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WR_EPOCH_KERNEL");
+        v = (e && strcmp(e, "two_barrier") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // 0 = eligible (cfg filled), -1000 = not eligible (use the per-step path), anything else = error
 static int epoch_config(int64_t n_elems, int D, int64_t max_batch, EpochConfig *cfg) {
     if (n_elems & 3) return -1000;
+    memset(cfg, 0, sizeof(*cfg));
+    if (epoch_owner_enabled()) {
+        const int rco = epoch_owner_config(n_elems, D, max_batch, cfg);
+        if (rco != -1000) return rco;
+        memset(cfg, 0, sizeof(*cfg));
+    }
     int rc;
     switch (D) {
         case 16: rc = epoch_config_for<4, 1>(n_elems >> 2, cfg); break;
@@ -632,6 +1011,9 @@ static void epoch_fill(EpochParams &p, const EpochConfig &cfg, float *P, float *
     p.P = (float4 *)P; p.M = (float4 *)M; p.V = (float4 *)V; p.G = (float4 *)G;
     p.n4 = n_elems >> 2;
     p.chunk = cfg.chunk;
+    p.rows_per_cta = cfg.rows_per_cta;
+    p.bcap = cfg.bcap;
+    p.depth = cfg.depth;
     p.n_users = n_users; p.n_items = n_items;
     p.gamma = gamma; p.l2 = l2;
     p.w1 = (float)(1.0 - beta1); p.beta2 = (float)beta2; p.w2 = (float)(1.0 - beta2); p.eps = eps;
@@ -746,6 +1128,7 @@ struct wr_bprmf_ctx {
     int64_t stage_cap;
     int64_t *dev_ids;                  // device [CTX_RING][3 * dev_cap]: where the helper warps put the ids they pull over PCIe
     int64_t dev_cap;
+    int64_t bcap;                      // batch capacity the resident kernel is configured for
     float *dev_loss;                   // large tables: per-step launches, loss by copy
     uint32_t pushed;                   // steps handed over so far
     uint32_t first_live;               // first step the resident kernel (or the next launch) is responsible for
@@ -891,7 +1274,7 @@ extern "C" int wr_bprmf_ctx_sync(wr_bprmf_ctx *c) {
     // close: a descriptor with B = -1 in the slot of the next step
     const uint32_t s = c->pushed;
     EpochConfig cfg;
-    rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, 1, &cfg);
+    rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, c->bcap > 0 ? c->bcap : 1, &cfg);
     if (rc) return rc;
     if (s >= CTX_RING) {
         rc = ctx_wait_word(c, cfg, &c->hr->done[s % CTX_RING], s - CTX_RING);
@@ -927,7 +1310,7 @@ extern "C" int wr_bprmf_ctx_wait(wr_bprmf_ctx *c, int64_t step, int wait, float 
     if (step < 0 || step >= (int64_t)c->pushed || (int64_t)c->pushed - step > (int64_t)CTX_RING || wait < 1 || wait > 2)
         return WR_E_SIZE;
     EpochConfig cfg;
-    int rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, 1, &cfg);
+    int rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, c->bcap > 0 ? c->bcap : 1, &cfg);
     if (rc) return rc == -1000 ? WR_E_SIZE : rc;
     const uint32_t s = (uint32_t)step;
     rc = ctx_wait_word(c, cfg, wait == 2 ? &c->hr->lossq[2 * (s % CTX_RING)] : &c->hr->done[s % CTX_RING], s);
@@ -945,7 +1328,16 @@ extern "C" int wr_bprmf_ctx_step(wr_bprmf_ctx *c, const int64_t *host_ids, int64
     const int64_t n_elems = (c->n_users + c->n_items) * c->D;
     const int D = c->D;
     EpochConfig cfg;
-    int rc = epoch_config(n_elems, D, B, &cfg);
+    // the resident kernel stages whole batches in shared memory: it is launched for the largest batch seen so far (at least
+    // 2,048 rows, in steps of 1,024) and relaunched when a larger one arrives
+    int64_t bcap = c->bcap;
+    if (B > bcap) bcap = B < 2048 ? 2048 : (B + 1023) & ~(int64_t)1023;
+    int rc = epoch_config(n_elems, D, bcap, &cfg);
+    if (rc == 0 && bcap != c->bcap) {
+        rc = wr_bprmf_ctx_sync(c);        // (still configured for the old size: closes the running kernel, if any)
+        if (rc) return rc;
+        c->bcap = bcap;
+    }
     if (rc == -1000) {
         // large tables / batches: per-step launches that read the ids straight from the mapped buffer; the loss comes back by copy
         if (!ctx_ids_are_mapped(c, host_ids)) return WR_E_ALIGN;
