@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch one kernel of interest at the shape its numbers are quoted on, for `ncu --set full` captures.
 
-    python scripts/ncu_targets.py step|epoch|stream|adam_big|eval_tc64|eval_tc128|eval_fp32x|spmm_cfg4|spmm_ml1m
+    python scripts/ncu_targets.py step|epoch|adam_big|adam_marked|eval_tc64|eval_tc128|eval_x64|eval_x128|spmm_cfg4|spmm_cfg4_masked|spmm_ml1m
 
 Each target does a couple of un-profiled warm-up launches of everything it needs and then the launches to capture
 (the ncu command line selects them with -k / -s / -c; see profiles/README.md).
@@ -49,6 +49,17 @@ elif what == 'adam_big':
     for k in range(3):
         _lib.bpr_fwd_bwd(P[:nU], P[nU:], u, p, n, G[:nU], G[nU:], loss, ws)
         _lib.adam_l2_sweep(P, M, V, G, k + 1, 1e-3, 1e-6)
+elif what == 'adam_marked':       # the row-marked step on tables far beyond L2 (wr_bprmf_step_marked)
+    nU, nI, d, b = 10_000_000, 2_000_000, 128, 65536
+    P = torch.empty((nU + nI, d), device=dev).normal_(0, 0.01)
+    M, V, G = torch.zeros_like(P), torch.zeros_like(P), torch.zeros_like(P)
+    loss = torch.zeros(1, device=dev)
+    touched = _lib.row_map(nU + nI, dev)
+    u = torch.randint(0, nU, (b,), device=dev)
+    p = torch.randint(0, nI, (b,), device=dev)
+    n = torch.randint(1, nI, (b,), device=dev)
+    for k in range(3):
+        _lib.bprmf_step(P, M, V, G, u, p, n, nU, k + 1, 1e-3, 1e-6, loss, ws, touched=touched)
 elif what.startswith('eval_'):
     d = 128 if what.endswith('128') else 64
     nUs, nIs, Rs = 200_000, 1_000_000, 262_144
@@ -61,22 +72,40 @@ elif what.startswith('eval_'):
     hi_ = torch.sort(torch.randint(0, nIs, (nUs, 50), device=dev, generator=g), dim=1).values.to(torch.int32).reshape(-1).contiguous()
     for k in range(2):
         _lib.eval_rank_topk(Ub, Ib, us, ps, hp_, hi_, ws, precision=precision)
-elif what in ('spmm_cfg4', 'spmm_ml1m'):
+elif what in ('spmm_cfg4', 'spmm_ml1m', 'spmm_cfg4_masked'):
     from whisprrec_b200.models.general.LightGCN import build_norm_adj_device
     from whisprrec_b200.utils import synthetic
-    if what == 'spmm_cfg4':
+    if what in ('spmm_cfg4', 'spmm_cfg4_masked'):
         U, I, E, D = 10_000_000, 2_000_000, 500_000_000, 128
     else:
         U, I, E, D = 6040, 3706, 669_000, 64
     users, items = synthetic.power_law_pairs(U, I, E, device=dev)
     rowptr, col, val, dinv = build_norm_adj_device(U, I, users, items, ws)
+    users_n = users.numel()
+    if what == 'spmm_cfg4_masked':
+        users_keep, items_keep = users[:4_000_000].clone(), items[:4_000_000].clone()
+        users_n = 4_000_000
     del users, items
     torch.cuda.empty_cache()
     X = torch.randn((U + I, D), device=dev, generator=g) * 0.1
     Y, pool = torch.empty_like(X), torch.empty_like(X)
     plan = _lib.SpmmPlan(rowptr.cpu().numpy(), D, dev)
-    for k in range(2):
-        _lib.csr_spmm(rowptr, col, val, X, Y=Y, acc_in=X, acc_out=pool, plan=plan)
+    if what == 'spmm_cfg4_masked':     # the first adjoint pass: X = pooled gradient of a 65,536-row batch, unmarked rows skipped
+        b = 65536
+        sel = torch.randint(0, users_n, (b,), device=dev, generator=g)
+        bu, bp = users_keep[sel].contiguous(), items_keep[sel].contiguous()
+        bn = torch.randint(1, I, (b,), device=dev, generator=g)
+        x_rows = _lib.row_map(U + I, dev)
+        _lib.mark_rows(bu, bp, bn, U, I, x_rows)
+        X.zero_()
+        X[bu] = 0.01
+        X[U + bp] = 0.01
+        X[U + bn] = -0.01
+        for k in range(2):
+            _lib.csr_spmm(rowptr, col, val, X, Y=Y, add=pool, plan=plan, x_rows=x_rows)
+    else:
+        for k in range(2):
+            _lib.csr_spmm(rowptr, col, val, X, Y=Y, acc_in=X, acc_out=pool, plan=plan)
 else:
     raise SystemExit('unknown target ' + what)
 torch.cuda.synchronize()

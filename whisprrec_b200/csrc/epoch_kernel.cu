@@ -975,10 +975,25 @@ static bool epoch_owner_enabled() {
 }
 
 // 0 = eligible (cfg filled), -1000 = not eligible (use the per-step path), anything else = error
-static int epoch_config(int64_t n_elems, int D, int64_t max_batch, EpochConfig *cfg) {
+// WR_CTX_KERNEL=owner puts the host-fed context on the one-barrier kernel too (its streaming path is complete and passes the
+// same tests; see epoch_config for why it is not the default there)
+static bool ctx_owner_ok() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WR_CTX_KERNEL");
+        v = (e && strcmp(e, "owner") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// owner_ok: the one-barrier kernel may be chosen.  The host-fed context keeps the two-barrier kernel: with the host waiting
+// for every step, what counts is the latency of ONE step from descriptor to completion word, and there the owner form
+// loses ~2.7 us (every CTA stages and scans the whole batch before it can start; measured e2e 25.6 -> 28.3 us per step),
+// while it wins where steps run back to back (6.4 -> 5.6 us per step).
+static int epoch_config(int64_t n_elems, int D, int64_t max_batch, EpochConfig *cfg, bool owner_ok = true) {
     if (n_elems & 3) return -1000;
     memset(cfg, 0, sizeof(*cfg));
-    if (epoch_owner_enabled()) {
+    if (owner_ok && epoch_owner_enabled()) {
         const int rco = epoch_owner_config(n_elems, D, max_batch, cfg);
         if (rco != -1000) return rco;
         memset(cfg, 0, sizeof(*cfg));
@@ -1274,7 +1289,7 @@ extern "C" int wr_bprmf_ctx_sync(wr_bprmf_ctx *c) {
     // close: a descriptor with B = -1 in the slot of the next step
     const uint32_t s = c->pushed;
     EpochConfig cfg;
-    rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, c->bcap > 0 ? c->bcap : 1, &cfg);
+    rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, c->bcap > 0 ? c->bcap : 1, &cfg, ctx_owner_ok());
     if (rc) return rc;
     if (s >= CTX_RING) {
         rc = ctx_wait_word(c, cfg, &c->hr->done[s % CTX_RING], s - CTX_RING);
@@ -1310,7 +1325,7 @@ extern "C" int wr_bprmf_ctx_wait(wr_bprmf_ctx *c, int64_t step, int wait, float 
     if (step < 0 || step >= (int64_t)c->pushed || (int64_t)c->pushed - step > (int64_t)CTX_RING || wait < 1 || wait > 2)
         return WR_E_SIZE;
     EpochConfig cfg;
-    int rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, c->bcap > 0 ? c->bcap : 1, &cfg);
+    int rc = epoch_config((c->n_users + c->n_items) * c->D, c->D, c->bcap > 0 ? c->bcap : 1, &cfg, ctx_owner_ok());
     if (rc) return rc == -1000 ? WR_E_SIZE : rc;
     const uint32_t s = (uint32_t)step;
     rc = ctx_wait_word(c, cfg, wait == 2 ? &c->hr->lossq[2 * (s % CTX_RING)] : &c->hr->done[s % CTX_RING], s);
@@ -1332,7 +1347,7 @@ extern "C" int wr_bprmf_ctx_step(wr_bprmf_ctx *c, const int64_t *host_ids, int64
     // 2,048 rows, in steps of 1,024) and relaunched when a larger one arrives
     int64_t bcap = c->bcap;
     if (B > bcap) bcap = B < 2048 ? 2048 : (B + 1023) & ~(int64_t)1023;
-    int rc = epoch_config(n_elems, D, bcap, &cfg);
+    int rc = epoch_config(n_elems, D, bcap, &cfg, ctx_owner_ok());
     if (rc == 0 && bcap != c->bcap) {
         rc = wr_bprmf_ctx_sync(c);        // (still configured for the old size: closes the running kernel, if any)
         if (rc) return rc;
