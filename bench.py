@@ -605,15 +605,16 @@ def extras_sharded(peers, dev, hbm_peak, flush):
         step = lambda: S.bprmf_step(tabs, u, p, n, b * world, LR, L2)
         step()
         ms = timed_max(step, 5)
-        step_bytes = algorithmic_bytes_adam(lay.n_local, d) + algorithmic_bytes_bpr(b, d)
+        # the row-marked sweep moves 24 B per parameter (G is read and re-zeroed only in the rows that received a gradient)
+        step_bytes = algorithmic_bytes_adam(lay.n_local, d) * 3 // 4 + algorithmic_bytes_bpr(b, d)
         out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {
             'ms_per_step': ms, 'interactions_per_s': b * world / (ms * 1e-3), 'rows_per_gpu': lay.n_local,
             'algorithmic_gbs_per_gpu': step_bytes / (ms * 1e-3) / 1e9,
             'frac_of_hbm_peak': step_bytes / (ms * 1e-3) / 1e9 / hbm_peak,
             'note': 'total table fixed (24.6 GB of state over all GPUs), batch 65536 per GPU; row exchange (request lists to '
                     'the owners, owners store the rows into the requesters\' buffers, batch kernel on local memory, gradient '
-                    'rows into the owners\' inboxes: posted NVLink stores only), local inbox reduction, local Adam sweep; '
-                    '4 cross-GPU barriers per step'}
+                    'rows into the owners\' inboxes: posted NVLink stores only), local inbox reduction, row-marked local Adam '
+                    'sweep (24 B per parameter); 3 cross-GPU barriers per step'}
         del tabs
     except Exception as e:  # noqa: BLE001
         out['bprmf_10Mx2M_d128_b65536_per_gpu_sharded'] = {'error': repr(e)}

@@ -624,6 +624,27 @@ __global__ void __maxnreg__(64) bprmf_epoch_kernel(const EpochParams p) {
 //   * ownership is cyclic (row r belongs to CTA r % grid, local row r / grid): users, items and hot rows spread evenly;
 //   * each batch entry is evaluated by up to three CTAs (the arithmetic is ~1 % of a step);
 //   * the next step's ownership scan runs between a CTA's arrival at the barrier and its wait (ids and ownership only).
+// x added into a float4 in shared memory.  There is no native fp32 add on shared memory (atomicAdd(float) compiles to one
+// compare-and-swap loop per float); one 128-bit CAS covers the whole float4.
+__device__ __forceinline__ void smem_add_f4(float4 *addr, float4 x) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(addr);
+    float4 old = *addr;
+    for (;;) {
+        const float4 neu = make_float4(old.x + x.x, old.y + x.y, old.z + x.z, old.w + x.w);
+        unsigned __int128 cmp, val, got;
+        cmp = ((unsigned __int128)__float_as_uint(old.w) << 96) | ((unsigned __int128)__float_as_uint(old.z) << 64) |
+              ((unsigned __int128)__float_as_uint(old.y) << 32) | (unsigned __int128)__float_as_uint(old.x);
+        val = ((unsigned __int128)__float_as_uint(neu.w) << 96) | ((unsigned __int128)__float_as_uint(neu.z) << 64) |
+              ((unsigned __int128)__float_as_uint(neu.y) << 32) | (unsigned __int128)__float_as_uint(neu.x);
+        asm volatile("atom.shared.cas.b128 %0, [%1], %2, %3;" : "=q"(got) : "r"(a), "q"(cmp), "q"(val) : "memory");
+        if (got == cmp) break;
+        old.x = __uint_as_float((uint32_t)got);
+        old.y = __uint_as_float((uint32_t)(got >> 32));
+        old.z = __uint_as_float((uint32_t)(got >> 64));
+        old.w = __uint_as_float((uint32_t)(got >> 96));
+    }
+}
+
 __device__ __forceinline__ void grid_arrive(WrWorkspace *ws, uint32_t value) {
     if (threadIdx.x == 0) st_release_gpu(&ws->ep_flag[32 * blockIdx.x], value);
 }
@@ -720,19 +741,21 @@ __global__ void __maxnreg__(64) bprmf_epoch_owner_kernel(const EpochParams p) {
     bool loaded = false, aborted = false, scanned = false;
     uint32_t s = p.first_step;
     for (;; ++s) {
-        if (tid == 0) {
-            uint32_t run = 1;
-            for (uint32_t spins = 0;; ++spins) {
-                if ((int32_t)(lds_acquire(&s_ready) - (s + 1u)) >= 0) break;
-                if (lds_acquire(&s_exit_at) <= s) { run = 0; break; }
-                if ((spins & 1023u) == 1023u && (ld_acquire_u32(&ws->ep_abort) | *(volatile uint32_t *)&s_abort)) { run = 0; s_abort = 1; break; }
+        if (!scanned) {      // (a step that was scanned ahead is known to be staged: straight on from the barrier)
+            if (tid == 0) {
+                uint32_t run = 1;
+                for (uint32_t spins = 0;; ++spins) {
+                    if ((int32_t)(lds_acquire(&s_ready) - (s + 1u)) >= 0) break;
+                    if (lds_acquire(&s_exit_at) <= s) { run = 0; break; }
+                    if ((spins & 1023u) == 1023u && (ld_acquire_u32(&ws->ep_abort) | *(volatile uint32_t *)&s_abort)) { run = 0; s_abort = 1; break; }
+                }
+                s_run = run;
             }
-            s_run = run;
+            if (!loaded) asm volatile("cp.async.wait_all;" ::: "memory");
+            workers_sync();
+            loaded = true;
+            if (!*(volatile uint32_t *)&s_run) break;
         }
-        if (!loaded) asm volatile("cp.async.wait_all;" ::: "memory");
-        workers_sync();
-        loaded = true;
-        if (!*(volatile uint32_t *)&s_run) break;
         const uint32_t rel = s - p.first_step;
         if (p.trace && cta == 0 && tid == 0) trace_stamp(p, s, 0);
         if (p.cta_trace && tid == 0) p.cta_trace[((size_t)rel * grid + cta) * 4 + 0] = global_timer_ns() | (scanned ? 0ull : 1ull);
@@ -798,11 +821,7 @@ __global__ void __maxnreg__(64) bprmf_epoch_owner_kernel(const EpochParams p) {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) {
                     const float4 x = role == 0 ? scale4(sub4(pe[v], ne[v]), c) : scale4(ue[v], role == 1 ? c : -c);
-                    float *gv = g + 4 * (sub + v * LPR);
-                    atomicAdd(gv + 0, x.x);
-                    atomicAdd(gv + 1, x.y);
-                    atomicAdd(gv + 2, x.z);
-                    atomicAdd(gv + 3, x.w);
+                    smem_add_f4(reinterpret_cast<float4 *>(g + 4 * (sub + v * LPR)), x);
                 }
             }
         }
