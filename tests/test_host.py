@@ -74,8 +74,23 @@ def test_argument_errors_need_no_gpu():
     assert lib.wr_topk_merge(16, 16, 2, 10, 33, 16, 16, None) == -4
     assert lib.wr_peer_barrier(None, 2, 0, 1, None, None, 0, None, None, None) == -1
     assert lib.wr_bprmf_step_sharded_supported(4873, 64) == 1 and lib.wr_bprmf_step_sharded_supported(6_000_000, 128) == 0
+    # the sparse-gradient entry points (row map) and the copy-engine pushes
+    assert lib.wr_mark_rows(16, 16, 16, 8, 10, 7, None, None) == -1
+    assert lib.wr_mark_rows(16, 16, 16, 0, 10, 7, 16, None) == -2
+    assert lib.wr_adam_l2_sweep_marked(16, 16, 16, 16, 100, 64, None, 0.0, 0.9, 0.999, 1e-8, 1e-3, 1.0, None, None) == -1
+    assert lib.wr_adam_l2_sweep_marked(16, 16, 16, 16, 100, 6, 16, 0.0, 0.9, 0.999, 1e-8, 1e-3, 1.0, None, None) == -3
+    assert lib.wr_adam_l2_sweep_marked(16, 16, 16, 20, 100, 64, 16, 0.0, 0.9, 0.999, 1e-8, 1e-3, 1.0, None, None) == -5
+    assert lib.wr_inbox_scatter_marked(None, 16, 16, 2, 100, 64, 16, None) == -1
+    assert lib.wr_bprmf_step_marked(16, 16, 16, 16, None, 16, 16, 16, 8, 64, 10, 7, 1e-10, 0.0, 0.9, 0.999, 1e-8, 1e-3, 1.0,
+                                    None, 16, 16, None) == -1
+    assert lib.wr_push_shard_dma(None, 100, 2, 0, 16, None) == -1
+    assert lib.wr_push_shard_dma(16, 100, 9, 0, 16, None) == -2
+    assert lib.wr_push_marked_rows(None, 64, 16, 16, None) == -1
     shards = _lib.ShardsStruct()
     shards.world, shards.rank, shards.n_users, shards.n_items, shards.rows_u_local, shards.rows_i_local = 2, 0, 10, 7, 5, 4
+    assert lib.wr_push_marked_rows(ctypes.addressof(shards), 64, 16, 16, None) == -1                     # bases not mapped
+    assert lib.wr_csr_spmm_sharded_dma(16, 16, 16, 9, 64, None, 16, None, 0, None, None, 1.0, None, 16, 16, 64, 32, 1, 0, 16,
+                                       None) == -1
     assert lib.wr_gather_rows_sharded(ctypes.addressof(shards), 0, 16, 4, 64, 16, 16, None) == -1        # bases not mapped
     shards.rows_u_local = 6
     assert lib.wr_gather_rows_sharded(ctypes.addressof(shards), 0, 16, 4, 64, 16, 16, None) == -2        # layout mismatch
