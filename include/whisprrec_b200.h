@@ -497,8 +497,10 @@ int wr_embloss_owner_scatter(const float *T_local, float *G_local, int D, int wo
  * (2) the last CTA to finish the Adam phase tells every peer that this rank's rows are final, and the next step's
  * kernel waits for that before its first remote gather.  T / Gd: parameter and gradient shards; M / V: this rank's
  * moment shards; epoch: the step number 1, 2, 3, ... (same on every rank, each used once);
- * host_flags[g]: rank g's zero-initialised array of 2 * WR_MAX_WORLD uint32; host_slots[g]: rank g's array of
- * 2 * WR_MAX_WORLD floats.  loss_out[0] = the loss of the GLOBAL batch (identical on every rank).
+ * host_flags[g]: rank g's zero-initialised array of 2 * WR_MAX_WORLD uint32 ([1][r]: rank r's rows are final);
+ * host_slots[g]: rank g's zero-initialised, 8-byte aligned array of 2 * WR_MAX_WORLD floats, used as WR_MAX_WORLD 8-byte
+ * words: word [r] = {epoch, rank r's loss share} -- arrival and payload in one store, so no fence (an NVLink round trip)
+ * sits between them.  loss_out[0] = the loss of the GLOBAL batch (identical on every rank).
  * Supported when wr_bprmf_step_sharded_supported(rows of a shard, D) (cache-sized shards, D in {16,...,256});
  * otherwise use wr_bpr_fwd_bwd_sharded / wr_peer_barrier / wr_adam_l2_sweep / wr_peer_barrier.
  */

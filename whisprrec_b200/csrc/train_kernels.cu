@@ -540,28 +540,39 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
             loss_sum = warp_sum(t) / p.loss_div;
         }
         if (sy.world > 1) {
-            const int half = (int)(sy.epoch & 1u) * WR_MAX_WORLD;
+            // Arrival and loss share travel as ONE 8-byte word {epoch, loss bits} per peer (slots[g] read as uint64[world]):
+            // no fence between a payload and its flag (a fence.sys behind a remote store is an NVLink round trip).  The
+            // word is a release: every local CTA fenced its REDs at system scope before the ticket this thread acquired.
+            // One slot per sender suffices: a peer writes epoch e + 1 only after it has seen this rank's rows-final flag
+            // of epoch e, which is published after the losses of epoch e were read.
+            loss_sum = __shfl_sync(0xffffffffu, loss_sum, 0);
             if (threadIdx.x < sy.world) {
                 const int g = threadIdx.x;
-                asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(sy.slots[g] + half + sy.rank), "f"(loss_sum) : "memory");
                 __threadfence_system();
-                st_release_sys(sy.flags[g] + sy.rank, sy.epoch);
+                unsigned long long *dst = reinterpret_cast<unsigned long long *>(sy.slots[g]) + sy.rank;
+                const unsigned long long word = ((unsigned long long)__float_as_uint(loss_sum) << 32) | sy.epoch;
+                asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
+                const unsigned long long *src = reinterpret_cast<const unsigned long long *>(sy.slots[sy.rank]) + g;
                 const uint64_t t0 = global_timer_ns();
-                while ((int32_t)(ld_acquire_sys(sy.flags[sy.rank] + g) - sy.epoch) < 0) {
+                float got = 0.f;
+                for (;;) {
+                    unsigned long long w;
+                    asm volatile("ld.acquire.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                    if ((int32_t)((uint32_t)w - sy.epoch) >= 0) {
+                        got = __uint_as_float((uint32_t)(w >> 32));
+                        break;
+                    }
                     if (global_timer_ns() - t0 > WR_PEER_TIMEOUT_NS) {      // the peer is gone: do not hang the GPU
                         atomicOr(&p.ws->status, WR_STATUS_PEER_TIMEOUT);
                         break;
                     }
                 }
+                red[threadIdx.x] = got;          // (`red` is free again: block_sum finished before the barrier above)
             }
             __syncthreads();
             if (threadIdx.x == 0) {
                 float t = 0.f;
-                for (int g = 0; g < sy.world; ++g) {
-                    float v;
-                    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(sy.slots[sy.rank] + half + g) : "memory");
-                    t += v;
-                }
+                for (int g = 0; g < sy.world; ++g) t += red[g];      // rank order: the same sum on every rank
                 loss_sum = t;
                 __threadfence();
                 st_release_gpu(&p.ws->ticket[5], sy.epoch);     // the gate: every rank's gradients have landed
@@ -630,8 +641,12 @@ __global__ void __launch_bounds__(256, 4) bprmf_step_kernel(BprParamsT<TABS> p, 
             p.ws->ticket[3] = 0;
             p.ws->ticket[4] = 0;
             if (sy.world > 1) {                 // this rank's rows of P are final: peers may gather them for step e+1
+                // ONE fence, then relaxed stores that travel side by side (a release store per peer waits for the
+                // previous peer's acknowledgement: world - 1 serialised NVLink round trips on the next step's critical path)
                 __threadfence_system();
-                for (int g = 0; g < sy.world; ++g) st_release_sys(sy.flags[g] + WR_MAX_WORLD + sy.rank, sy.epoch);
+                for (int g = 0; g < sy.world; ++g)
+                    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sy.flags[g] + WR_MAX_WORLD + sy.rank), "r"(sy.epoch)
+                                 : "memory");
             }
         }
     }
