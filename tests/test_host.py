@@ -96,6 +96,15 @@ def test_argument_errors_need_no_gpu():
     assert lib.wr_gather_rows_sharded(ctypes.addressof(shards), 0, 16, 4, 64, 16, 16, None) == -2        # layout mismatch
 
 
+def test_unsupported_embedding_size_is_refused_at_construction():
+    """Sizes the evaluation kernels do not cover fail when the model is built, not after the first epoch."""
+    corpus = ml100k_corpus()
+    for cls in (BPRMF, LightGCN):
+        with pytest.raises(ValueError, match='embedding_size'):
+            cls(model_args(cls, embedding_size=96), corpus)
+    assert BPRMF(model_args(BPRMF, embedding_size=128), corpus).emb_size == 128
+
+
 def test_product_refuses_cpu_tensors():
     with pytest.raises(_lib.WhisprError):
         _lib.ptr(torch.zeros(4))

@@ -549,13 +549,19 @@ def _eval_rank_topk(Uemb, Iemb, user, pos, hist_ptr, hist_idx, ws, k, precision,
     return rank, target, tki, tkv, sc
 
 
+METRIC_CUTOFFS_PER_CALL = 8       # wr_metrics takes up to 8 cut-offs per launch
+EVAL_DIMS = (16, 32, 64, 128)     # embedding sizes the full-ranking evaluation kernels are instantiated for
+
+
 def metrics(rank, ks, ws):
-    """float64 tensor [2, len(ks)]: row 0 = HR@k, row 1 = NDCG@k."""
+    """float64 tensor [2, len(ks)]: row 0 = HR@k, row 1 = NDCG@k (any number of cut-offs: 8 per launch)."""
     nk = len(ks)
-    out = torch.empty((2, nk), dtype=torch.float64, device=rank.device)
-    arr = (ctypes.c_int * nk)(*[int(k) for k in ks])
-    check(load().wr_metrics(ptr(rank, I32), rank.numel(), arr, nk, out.data_ptr(), ws.ptr, stream_ptr()))
-    return out
+    if nk <= METRIC_CUTOFFS_PER_CALL:
+        out = torch.empty((2, nk), dtype=torch.float64, device=rank.device)
+        arr = (ctypes.c_int * nk)(*[int(k) for k in ks])
+        check(load().wr_metrics(ptr(rank, I32), rank.numel(), arr, nk, out.data_ptr(), ws.ptr, stream_ptr()))
+        return out
+    return torch.cat([metrics(rank, ks[c:c + METRIC_CUTOFFS_PER_CALL], ws) for c in range(0, nk, METRIC_CUTOFFS_PER_CALL)], dim=1)
 
 
 def gather_rows(T, idx, ws, out=None):

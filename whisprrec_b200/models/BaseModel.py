@@ -186,6 +186,12 @@ class GeneralModel(BaseModel):
         self.num_neg = args.num_neg
         self.test_all = args.test_all
         self.tables = None
+        # The reference takes any embedding size; here training runs any multiple of 4 but the full-ranking evaluation
+        # kernels exist for a few sizes only.  Say so now, not at the first dev evaluation after an epoch of training.
+        emb = getattr(args, 'embedding_size', None)
+        if emb is not None and int(emb) not in _lib.EVAL_DIMS:
+            raise ValueError('--embedding_size %s: the evaluation kernels of whisprrec_b200 support %s'
+                             % (emb, ', '.join(str(d) for d in _lib.EVAL_DIMS)))
 
     # ---- fused parameter tables ----------------------------------------------------------------------
     def _embedding_pair(self):
