@@ -6,7 +6,9 @@ cap() {  # name regex skip count
   echo "$1 rc=$?"; tail -2 gpurun_out/ncu_$1.log
 }
 cap step bprmf_step_kernel 3 2
+export WR_EPOCH_KERNEL=two_barrier      # the first resident kernel (scripts/_ncu2.sh captures the owner-computes one)
 cap epoch bprmf_epoch_kernel 1 1
+unset WR_EPOCH_KERNEL
 cap adam_big 'adam_sweep_kernel|bpr_fwd_bwd_kernel' 2 2
 cap eval_tc64 eval_tc_rank_kernel 1 1
 cap eval_tc128 eval_tc_rank_kernel 1 1
